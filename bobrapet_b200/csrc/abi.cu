@@ -1,0 +1,609 @@
+// abi.cu — the C ABI of include/bobrafrontier.h: context, topology arena, batch evaluation.
+//
+// Host side of the boundary.  Packs Story topologies into the device record format
+// (device_record.h), validates what validateRuntimeDependencyGraph validates
+// (internal/controller/runs/dag.go:3076-3146), plans shared memory for the frontier
+// kernel and drives H2D -> kernels -> D2H for the host-buffer entry point.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/bobrafrontier.h"
+#include "device_record.h"
+
+namespace bf {
+cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, unsigned long long* offsets,
+                             bf_expansion* out, unsigned long long cap, cudaStream_t stream, uint32_t* launches);
+int frontier_max_blocks_per_sm(uint32_t threads, uint32_t smem_bytes);
+}  // namespace bf
+
+namespace {
+
+inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+inline size_t round_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct TopoMeta {
+  bool alive = false;
+  uint32_t S = 0, E = 0, P = 0, bytes = 0;
+  size_t offset = 0;  // in arena
+  std::vector<uint32_t> child_first;
+  uint32_t child_nibbles = 0;
+};
+
+}  // namespace
+
+struct bf_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::string err;
+
+  uint8_t* arena = nullptr;
+  size_t arena_cap = 0, arena_used = 0;
+  std::vector<TopoMeta> meta;
+  std::vector<uint32_t> free_slots;
+  std::vector<bf::Slot> slots_host;
+  bf::Slot* slots_dev = nullptr;
+  size_t slots_dev_cap = 0;
+  bool slots_dirty = true;
+  uint32_t max_rec_bytes = 0;
+  uint32_t n_alive = 0;
+
+  // host-API staging
+  uint8_t* d_state = nullptr; size_t d_state_cap = 0;
+  uint8_t* d_result = nullptr; size_t d_result_cap = 0;
+  unsigned long long* d_counts = nullptr;
+  bf_expansion* d_exp = nullptr; size_t d_exp_cap = 0;
+  // scratch shared by both entry points
+  uint32_t* d_exp_counts = nullptr; size_t d_exp_counts_cap = 0;
+  unsigned long long* d_offsets = nullptr; size_t d_offsets_cap = 0;
+  unsigned long long* d_block_sums = nullptr; size_t d_block_sums_cap = 0;
+
+  bf_stats stats{};
+};
+
+namespace {
+
+int fail(bf_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+int cuda_fail(bf_ctx* c, cudaError_t e, const char* what) {
+  return fail(c, BF_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define BF_CUDA(c, call)                                   \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) return cuda_fail(c, e__, #call); \
+  } while (0)
+
+template <typename T>
+int ensure_dev(bf_ctx* c, T*& p, size_t& cap, size_t need_elems) {
+  if (need_elems <= cap) return BF_OK;
+  size_t ncap = cap ? cap : 1;
+  while (ncap < need_elems) ncap *= 2;
+  T* np = nullptr;
+  cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+  if (e != cudaSuccess) return fail(c, BF_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  if (p) cudaFree(p);
+  p = np;
+  cap = ncap;
+  return BF_OK;
+}
+
+// ---- record building -----------------------------------------------------------------------
+struct RecPlan {
+  uint32_t off_col, off_planes, off_par, off_allow, rec_bytes, W, child_nibbles;
+  std::vector<uint32_t> child_first, allow_off;
+};
+
+int plan_record(const bf_topology& t, RecPlan& p, std::string& why) {
+  if (t.n_steps == 0 || t.n_steps > BF_MAX_STEPS) { why = "n_steps out of range (1..1024)"; return BF_ETOPO; }
+  if (t.n_edges > BF_MAX_EDGES) { why = "n_edges exceeds 65535"; return BF_ETOPO; }
+  if (!t.row_ptr || !t.step_flags || (t.n_edges && !t.col_idx)) { why = "null topology array"; return BF_EINVAL; }
+  if (t.n_parallel > BF_MAX_PARALLEL) { why = "more than 64 parallel steps"; return BF_ETOPO; }
+  if (t.n_parallel && !t.parallel) { why = "null parallel descs"; return BF_EINVAL; }
+  const uint32_t S = t.n_steps, E = t.n_edges;
+  if (t.row_ptr[0] != 0 || t.row_ptr[S] != E) { why = "row_ptr[0] != 0 or row_ptr[S] != E"; return BF_ETOPO; }
+  for (uint32_t i = 0; i < S; ++i)
+    if (t.row_ptr[i + 1] < t.row_ptr[i]) { why = "row_ptr not monotone"; return BF_ETOPO; }
+  for (uint32_t e = 0; e < E; ++e)
+    if (t.col_idx[e] >= S) { why = "unknown step dependency (col_idx >= S)"; return BF_ETOPO; }  // dag.go:3087-3098
+  // acyclicity (Kahn), dag.go:3100-3145.  indegree[i] = number of deps of i.
+  {
+    std::vector<uint32_t> indeg(S), head(S + 1, 0), out(E), stack;
+    for (uint32_t i = 0; i < S; ++i) indeg[i] = t.row_ptr[i + 1] - t.row_ptr[i];
+    for (uint32_t e = 0; e < E; ++e) head[t.col_idx[e] + 1]++;
+    for (uint32_t i = 0; i < S; ++i) head[i + 1] += head[i];
+    std::vector<uint32_t> fill(head.begin(), head.end() - 1);
+    for (uint32_t i = 0; i < S; ++i)
+      for (uint32_t e = t.row_ptr[i]; e < t.row_ptr[i + 1]; ++e) out[fill[t.col_idx[e]]++] = i;
+    for (uint32_t i = 0; i < S; ++i)
+      if (indeg[i] == 0) stack.push_back(i);
+    uint32_t visited = 0;
+    while (!stack.empty()) {
+      const uint32_t u = stack.back();
+      stack.pop_back();
+      ++visited;
+      for (uint32_t x = head[u]; x < head[u + 1]; ++x)
+        if (--indeg[out[x]] == 0) stack.push_back(out[x]);
+    }
+    if (visited != S) { why = "dependency cycle detected"; return BF_ETOPO; }
+  }
+  uint32_t prev_step = 0;
+  p.child_first.assign(t.n_parallel, 0);
+  p.allow_off.assign(t.n_parallel, 0);
+  uint32_t nib = 0, allow_words = 0;
+  for (uint32_t q = 0; q < t.n_parallel; ++q) {
+    const bf_parallel_desc& d = t.parallel[q];
+    if (d.step >= S) { why = "parallel desc step out of range"; return BF_ETOPO; }
+    if ((t.step_flags[d.step] & BF_SF_TYPE_MASK) != BF_STEP_PARALLEL) { why = "parallel desc on a non-parallel step"; return BF_ETOPO; }
+    if (q && d.step <= prev_step) { why = "parallel descs must ascend by step"; return BF_ETOPO; }
+    if (t.branch_allow_bits && (uint64_t)d.allow_first + d.branches > t.n_branch_allow_bits) { why = "branch_allow_bits too short"; return BF_EINVAL; }
+    prev_step = d.step;
+    nib = round_up(nib, 8);
+    p.child_first[q] = nib;
+    nib += d.branches;
+    allow_words += (d.branches + 31) / 32 + (d.branches == 0 ? 1 : 0);
+  }
+  if (nib > 0xFFFF) { why = "too many parallel branches"; return BF_ETOPO; }
+  p.child_nibbles = round_up(nib, 8);
+  p.W = (S + 31) / 32;
+  uint32_t off = sizeof(bf::TopoHeader);
+  off += round_up(2 * (S + 1), 16);
+  p.off_col = off;
+  off += round_up(2 * E, 16);
+  p.off_planes = off;
+  off += round_up(bf::PL_COUNT * p.W * 4, 16);
+  p.off_par = off;
+  off += t.n_parallel * (uint32_t)sizeof(bf::ParDesc);
+  p.off_allow = off;
+  uint32_t aw = 0;
+  for (uint32_t q = 0; q < t.n_parallel; ++q) {
+    p.allow_off[q] = p.off_allow + aw * 4;
+    aw += (t.parallel[q].branches + 31) / 32 + (t.parallel[q].branches == 0 ? 1 : 0);
+  }
+  off += allow_words * 4;
+  p.rec_bytes = round_up(off, 16);
+  return BF_OK;
+}
+
+void build_record(const bf_topology& t, const RecPlan& p, uint8_t* rec) {
+  memset(rec, 0, p.rec_bytes);
+  const uint32_t S = t.n_steps, E = t.n_edges, W = p.W;
+  bf::TopoHeader h{};
+  h.S = (uint16_t)S; h.W = (uint16_t)W; h.E = (uint16_t)E; h.P = (uint16_t)t.n_parallel;
+  h.child_nibbles = (uint16_t)p.child_nibbles;
+  h.off_col = p.off_col; h.off_planes = p.off_planes; h.off_par = p.off_par; h.rec_bytes = p.rec_bytes;
+  uint16_t* rp = reinterpret_cast<uint16_t*>(rec + sizeof(bf::TopoHeader));
+  for (uint32_t i = 0; i <= S; ++i) rp[i] = (uint16_t)t.row_ptr[i];
+  if (E) memcpy(rec + p.off_col, t.col_idx, 2 * (size_t)E);
+  uint32_t* planes = reinterpret_cast<uint32_t*>(rec + p.off_planes);
+  uint32_t nm = 0, nc = 0, nf = 0;
+  for (uint32_t i = 0; i < S; ++i) {
+    const uint8_t f = t.step_flags[i];
+    const uint32_t w = i >> 5, b = 1u << (i & 31u);
+    if (f & 1u) planes[bf::PL_T0 * W + w] |= b;
+    if (f & 2u) planes[bf::PL_T1 * W + w] |= b;
+    if (f & 4u) planes[bf::PL_T2 * W + w] |= b;
+    if (f & BF_SF_ALLOW_FAILURE) planes[bf::PL_AF * W + w] |= b;
+    if (f & BF_SF_ON_TIMEOUT_SKIP) planes[bf::PL_TS * W + w] |= b;
+    if (f & BF_SF_HAS_IF) planes[bf::PL_HASIF * W + w] |= b;
+    const uint32_t g = (f & BF_SF_GROUP_MASK) >> BF_SF_GROUP_SHIFT;
+    if (g == BF_GROUP_COMPENSATION) { planes[bf::PL_G1 * W + w] |= b; nc++; }
+    else if (g == BF_GROUP_MAIN) nm++;
+    else { planes[bf::PL_G2 * W + w] |= b; nf++; }  // 2 (and the unused code 3) count as finally
+  }
+  h.n_main = (uint16_t)nm; h.n_comp = (uint16_t)nc; h.n_final = (uint16_t)nf;
+  bf::ParDesc* pd = reinterpret_cast<bf::ParDesc*>(rec + p.off_par);
+  for (uint32_t q = 0; q < t.n_parallel; ++q) {
+    pd[q].step = t.parallel[q].step;
+    pd[q].branches = t.parallel[q].branches;
+    pd[q].child_first = p.child_first[q];
+    pd[q].allow_off = p.allow_off[q];
+    pd[q].reserved = 0;
+    uint32_t* aw = reinterpret_cast<uint32_t*>(rec + p.allow_off[q]);
+    if (t.branch_allow_bits)
+      for (uint32_t b = 0; b < t.parallel[q].branches; ++b) {
+        const uint32_t src = t.parallel[q].allow_first + b;
+        if ((t.branch_allow_bits[src >> 3] >> (src & 7u)) & 1u) aw[b >> 5] |= 1u << (b & 31u);
+      }
+  }
+  memcpy(rec, &h, sizeof h);
+}
+
+int grow_arena(bf_ctx* c, size_t need_total) {
+  if (need_total <= c->arena_cap) return BF_OK;
+  size_t ncap = c->arena_cap ? c->arena_cap : (size_t)64 << 20;
+  while (ncap < need_total) ncap *= 2;
+  uint8_t* na = nullptr;
+  cudaError_t e = cudaMalloc(&na, ncap);
+  if (e != cudaSuccess) {  // retry exact
+    ncap = round_up_sz(need_total, (size_t)1 << 20);
+    e = cudaMalloc(&na, ncap);
+    if (e != cudaSuccess) return fail(c, BF_ENOMEM, std::string("arena cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  if (c->arena && c->arena_used) {
+    e = cudaMemcpy(na, c->arena, c->arena_used, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) { cudaFree(na); return cuda_fail(c, e, "arena copy"); }
+  }
+  if (c->arena) cudaFree(c->arena);
+  c->arena = na;
+  c->arena_cap = ncap;
+  for (size_t s = 0; s < c->meta.size(); ++s)
+    if (c->meta[s].alive) c->slots_host[s].addr = (uint64_t)(uintptr_t)(c->arena + c->meta[s].offset);
+  c->slots_dirty = true;
+  return BF_OK;
+}
+
+int sync_slots(bf_ctx* c, cudaStream_t stream) {
+  if (!c->slots_dirty) return BF_OK;
+  const size_t n = c->slots_host.size();
+  if (n > c->slots_dev_cap) {
+    size_t ncap = c->slots_dev_cap ? c->slots_dev_cap : 1024;
+    while (ncap < n) ncap *= 2;
+    bf::Slot* np = nullptr;
+    BF_CUDA(c, cudaMalloc(&np, ncap * sizeof(bf::Slot)));
+    if (c->slots_dev) cudaFree(c->slots_dev);
+    c->slots_dev = np;
+    c->slots_dev_cap = ncap;
+  }
+  if (n) BF_CUDA(c, cudaMemcpyAsync(c->slots_dev, c->slots_host.data(), n * sizeof(bf::Slot), cudaMemcpyHostToDevice, stream));
+  BF_CUDA(c, cudaStreamSynchronize(stream));
+  c->slots_dirty = false;
+  return BF_OK;
+}
+
+int check_layout(bf_ctx* c, const bf_layout& L) {
+  if (L.steps_max == 0 || L.steps_max > BF_MAX_STEPS) return fail(c, BF_EINVAL, "layout.steps_max out of range");
+  if (L.words != (L.steps_max + 31) / 32) return fail(c, BF_EINVAL, "layout.words != ceil(steps_max/32)");
+  if (L.state_stride % 16 || L.result_stride % 16 || L.state_stride == 0 || L.result_stride == 0)
+    return fail(c, BF_EINVAL, "strides must be non-zero multiples of 16");
+  if (L.off_phase == BF_OFF_NONE || L.off_ready == BF_OFF_NONE || L.off_skip == BF_OFF_NONE)
+    return fail(c, BF_EINVAL, "phase / ready / skip fields are mandatory");
+  const uint32_t W = L.words;
+  auto in_state = [&](uint32_t off, uint32_t len) { return off == BF_OFF_NONE || (off % 4 == 0 && off >= 16 && off + len <= L.state_stride); };
+  auto in_res = [&](uint32_t off, uint32_t len) { return off == BF_OFF_NONE || (off % 4 == 0 && off >= 16 && off + len <= L.result_stride); };
+  if (!in_state(L.off_phase, W * 16) || !in_state(L.off_cond, W * 8) || !in_state(L.off_decision, W * 8) ||
+      !in_state(L.off_child, (L.child_nibbles + 1) / 2))
+    return fail(c, BF_EINVAL, "state field outside the record");
+  if (!in_res(L.off_ready, W * 4) || !in_res(L.off_skip, W * 4) || !in_res(L.off_fail, W * 4) ||
+      !in_res(L.off_needs_cond, W * 4) || !in_res(L.off_skip_dep, W * 4) || !in_res(L.off_phase_out, W * 16))
+    return fail(c, BF_EINVAL, "result field outside the record");
+  return BF_OK;
+}
+
+// shared-memory plan + launch of one pass on device buffers
+int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_result, bf_expansion* d_exp,
+             unsigned long long* d_counts, cudaStream_t stream) {
+  const bf_layout& L = b.layout;
+  if (int rc = sync_slots(c, stream)) return rc;
+  if (c->max_rec_bytes == 0) return fail(c, BF_ETOPO, "no topology has been uploaded");
+
+  bf::KParams P{};
+  P.state = d_state; P.result = d_result; P.slots = c->slots_dev;
+  P.counts = (b.flags & BF_EVAL_NO_COUNTS) ? nullptr : d_counts;
+  P.n_slots = (uint32_t)c->slots_host.size();
+  P.n_runs = b.n_runs; P.flags = b.flags; P.max_iter = b.max_iterations;
+  P.words = L.words;
+  P.state_stride = L.state_stride; P.off_phase = L.off_phase; P.off_cond = L.off_cond;
+  P.off_decision = L.off_decision; P.off_child = L.off_child;
+  P.result_stride = L.result_stride; P.off_ready = L.off_ready; P.off_skip = L.off_skip; P.off_fail = L.off_fail;
+  P.off_needs_cond = L.off_needs_cond; P.off_skip_dep = L.off_skip_dep; P.off_phase_out = L.off_phase_out;
+
+  const bool want_exp = (b.flags & BF_EVAL_EXPANSION) && d_exp != nullptr;
+  if (want_exp) {
+    if (int rc = ensure_dev(c, c->d_exp_counts, c->d_exp_counts_cap, b.n_runs)) return rc;
+    if (int rc = ensure_dev(c, c->d_offsets, c->d_offsets_cap, b.n_runs)) return rc;
+    if (int rc = ensure_dev(c, c->d_block_sums, c->d_block_sums_cap, (size_t)(b.n_runs + 1023) / 1024 + 1)) return rc;
+    P.exp_counts = c->d_exp_counts;
+  }
+
+  // ---- shared-memory plan ----
+  P.topo_buf_bytes = round_up(c->max_rec_bytes, 16);
+  P.stage_bytes = L.state_stride + P.topo_buf_bytes;
+  P.work_bytes = round_up(84 * L.words, 16);
+  const uint32_t budget = 227u * 1024u - 128u;
+  uint32_t best_st = 0, best_wpb = 0, best_score = 0;
+  const char* env_st = getenv("BF_STAGES");
+  const char* env_w = getenv("BF_WARPS");
+  for (uint32_t st = 8; st >= 1; --st) {
+    if (env_st && (uint32_t)atoi(env_st) != st) continue;
+    const uint32_t per_warp = st * P.stage_bytes + P.work_bytes + 64;
+    uint32_t wpb = budget / per_warp;
+    if (wpb > 16) wpb = 16;
+    if (env_w && (uint32_t)atoi(env_w) < wpb) wpb = (uint32_t)atoi(env_w);
+    if (wpb == 0) continue;
+    // enough bytes in flight to cover HBM latency (Little: ~45 KB/SM), then as many warps as fit
+    uint32_t inflight_kb = wpb * (st - 1) * P.stage_bytes / 1024u;
+    if (inflight_kb > 96) inflight_kb = 96;
+    const uint32_t score = inflight_kb + wpb * 8 + (st <= 4 ? 1 : 0);
+    if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; }
+  }
+  if (best_wpb == 0) return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
+  P.stages = best_st;
+  P.warps_per_block = best_wpb;
+  const uint32_t smem = 128 + best_wpb * (best_st * P.stage_bytes + P.work_bytes + 64);
+  int per_sm = bf::frontier_max_blocks_per_sm(best_wpb * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  const char* env_b = getenv("BF_BLOCKS_PER_SM");
+  if (env_b && atoi(env_b) >= 1 && atoi(env_b) < per_sm) per_sm = atoi(env_b);
+  uint32_t grid = (uint32_t)c->sm_count * (uint32_t)per_sm;
+  const uint32_t need_blocks = (b.n_runs + best_wpb - 1) / best_wpb;
+  if (grid > need_blocks) grid = need_blocks ? need_blocks : 1;
+
+  if (b.n_runs) {
+    BF_CUDA(c, bf::launch_frontier(P, grid, smem, stream));
+    c->stats.kernel_launches += 1;
+    if (want_exp) {
+      uint32_t nl = 0;
+      BF_CUDA(c, bf::launch_expansion(P, c->d_block_sums, c->d_offsets, d_exp, b.expansion_cap, stream, &nl));
+      c->stats.kernel_launches += nl;
+    }
+  }
+  c->stats.last_grid = grid; c->stats.last_block = best_wpb * 32; c->stats.last_smem_bytes = smem; c->stats.last_stages = best_st;
+  return BF_OK;
+}
+
+int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_t* slots_out) {
+  std::vector<RecPlan> plans(count);
+  size_t total = 0;
+  std::string why;
+  for (uint32_t i = 0; i < count; ++i) {
+    const int rc = plan_record(topos[i], plans[i], why);
+    if (rc != BF_OK) return fail(c, rc, "topology " + std::to_string(i) + ": " + why);
+    total += plans[i].rec_bytes;
+  }
+  const size_t base = round_up_sz(c->arena_used, 16);
+  if (int rc = grow_arena(c, base + total)) return rc;
+  std::vector<uint8_t> staging;
+  try { staging.resize(total); } catch (const std::bad_alloc&) { return fail(c, BF_ENOMEM, "host staging allocation failed"); }
+  size_t off = 0;
+  for (uint32_t i = 0; i < count; ++i) {
+    build_record(topos[i], plans[i], staging.data() + off);
+    off += plans[i].rec_bytes;
+  }
+  if (total) BF_CUDA(c, cudaMemcpy(c->arena + base, staging.data(), total, cudaMemcpyHostToDevice));
+  off = 0;
+  for (uint32_t i = 0; i < count; ++i) {
+    uint32_t slot;
+    if (!c->free_slots.empty()) { slot = c->free_slots.back(); c->free_slots.pop_back(); }
+    else { slot = (uint32_t)c->meta.size(); c->meta.emplace_back(); c->slots_host.push_back(bf::Slot{0, 0, 0}); }
+    TopoMeta& m = c->meta[slot];
+    m.alive = true; m.S = topos[i].n_steps; m.E = topos[i].n_edges; m.P = topos[i].n_parallel;
+    m.bytes = plans[i].rec_bytes; m.offset = base + off; m.child_first = plans[i].child_first;
+    m.child_nibbles = plans[i].child_nibbles;
+    c->slots_host[slot] = bf::Slot{(uint64_t)(uintptr_t)(c->arena + m.offset), m.bytes, m.S};
+    if (m.bytes > c->max_rec_bytes) c->max_rec_bytes = m.bytes;
+    off += plans[i].rec_bytes;
+    slots_out[i] = slot;
+    c->n_alive++;
+  }
+  c->arena_used = base + total;
+  c->slots_dirty = true;
+  return BF_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+uint32_t bf_abi_version(void) { return BF_ABI_VERSION; }
+
+const char* bf_strerror(int status) {
+  switch (status) {
+    case BF_OK: return "ok";
+    case BF_EINVAL: return "invalid argument";
+    case BF_ENOMEM: return "out of memory";
+    case BF_ECUDA: return "CUDA error";
+    case BF_ENCCL: return "collective error";
+    case BF_ETOPO: return "topology rejected";
+    case BF_ENODEV: return "no usable device";
+    default: return "unknown status";
+  }
+}
+
+const char* bf_last_error(const bf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int bf_create(bf_ctx** out, const bf_config* cfg) {
+  if (!out) return BF_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return BF_ENODEV; }
+  const int dev = cfg ? cfg->device : 0;
+  if (dev < 0 || dev >= ndev) return BF_ENODEV;
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return BF_ECUDA;
+  if (prop.major < 10) return BF_ENODEV;  // built for sm_100a only
+  bf_ctx* c = new (std::nothrow) bf_ctx();
+  if (!c) return BF_ENOMEM;
+  c->device = dev;
+  c->sm_count = prop.multiProcessorCount;
+  c->stats.sm_count = (uint32_t)prop.multiProcessorCount;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&c->d_counts, sizeof(bf_counts)) != cudaSuccess) {
+    delete c;
+    return BF_ECUDA;
+  }
+  if (cfg && cfg->arena_bytes) {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (grow_arena(c, (size_t)cfg->arena_bytes) != BF_OK) { bf_destroy(c); return BF_ENOMEM; }
+  }
+  if (cfg && cfg->max_topologies) { c->meta.reserve(cfg->max_topologies); c->slots_host.reserve(cfg->max_topologies); }
+  *out = c;
+  return BF_OK;
+}
+
+void bf_destroy(bf_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
+  cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums);
+  delete c;
+}
+
+int bf_topology_put_many(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_t* slots_out) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  if ((!topos || !slots_out) && count) return fail(c, BF_EINVAL, "null topos/slots_out");
+  BF_CUDA(c, cudaSetDevice(c->device));
+  return put_many_locked(c, topos, count, slots_out);
+}
+
+int bf_topology_put(bf_ctx* c, const bf_topology* topo, uint32_t* slot_out) { return bf_topology_put_many(c, topo, 1, slot_out); }
+
+int bf_topology_drop(bf_ctx* c, uint32_t slot) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (slot >= c->meta.size() || !c->meta[slot].alive) return fail(c, BF_ETOPO, "drop of an unknown slot");
+  c->meta[slot].alive = false;
+  c->slots_host[slot] = bf::Slot{0, 0, 0};
+  c->free_slots.push_back(slot);
+  c->n_alive--;
+  c->slots_dirty = true;
+  if (c->n_alive == 0) {  // arena is a bump allocator: it resets when the last topology goes
+    c->arena_used = 0;
+    c->max_rec_bytes = 0;
+  }
+  return BF_OK;
+}
+
+int bf_topology_child_first(const bf_ctx* c, uint32_t slot, uint32_t* out, uint32_t cap) {
+  if (!c || slot >= c->meta.size() || !c->meta[slot].alive) return BF_ETOPO;
+  const TopoMeta& m = c->meta[slot];
+  for (uint32_t q = 0; q < m.P && q < cap; ++q) out[q] = m.child_first[q];
+  return (int)m.P;
+}
+
+int bf_topology_record(const bf_ctx* c, uint32_t slot, uint64_t* dev_addr, uint32_t* bytes) {
+  if (!c || slot >= c->meta.size() || !c->meta[slot].alive) return BF_ETOPO;
+  if (dev_addr) *dev_addr = c->slots_host[slot].addr;
+  if (bytes) *bytes = c->meta[slot].bytes;
+  return BF_OK;
+}
+
+int bf_layout_init(bf_layout* out, uint32_t steps_max, uint32_t child_nibbles, uint32_t fields) {
+  if (!out || steps_max == 0 || steps_max > BF_MAX_STEPS) return BF_EINVAL;
+  bf_layout L{};
+  L.steps_max = steps_max;
+  L.words = (steps_max + 31) / 32;
+  L.fields = fields;
+  L.child_nibbles = (fields & BF_F_CHILD) ? child_nibbles : 0;
+  uint32_t off = sizeof(bf_run_header);
+  L.off_phase = off; off += L.words * 16;
+  L.off_cond = BF_OFF_NONE; L.off_decision = BF_OFF_NONE; L.off_child = BF_OFF_NONE;
+  if (fields & BF_F_COND) { L.off_cond = off; off += L.words * 8; }
+  if (fields & BF_F_DECISION) { L.off_decision = off; off += L.words * 8; }
+  if (fields & BF_F_CHILD) { L.off_child = off; off += round_up((L.child_nibbles + 1) / 2, 4); }
+  L.state_stride = round_up(off, 16);
+  off = sizeof(bf_result_header);
+  L.off_ready = off; off += L.words * 4;
+  L.off_skip = off; off += L.words * 4;
+  L.off_fail = L.off_needs_cond = L.off_skip_dep = L.off_phase_out = BF_OFF_NONE;
+  if (fields & BF_F_OUT_FAIL) { L.off_fail = off; off += L.words * 4; }
+  if (fields & BF_F_OUT_NEEDS_COND) { L.off_needs_cond = off; off += L.words * 4; }
+  if (fields & BF_F_OUT_SKIP_DEP) { L.off_skip_dep = off; off += L.words * 4; }
+  if (fields & BF_F_OUT_PHASE) { L.off_phase_out = off; off += L.words * 16; }
+  L.result_stride = round_up(off, 16);
+  *out = L;
+  return BF_OK;
+}
+
+int bf_eval_device(bf_ctx* c, const bf_batch* b, void* stream) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!b || b->struct_size != sizeof(bf_batch)) return fail(c, BF_EINVAL, "bad bf_batch.struct_size");
+  if (int rc = check_layout(c, b->layout)) return rc;
+  if (b->n_runs && (!b->state || !b->result)) return fail(c, BF_EINVAL, "null state/result");
+  BF_CUDA(c, cudaSetDevice(c->device));
+  return run_pass(c, *b, static_cast<const uint8_t*>(b->state), static_cast<uint8_t*>(b->result), b->expansion,
+                  reinterpret_cast<unsigned long long*>(b->counts), static_cast<cudaStream_t>(stream));
+}
+
+int bf_eval(bf_ctx* c, const bf_batch* b) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!b || b->struct_size != sizeof(bf_batch)) return fail(c, BF_EINVAL, "bad bf_batch.struct_size");
+  if (int rc = check_layout(c, b->layout)) return rc;
+  if (b->n_runs && (!b->state || !b->result)) return fail(c, BF_EINVAL, "null state/result");
+  const bf_layout& L = b->layout;
+  const size_t sbytes = (size_t)b->n_runs * L.state_stride, rbytes = (size_t)b->n_runs * L.result_stride;
+  if (b->flags & BF_EVAL_VALIDATE) {
+    const uint8_t* st = static_cast<const uint8_t*>(b->state);
+    for (uint32_t r = 0; r < b->n_runs; ++r) {
+      const bf_run_header* h = reinterpret_cast<const bf_run_header*>(st + (size_t)r * L.state_stride);
+      if (h->topo_slot >= c->meta.size() || !c->meta[h->topo_slot].alive)
+        return fail(c, BF_ETOPO, "run " + std::to_string(r) + ": unknown topology slot");
+      const TopoMeta& m = c->meta[h->topo_slot];
+      if (m.S > L.steps_max) return fail(c, BF_EINVAL, "run " + std::to_string(r) + ": topology larger than layout.steps_max");
+      if (L.off_child != BF_OFF_NONE && m.child_nibbles > L.child_nibbles)
+        return fail(c, BF_EINVAL, "run " + std::to_string(r) + ": child area too small");
+      const uint8_t* ph = reinterpret_cast<const uint8_t*>(h) + L.off_phase;
+      for (uint32_t i = 0; i < m.S; ++i)
+        if (((ph[i >> 1] >> ((i & 1u) * 4u)) & 0xFu) == BF_PHASE_RESERVED)
+          return fail(c, BF_EINVAL, "run " + std::to_string(r) + ": reserved phase code 15");
+    }
+  }
+  BF_CUDA(c, cudaSetDevice(c->device));
+  if (int rc = ensure_dev(c, c->d_state, c->d_state_cap, sbytes)) return rc;
+  if (int rc = ensure_dev(c, c->d_result, c->d_result_cap, rbytes)) return rc;
+  const bool want_exp = (b->flags & BF_EVAL_EXPANSION) && b->expansion && b->expansion_cap;
+  if (want_exp)
+    if (int rc = ensure_dev(c, c->d_exp, c->d_exp_cap, (size_t)b->expansion_cap)) return rc;
+  cudaStream_t s = c->stream;
+  if (sbytes) BF_CUDA(c, cudaMemcpyAsync(c->d_state, b->state, sbytes, cudaMemcpyHostToDevice, s));
+  BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
+  bf_batch db = *b;
+  if (!want_exp) db.flags &= ~BF_EVAL_EXPANSION;
+  if (int rc = run_pass(c, db, c->d_state, c->d_result, want_exp ? c->d_exp : nullptr, c->d_counts, s)) return rc;
+  if (rbytes) BF_CUDA(c, cudaMemcpyAsync(b->result, c->d_result, rbytes, cudaMemcpyDeviceToHost, s));
+  bf_counts hc{};
+  BF_CUDA(c, cudaMemcpyAsync(&hc, c->d_counts, sizeof hc, cudaMemcpyDeviceToHost, s));
+  BF_CUDA(c, cudaStreamSynchronize(s));
+  if (want_exp) {
+    const uint64_t n = hc.expansion < b->expansion_cap ? hc.expansion : b->expansion_cap;
+    if (n) BF_CUDA(c, cudaMemcpy(b->expansion, c->d_exp, (size_t)n * sizeof(bf_expansion), cudaMemcpyDeviceToHost));
+  }
+  if (b->counts) *b->counts = hc;
+  return BF_OK;
+}
+
+int bf_alloc_pinned(bf_ctx* c, size_t bytes, void** out) {
+  if (!c || !out) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  BF_CUDA(c, cudaSetDevice(c->device));
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(c, BF_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return BF_OK;
+}
+
+int bf_free_pinned(bf_ctx* c, void* p) {
+  if (!c) return BF_EINVAL;
+  if (!p) return BF_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  BF_CUDA(c, cudaFreeHost(p));
+  return BF_OK;
+}
+
+int bf_get_stats(const bf_ctx* c, bf_stats* out) {
+  if (!c || !out) return BF_EINVAL;
+  *out = c->stats;
+  out->arena_used_bytes = c->arena_used;
+  out->arena_cap_bytes = c->arena_cap;
+  out->n_topologies = c->n_alive;
+  out->sm_count = (uint32_t)c->sm_count;
+  return BF_OK;
+}
+
+}  // extern "C"

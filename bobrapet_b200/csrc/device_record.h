@@ -1,0 +1,76 @@
+// device_record.h — HBM layouts shared by the host packer (abi.cu) and the kernels.
+//
+// A topology (one Story generation: needs-adjacency + static step flags) is one
+// contiguous, 16-byte aligned, 16-byte padded record in the arena so that a warp
+// stages it into shared memory with ONE cp.async.bulk (TMA) copy:
+//
+//   +0            TopoHeader (32 B)
+//   +32           row_ptr   u16[S+1]          CSR over allStorySteps (dag.go:3270), pad 16
+//   +off_col      col_idx   u16[E]            dependency step indices, pad 16
+//   +off_planes   planes    u32[8][W]         static step flags, BIT-SLICED (W = ceil(S/32)):
+//                                             t0,t1,t2 (type), AF, TS, HAS_IF, G1 (comp), G2 (finally)
+//                                             = S bytes, same size as the canonical u8 step_flags[S]
+//   +off_par      ParDesc[P] (16 B each) followed by the branch allowFailure bit words
+//
+// Canonical ("algorithmic") bytes per topology, SURVEY.md section 8(d):
+//   2*(S+1) + 2*E + S.  The header and the 16-byte paddings are overhead (~1.5% at cfg3).
+#pragma once
+#include <stdint.h>
+
+namespace bf {
+
+struct TopoHeader {
+  uint16_t S;          // steps
+  uint16_t W;          // ceil(S/32)
+  uint16_t E;          // edges
+  uint16_t P;          // parallel descs
+  uint16_t n_main, n_comp, n_final;
+  uint16_t child_nibbles;  // total child nibbles of all descs
+  uint32_t off_col;
+  uint32_t off_planes;
+  uint32_t off_par;
+  uint32_t rec_bytes;  // multiple of 16
+};
+static_assert(sizeof(TopoHeader) == 32, "TopoHeader must be 32 bytes");
+
+enum Plane { PL_T0 = 0, PL_T1, PL_T2, PL_AF, PL_TS, PL_HASIF, PL_G1, PL_G2, PL_COUNT };
+
+struct ParDesc {
+  uint16_t step;
+  uint16_t branches;
+  uint32_t child_first;  // nibble offset in the run's child area
+  uint32_t allow_off;    // byte offset (from record start) of this desc's allowFailure bit words
+  uint32_t reserved;
+};
+static_assert(sizeof(ParDesc) == 16, "ParDesc must be 16 bytes");
+
+struct Slot {          // device slot table entry
+  uint64_t addr;       // device address of the record (0 = dead slot)
+  uint32_t bytes;      // rec_bytes
+  uint32_t S;
+};
+static_assert(sizeof(Slot) == 16, "Slot must be 16 bytes");
+
+struct KParams {
+  const uint8_t* state;
+  uint8_t* result;
+  const Slot* slots;
+  unsigned long long* counts;   // bf_counts (4 x u64) or nullptr
+  uint32_t* exp_counts;         // [n_runs] compact per-run expansion counts or nullptr
+  uint32_t n_slots;
+  uint32_t n_runs;
+  uint32_t flags;               // BF_EVAL_*
+  uint32_t max_iter;
+  // layout (bf_layout)
+  uint32_t words;
+  uint32_t state_stride, off_phase, off_cond, off_decision, off_child;
+  uint32_t result_stride, off_ready, off_skip, off_fail, off_needs_cond, off_skip_dep, off_phase_out;
+  // shared-memory plan
+  uint32_t stages;
+  uint32_t topo_buf_bytes;      // per-stage room for a topology record
+  uint32_t stage_bytes;         // state_stride + topo_buf_bytes (multiple of 16)
+  uint32_t work_bytes;          // per-warp scratch
+  uint32_t warps_per_block;
+};
+
+}  // namespace bf

@@ -1,0 +1,160 @@
+"""Frontier — thin Python handle over the C ABI (include/bobrafrontier.h).
+
+This is the call a user of the Python binding makes; it is the same call path the
+cgo shim uses (go/frontier/frontier.go): bf_create -> bf_topology_put_many ->
+bf_eval / bf_eval_device.  There is no CPU path here: without the CUDA library or
+without a B200 the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi as A
+from .records import EXP_DTYPE, PAR_DTYPE, TOPO_DTYPE
+
+
+class TopologySet:
+    """`count` topologies held as concatenated numpy arrays (keeps them alive for the C call).
+
+    S, E, P : [count] uint32; row_ptr: concatenation of (S[i]+1) uint32 each; col_idx uint16;
+    step_flags uint8; parallel PAR_DTYPE; allow_bits uint8 (bit arrays, one shared pool)."""
+
+    def __init__(self, S, E, row_ptr, col_idx, step_flags, P=None, parallel=None, allow_bits=None):
+        self.S = np.ascontiguousarray(S, dtype=np.uint32)
+        self.E = np.ascontiguousarray(E, dtype=np.uint32)
+        self.count = int(self.S.shape[0])
+        self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+        self.col_idx = np.ascontiguousarray(col_idx, dtype=np.uint16)
+        self.step_flags = np.ascontiguousarray(step_flags, dtype=np.uint8)
+        self.P = np.zeros(self.count, dtype=np.uint32) if P is None else np.ascontiguousarray(P, dtype=np.uint32)
+        self.parallel = np.zeros(0, dtype=PAR_DTYPE) if parallel is None else np.ascontiguousarray(parallel, dtype=PAR_DTYPE)
+        self.allow_bits = np.zeros(0, dtype=np.uint8) if allow_bits is None else np.ascontiguousarray(allow_bits, dtype=np.uint8)
+        assert self.row_ptr.shape[0] == int(self.S.sum()) + self.count
+        assert self.col_idx.shape[0] == int(self.E.sum())
+        assert self.step_flags.shape[0] == int(self.S.sum())
+        assert self.parallel.shape[0] == int(self.P.sum())
+
+    def descriptors(self) -> np.ndarray:
+        """Array of bf_topology structs pointing into the concatenated arrays."""
+        t = np.zeros(self.count, dtype=TOPO_DTYPE)
+        S64, E64, P64 = self.S.astype(np.uint64), self.E.astype(np.uint64), self.P.astype(np.uint64)
+        rp_off = np.concatenate(([0], np.cumsum(S64 + 1)[:-1])).astype(np.uint64)
+        ci_off = np.concatenate(([0], np.cumsum(E64)[:-1])).astype(np.uint64)
+        sf_off = np.concatenate(([0], np.cumsum(S64)[:-1])).astype(np.uint64)
+        pd_off = np.concatenate(([0], np.cumsum(P64)[:-1])).astype(np.uint64)
+        t["n_steps"], t["n_edges"], t["n_parallel"] = self.S, self.E, self.P
+        t["row_ptr"] = np.uint64(self.row_ptr.ctypes.data) + rp_off * np.uint64(4)
+        t["col_idx"] = np.uint64(self.col_idx.ctypes.data if self.col_idx.size else 0) + ci_off * np.uint64(2)
+        t["step_flags"] = np.uint64(self.step_flags.ctypes.data) + sf_off
+        if self.parallel.size:
+            t["parallel"] = np.uint64(self.parallel.ctypes.data) + pd_off * np.uint64(PAR_DTYPE.itemsize)
+        if self.allow_bits.size:
+            t["branch_allow_bits"] = np.uint64(self.allow_bits.ctypes.data)
+            t["n_branch_allow_bits"] = np.uint32(self.allow_bits.size * 8)
+        return t
+
+    def algorithmic_bytes(self) -> int:
+        """Canonical topology bytes, SURVEY.md 8(d): 2(S+1) + 2E + S per topology."""
+        return int((2 * (self.S.astype(np.int64) + 1) + 2 * self.E.astype(np.int64) + self.S.astype(np.int64)).sum())
+
+
+class Frontier:
+    def __init__(self, device: int = 0, arena_bytes: int = 0):
+        self._lib = A.load()
+        self._ctx = C.c_void_p()
+        cfg = A.Config(struct_size=C.sizeof(A.Config), device=device, arena_bytes=arena_bytes, max_topologies=0, flags=0)
+        rc = self._lib.bf_create(C.byref(self._ctx), C.byref(cfg))
+        if rc != A.BF_OK:
+            self._ctx = None
+            raise A.FrontierError(rc, "bf_create(device=%d): no CUDA fallback exists for this path" % device)
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.bf_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != A.BF_OK:
+            raise A.FrontierError(rc, "%s: %s" % (what, self._lib.bf_last_error(self._ctx).decode()))
+
+    # -- topologies
+    def put_topologies(self, ts: TopologySet) -> np.ndarray:
+        desc = ts.descriptors()
+        slots = np.zeros(ts.count, dtype=np.uint32)
+        rc = self._lib.bf_topology_put_many(self._ctx, desc.ctypes.data_as(C.POINTER(A.Topology)), ts.count,
+                                            slots.ctypes.data_as(C.POINTER(C.c_uint32)))
+        self._check(rc, "bf_topology_put_many")
+        return slots
+
+    def drop_topology(self, slot: int):
+        self._check(self._lib.bf_topology_drop(self._ctx, int(slot)), "bf_topology_drop")
+
+    def child_first(self, slot: int) -> np.ndarray:
+        out = np.zeros(A.MAX_PARALLEL, dtype=np.uint32)
+        n = self._lib.bf_topology_child_first(self._ctx, int(slot), out.ctypes.data_as(C.POINTER(C.c_uint32)), A.MAX_PARALLEL)
+        if n < 0:
+            raise A.FrontierError(n, "bf_topology_child_first")
+        return out[:n]
+
+    def topology_record(self, slot: int):
+        addr, nbytes = C.c_uint64(), C.c_uint32()
+        self._check(self._lib.bf_topology_record(self._ctx, int(slot), C.byref(addr), C.byref(nbytes)), "bf_topology_record")
+        return addr.value, nbytes.value
+
+    # -- evaluation over HOST buffers (H2D + kernels + D2H inside the call)
+    def eval(self, L: A.Layout, state: np.ndarray, result: Optional[np.ndarray] = None, flags: int = 0,
+             max_iterations: int = 0, expansion_cap: int = 0):
+        n = int(state.shape[0])
+        assert state.dtype == np.uint8 and state.flags["C_CONTIGUOUS"] and state.shape[1] == L.state_stride
+        if result is None:
+            result = np.zeros((n, L.result_stride), dtype=np.uint8)
+        counts = A.Counts()
+        exp = np.zeros(max(expansion_cap, 1), dtype=EXP_DTYPE) if (flags & A.EVAL_EXPANSION) else None
+        b = A.Batch(struct_size=C.sizeof(A.Batch), n_runs=n, flags=flags, max_iterations=max_iterations, layout=L,
+                    state=state.ctypes.data, result=result.ctypes.data,
+                    expansion=(exp.ctypes.data if exp is not None else None),
+                    expansion_cap=(expansion_cap if exp is not None else 0),
+                    counts=C.addressof(counts))
+        self._check(self._lib.bf_eval(self._ctx, C.byref(b)), "bf_eval")
+        cdict = {"ready": counts.ready, "skip": counts.skip, "expansion": counts.expansion, "evals": counts.evals}
+        if exp is not None:
+            return result, cdict, exp[:min(int(counts.expansion), expansion_cap)]
+        return result, cdict
+
+    # -- evaluation over DEVICE buffers (async on `stream`)
+    def eval_device(self, L: A.Layout, n_runs: int, state_ptr: int, result_ptr: int, counts_ptr: int = 0,
+                    stream: int = 0, flags: int = 0, max_iterations: int = 0, expansion_ptr: int = 0,
+                    expansion_cap: int = 0):
+        b = A.Batch(struct_size=C.sizeof(A.Batch), n_runs=n_runs, flags=flags, max_iterations=max_iterations, layout=L,
+                    state=state_ptr, result=result_ptr, expansion=(expansion_ptr or None), expansion_cap=expansion_cap,
+                    counts=(counts_ptr or None))
+        self._check(self._lib.bf_eval_device(self._ctx, C.byref(b), C.c_void_p(stream)), "bf_eval_device")
+
+    def alloc_pinned(self, nbytes: int) -> np.ndarray:
+        p = C.c_void_p()
+        self._check(self._lib.bf_alloc_pinned(self._ctx, nbytes, C.byref(p)), "bf_alloc_pinned")
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p.value
+        return arr
+
+    def free_pinned(self, arr: np.ndarray):
+        ptr = getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
+        if ptr is not None:
+            self._check(self._lib.bf_free_pinned(self._ctx, C.c_void_p(ptr)), "bf_free_pinned")
+
+    def stats(self) -> Dict[str, int]:
+        s = A.Stats()
+        self._check(self._lib.bf_get_stats(self._ctx, C.byref(s)), "bf_get_stats")
+        return {n: getattr(s, n) for n, _ in s._fields_}

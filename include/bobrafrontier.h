@@ -1,0 +1,309 @@
+/*
+ * bobrafrontier.h — C ABI of the B200-native StoryRun DAG ready-frontier engine.
+ *
+ * This is the drop-in boundary for ONE hot path of bubustack/bobrapet: the
+ * per-reconcile "which steps are ready now?" computation
+ *
+ *     DAGReconciler.findReadySteps      internal/controller/runs/dag.go:2631-2848
+ *     buildStateMaps                    internal/controller/runs/dag.go:3358-3391
+ *     clearConcurrencyQueuedSteps       internal/controller/runs/dag.go:2020-2051
+ *     checkSyncGates/Sleep/Wait         internal/controller/runs/dag.go:1455-1547, 1217-1288, 1291-1452
+ *     checkSyncParallelSteps            internal/controller/runs/dag.go:1112-1200
+ *     group selection, fail-fast,       internal/controller/runs/dag.go:422-511, 3289-3342
+ *       compensation skipping
+ *     launch effects of Execute         internal/controller/runs/step_executor.go:132-185,
+ *                                       internal/controller/runs/dag.go:1735-1775
+ *
+ * evaluated for a whole BATCH of live StoryRuns in one pass on the GPU.  The
+ * reference has no FFI for this path (it is Go-internal); these entry points
+ * are what a cgo shim (go/frontier/frontier.go) binds.
+ *
+ * Rules of the ABI: flat PODs, caller-owned buffers, no callbacks, no C++
+ * types, never aborts, never throws; every function returns 0 or a negative
+ * bf_status.  The library retains nothing the caller passed except the
+ * topologies (copied to HBM by bf_topology_put*).
+ *
+ * Everything here is integer/bit work; results are bit-exact against the
+ * oracle (oracle/), see DESIGN.md.
+ */
+#ifndef BOBRAFRONTIER_H_
+#define BOBRAFRONTIER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_ABI_VERSION 1u
+
+/* ------------------------------------------------------------------ status */
+typedef enum bf_status {
+  BF_OK = 0,
+  BF_EINVAL = -1, /* bad argument / malformed batch                              */
+  BF_ENOMEM = -2, /* host or device allocation failed                            */
+  BF_ECUDA = -3,  /* CUDA runtime error (bf_last_error has the text)             */
+  BF_ENCCL = -4,  /* collective error (multi-GPU count exchange)                 */
+  BF_ETOPO = -5,  /* topology rejected: unknown dep, cycle, too large, bad slot  */
+  BF_ENODEV = -6  /* no usable sm_100 device / extension built without CUDA      */
+} bf_status;
+
+/* ---------------------------------------------------------- phase encoding */
+/* 4-bit code per (run, step).  Order = declaration order of enums.Phase
+ * (pkg/enums/enums.go:44-97); 0 = "no StepState entry".  Code 14 folds the
+ * "queued" bit into the nibble: phase Pending whose message starts with one of
+ * the four "Queued due to ..." prefixes (dag.go:103-108, isConcurrencyQueued
+ * dag.go:2035-2051).  It is Pending for every purpose except that
+ * clearConcurrencyQueuedSteps removes it from the running set.               */
+enum {
+  BF_PHASE_NONE = 0,
+  BF_PHASE_PENDING = 1,
+  BF_PHASE_RUNNING = 2,
+  BF_PHASE_SUCCEEDED = 3,
+  BF_PHASE_FAILED = 4,
+  BF_PHASE_FINISHED = 5,
+  BF_PHASE_CANCELED = 6,
+  BF_PHASE_COMPENSATED = 7,
+  BF_PHASE_PAUSED = 8,
+  BF_PHASE_BLOCKED = 9,
+  BF_PHASE_SCHEDULING = 10,
+  BF_PHASE_TIMEOUT = 11,
+  BF_PHASE_ABORTED = 12,
+  BF_PHASE_SKIPPED = 13,
+  BF_PHASE_PENDING_QUEUED = 14,
+  BF_PHASE_RESERVED = 15 /* invalid on input; rejected by BF_EVAL_VALIDATE */
+};
+
+/* 16-entry boolean tables over the phase code (bit v = value for code v).   */
+#define BF_LUT_TERMINAL 0x38F8u   /* Phase.IsTerminal, enums.go:101-115          */
+#define BF_LUT_COMPLETED0 0x2008u /* Succeeded|Skipped, dag.go:3377              */
+#define BF_LUT_RUNNING 0x4106u    /* Running|Pending|Paused (+queued), :3379     */
+#define BF_LUT_RUNNING_Q 0x0106u  /* ... minus concurrency-queued, :2020-2033    */
+#define BF_LUT_RT_SAT 0x410Eu     /* dependencySatisfiedForRealtime, :3457-3473  */
+
+/* ------------------------------------------------------------- step flags  */
+/* One byte per step, static per Story generation (bf_topology_put).         */
+enum {
+  BF_STEP_ENGRAM = 0, /* step.Ref != nil                         */
+  BF_STEP_CONDITION = 1,
+  BF_STEP_PARALLEL = 2,
+  BF_STEP_SLEEP = 3,
+  BF_STEP_STOP = 4,
+  BF_STEP_WAIT = 5,
+  BF_STEP_EXECUTE_STORY = 6,
+  BF_STEP_GATE = 7
+};
+#define BF_SF_TYPE_MASK 0x07u
+#define BF_SF_ALLOW_FAILURE 0x08u   /* step.AllowFailure, story_types.go:193      */
+#define BF_SF_ON_TIMEOUT_SKIP 0x10u /* with.onTimeout == "skip", dag.go:1655-1668 */
+#define BF_SF_HAS_IF 0x20u          /* step.If != nil && != "", dag.go:2741       */
+#define BF_SF_GROUP_SHIFT 6         /* 0 main (spec.steps), 1 compensations, 2 finally */
+#define BF_SF_GROUP_MASK 0xC0u
+enum { BF_GROUP_MAIN = 0, BF_GROUP_COMPENSATION = 1, BF_GROUP_FINALLY = 2, BF_GROUP_DONE = 3 };
+
+/* -------------------------------------------------------------- run flags  */
+#define BF_RF_FAIL_FAST 0x01u           /* shouldFailFast, dag.go:3504-3511             */
+#define BF_RF_REALTIME 0x02u            /* story.Spec.Pattern.IsRealtime()              */
+#define BF_RF_TOPOLOGY_TERMINATED 0x04u /* Degraded/TopologyTerminated, dag.go:436-464  */
+#define BF_RF_HOST_GROUP 0x08u          /* tier K1: group given by host, skip stage I   */
+#define BF_RF_HOST_GROUP_SHIFT 4        /* bits 4-5: BF_GROUP_* when BF_RF_HOST_GROUP   */
+
+/* ----------------------------------------------------- cond / decision codes */
+/* 2 bits per (run, step), packed 4 per byte, LSB first.                      */
+enum {
+  BF_COND_PASS = 0, /* no `if`, realtime, or evaluated true and `with` refs fresh (dag.go:2741,2837,2844) */
+  BF_COND_SKIP = 1, /* evaluated false and refs not stale (dag.go:2820-2832)                            */
+  BF_COND_HOLD = 2, /* blocked / eval error / offloaded wait / stale refs (dag.go:2801-2842)            */
+  BF_COND_FAIL = 3  /* template-safety violation or offloaded under fail policy (dag.go:2744,2810)      */
+};
+enum {
+  BF_DEC_PENDING = 0,   /* keep waiting -> Paused                                      */
+  BF_DEC_SUCCEED = 1,   /* gate approved / sleep elapsed / wait satisfied -> Succeeded  */
+  BF_DEC_FAIL = 2,      /* gate rejected / invalid config / fail policy  -> Failed      */
+  BF_DEC_TIMED_OUT = 3  /* timeout elapsed while pending -> Skipped|Timeout (dag.go:1655) */
+};
+
+/* ---------------------------------------------------------------- limits   */
+#define BF_MAX_STEPS 1024u   /* steps per topology (CRD caps at 100+50+50, story_types.go:129-140) */
+#define BF_MAX_EDGES 65535u  /* u16 row_ptr on device                                             */
+#define BF_MAX_PARALLEL 64u  /* parallel steps per topology (children_registered is a u64)        */
+#define BF_OFF_NONE 0xFFFFFFFFu
+
+/* ------------------------------------------------------------- topologies  */
+typedef struct bf_parallel_desc {
+  uint16_t step;        /* index of the `parallel` step                                       */
+  uint16_t branches;    /* B = len(with.steps), step_executor.go:745-806                      */
+  uint32_t allow_first; /* index of branch 0's bit in branch_allow_bits (bit i -> branch i)   */
+} bf_parallel_desc;
+
+typedef struct bf_topology {
+  uint32_t n_steps;                /* S: main ++ compensations ++ finally (allStorySteps, dag.go:3270) */
+  uint32_t n_edges;                /* E                                                               */
+  const uint32_t* row_ptr;         /* [S+1], row_ptr[0]=0, row_ptr[S]=E; deps of step i = col_idx[row_ptr[i]..row_ptr[i+1]) */
+  const uint16_t* col_idx;         /* [E] dependency step indices (buildDependencyGraphs, dag.go:3024-3073) */
+  const uint8_t* step_flags;       /* [S] BF_SF_*                                                     */
+  const bf_parallel_desc* parallel; /* [n_parallel], ascending by step                                */
+  uint32_t n_parallel;
+  const uint8_t* branch_allow_bits; /* branch allowFailure bits (dag.go:1145-1158); may be NULL       */
+  uint32_t n_branch_allow_bits;
+} bf_topology;
+
+/* ------------------------------------------------------------ record layout */
+/* Dynamic state travels as ONE record per run (so the host->device copy is a
+ * single contiguous transfer and the kernel stages a run with one bulk copy):
+ *
+ *   offset 0   bf_run_header (16 B)
+ *   off_phase  phase nibbles, step i at byte i/2, low nibble first  (words*16 B)
+ *   off_cond   cond codes, 2 bits, step i at byte i/4               (words*8 B)  optional
+ *   off_decision decision codes, same packing                        (words*8 B)  optional
+ *   off_child  child StepRun phase nibbles of parallel steps, desc p starts at
+ *              nibble child_first[p] (assigned by bf_topology_put; branch order) optional
+ *
+ * Results likewise, one record per run:
+ *
+ *   offset 0   bf_result_header (16 B)
+ *   off_ready / off_skip / off_fail / off_needs_cond / off_skip_dep  bit masks,
+ *              step i = bit (i%32) of u32 word i/32  (words*4 B each)
+ *   off_phase_out  phase nibbles after this pass's status mutations  (words*16 B)
+ *
+ * All strides are multiples of 16 bytes.                                      */
+typedef struct bf_run_header {
+  uint32_t topo_slot;           /* from bf_topology_put                                          */
+  uint8_t run_flags;            /* BF_RF_*                                                       */
+  uint8_t reserved[3];
+  uint64_t children_registered; /* bit p: PrimitiveChildren[parallel p] non-empty, dag.go:1140   */
+} bf_run_header;
+
+typedef struct bf_result_header {
+  uint32_t summary;      /* BF_SUM_*                                                             */
+  uint32_t n_ready;      /* popcount(ready)                                                      */
+  uint32_t n_skip;       /* popcount(skip)                                                       */
+  uint32_t n_expansion;  /* child StepRuns to create for ready `parallel` steps                   */
+} bf_result_header;
+
+#define BF_SUM_GROUP_MASK 0x3u       /* BF_GROUP_* evaluated this pass (3 = finalize on host, dag.go:490-495) */
+#define BF_SUM_MAIN_DONE 0x4u        /* dag.go:431                                                        */
+#define BF_SUM_MAIN_FAILED 0x8u      /* len(mainFailed) > 0                                               */
+#define BF_SUM_COMP_DONE 0x10u
+#define BF_SUM_FINAL_DONE 0x20u
+#define BF_SUM_COMP_FAILED 0x40u
+#define BF_SUM_FINAL_FAILED 0x80u
+#define BF_SUM_PHASE_CHANGED 0x100u  /* some phase nibble was rewritten (needsPersist, dag.go:409-470)    */
+#define BF_SUM_ITER_SHIFT 16         /* bits 16-27: iterations run (fixpoint mode), dag.go:393            */
+
+/* field selection for bf_layout_init */
+#define BF_F_COND 0x1u
+#define BF_F_DECISION 0x2u
+#define BF_F_CHILD 0x4u
+#define BF_F_OUT_FAIL 0x10u
+#define BF_F_OUT_NEEDS_COND 0x20u
+#define BF_F_OUT_SKIP_DEP 0x40u
+#define BF_F_OUT_PHASE 0x80u
+
+typedef struct bf_layout {
+  uint32_t steps_max; /* max S over the topologies of the batch                      */
+  uint32_t words;     /* ceil(steps_max/32)                                          */
+  uint32_t fields;    /* BF_F_*                                                      */
+  uint32_t child_nibbles;
+  uint32_t state_stride;
+  uint32_t off_phase, off_cond, off_decision, off_child;
+  uint32_t result_stride;
+  uint32_t off_ready, off_skip, off_fail, off_needs_cond, off_skip_dep, off_phase_out;
+} bf_layout;
+
+/* ------------------------------------------------------------------ batch  */
+#define BF_EVAL_VALIDATE 0x1u   /* host API only: check slots / reserved nibbles before launch   */
+#define BF_EVAL_FIXPOINT 0x2u   /* iterate runDagIterations on device (dag.go:393-540), applying
+                                   launch effects of instantly-completing primitives             */
+#define BF_EVAL_EXPANSION 0x4u  /* emit (run, step, branch) tuples for ready parallel steps      */
+#define BF_EVAL_NO_COUNTS 0x8u  /* skip the global counters                                      */
+
+typedef struct bf_expansion {
+  uint32_t run;    /* index in the batch                      */
+  uint16_t step;   /* the parallel step                       */
+  uint16_t branch; /* branch index in with.steps              */
+} bf_expansion;
+
+typedef struct bf_counts {
+  uint64_t ready;     /* sum n_ready over the batch                                   */
+  uint64_t skip;      /* sum n_skip                                                   */
+  uint64_t expansion; /* sum n_expansion                                              */
+  uint64_t evals;     /* (run, step) pairs visited = sum of S over runs (dag.go:2647) */
+} bf_counts;
+
+typedef struct bf_batch {
+  uint32_t struct_size; /* sizeof(bf_batch)                                            */
+  uint32_t n_runs;
+  uint32_t flags;       /* BF_EVAL_*                                                   */
+  uint32_t max_iterations; /* fixpoint cap; 0 = S+1 (dag.go:393)                        */
+  bf_layout layout;
+  const void* state;    /* [n_runs * state_stride]                                     */
+  void* result;         /* [n_runs * result_stride]                                    */
+  bf_expansion* expansion; /* [expansion_cap], run-major/step/branch order; may be NULL */
+  uint64_t expansion_cap;
+  bf_counts* counts;    /* out; may be NULL                                            */
+} bf_batch;
+
+/* ------------------------------------------------------------------- ctx   */
+typedef struct bf_ctx bf_ctx;
+
+typedef struct bf_config {
+  uint32_t struct_size;
+  int32_t device;          /* CUDA ordinal; one ctx drives one GPU (one process per GPU) */
+  uint64_t arena_bytes;    /* initial topology arena in HBM (grows on demand); 0 = default */
+  uint32_t max_topologies; /* initial slot table size; 0 = default                       */
+  uint32_t flags;
+} bf_config;
+
+uint32_t bf_abi_version(void);
+const char* bf_strerror(int status);
+/* Last error text of this ctx (valid until the next call on the ctx). */
+const char* bf_last_error(const bf_ctx* ctx);
+
+int bf_create(bf_ctx** out, const bf_config* cfg);
+void bf_destroy(bf_ctx* ctx);
+
+/* Upload one topology; returns its slot in *slot_out.  Validates what
+ * validateRuntimeDependencyGraph (dag.go:3076-3146) validates: every col_idx
+ * < S (no unknown dep) and acyclicity (Kahn), else BF_ETOPO.                  */
+int bf_topology_put(bf_ctx* ctx, const bf_topology* topo, uint32_t* slot_out);
+/* Bulk form: `count` topologies, one bf_topology each; slots_out[count].      */
+int bf_topology_put_many(bf_ctx* ctx, const bf_topology* topos, uint32_t count, uint32_t* slots_out);
+int bf_topology_drop(bf_ctx* ctx, uint32_t slot);
+/* Nibble offset of parallel desc p's children inside the child area.          */
+int bf_topology_child_first(const bf_ctx* ctx, uint32_t slot, uint32_t* child_first_out, uint32_t cap);
+
+int bf_layout_init(bf_layout* out, uint32_t steps_max, uint32_t child_nibbles, uint32_t fields);
+
+/* Synchronous pass over HOST buffers: H2D(state) -> kernels -> D2H(result),
+ * returns when result/expansion/counts are filled.  Thread-safe per ctx.      */
+int bf_eval(bf_ctx* ctx, const bf_batch* batch);
+
+/* Asynchronous pass over DEVICE buffers on `stream` (a cudaStream_t): state,
+ * result, expansion and counts are device pointers; nothing is synchronised.
+ * counts must be zeroed by the caller unless BF_EVAL_NO_COUNTS (the library
+ * only adds).                                                                 */
+int bf_eval_device(bf_ctx* ctx, const bf_batch* batch, void* stream);
+
+/* Pinned host memory for batches (cgo: memory with no Go pointers).           */
+int bf_alloc_pinned(bf_ctx* ctx, size_t bytes, void** out);
+int bf_free_pinned(bf_ctx* ctx, void* p);
+
+/* Introspection used by bench/roofline accounting.                            */
+typedef struct bf_stats {
+  uint64_t kernel_launches;   /* kernels launched by this ctx so far            */
+  uint64_t arena_used_bytes;  /* HBM bytes of topology records                  */
+  uint64_t arena_cap_bytes;
+  uint32_t n_topologies;
+  uint32_t sm_count;
+  uint32_t last_grid, last_block, last_smem_bytes, last_stages;
+} bf_stats;
+int bf_get_stats(const bf_ctx* ctx, bf_stats* out);
+/* Device address + byte size of a topology record (for traffic accounting).   */
+int bf_topology_record(const bf_ctx* ctx, uint32_t slot, uint64_t* dev_addr, uint32_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOBRAFRONTIER_H_ */
