@@ -299,6 +299,13 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   P.off_decision = L.off_decision; P.off_child = L.off_child;
   P.result_stride = L.result_stride; P.off_ready = L.off_ready; P.off_skip = L.off_skip; P.off_fail = L.off_fail;
   P.off_needs_cond = L.off_needs_cond; P.off_skip_dep = L.off_skip_dep; P.off_phase_out = L.off_phase_out;
+  {
+    uint32_t tail = (uint32_t)sizeof(bf_result_header);
+    auto upd = [&](uint32_t off, uint32_t len) { if (off != BF_OFF_NONE && off + len > tail) tail = off + len; };
+    upd(L.off_ready, L.words * 4); upd(L.off_skip, L.words * 4); upd(L.off_fail, L.words * 4);
+    upd(L.off_needs_cond, L.words * 4); upd(L.off_skip_dep, L.words * 4); upd(L.off_phase_out, L.words * 16);
+    P.result_tail = tail;
+  }
 
   const bool want_exp = (b.flags & BF_EVAL_EXPANSION) && d_exp != nullptr;
   if (want_exp) {
@@ -311,7 +318,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   // ---- shared-memory plan ----
   P.topo_buf_bytes = round_up(c->max_rec_bytes, 16);
   P.stage_bytes = L.state_stride + P.topo_buf_bytes;
-  P.work_bytes = round_up(84 * L.words, 16);
+  P.work_bytes = round_up(52 * L.words, 16) + round_up(32 * L.words, 16);
   const uint32_t budget = 227u * 1024u - 128u;
   uint32_t best_st = 0, best_wpb = 0, best_score = 0;
   const char* env_st = getenv("BF_STAGES");

@@ -64,6 +64,7 @@ struct KParams {
   // layout (bf_layout)
   uint32_t words;
   uint32_t state_stride, off_phase, off_cond, off_decision, off_child;
+  uint32_t result_tail;         // first byte after the last result field (padding up to the stride is zeroed)
   uint32_t result_stride, off_ready, off_skip, off_fail, off_needs_cond, off_skip_dep, off_phase_out;
   // shared-memory plan
   uint32_t stages;

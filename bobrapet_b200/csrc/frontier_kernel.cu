@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
     uint32_t* mCAND = mFD + P.words;
     uint32_t* mREADY = mCAND + P.words;
     uint32_t* mFAIL = mREADY + P.words;
-    uint8_t* st = reinterpret_cast<uint8_t*>(mFAIL + P.words);
+    uint8_t* st = reinterpret_cast<uint8_t*>(work) + ((52u * P.words + 15u) & ~15u);  // 13 word arrays above
 
     // ---------------- stage A: transpose packed codes into bit planes ----------------
     {
@@ -559,6 +559,7 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
         po[m] = w;
       }
     }
+    for (uint32_t x = P.result_tail / 4 + lane; x < P.result_stride / 4; x += 32) reinterpret_cast<uint32_t*>(rr)[x] = 0u;
     tot_ready += n_ready; tot_skip += n_skip; tot_exp += n_exp; tot_evals += S;
 
     __syncwarp();  // every lane is done with this stage's buffers

@@ -1,0 +1,148 @@
+"""GPU parity: the CUDA path (through the C ABI, bf_eval) vs the packed oracle, bit for bit.
+
+Every comparison is on whole result records (header + every mask + phase_out), so a single
+wrong bit anywhere fails.  Integer/bit work: the bar is exact equality.
+"""
+import numpy as np
+import pytest
+
+from bobrapet_b200 import _abi as A
+from bobrapet_b200 import Frontier, synth
+from bobrapet_b200.records import make_layout, unpack_result
+from oracle import packed as PK
+from tests import randgen
+
+pytestmark = pytest.mark.gpu
+
+ALL = A.F_COND | A.F_DECISION | A.F_ALL_OUT
+
+
+@pytest.fixture(scope="module")
+def fr():
+    f = Frontier(0)
+    yield f
+    f.close()
+
+
+def _compare(fr, ts, slots, L, state, flags=0, max_iter=0, expansion=False):
+    pt = PK.PackedTopologies(ts, slots)
+    want, wcounts = PK.evaluate(pt, L, state, flags, max_iter, threads=8)
+    if expansion:
+        cap = int(wcounts["expansion"]) + 8
+        got, gcounts, gexp = fr.eval(L, state, flags=flags | A.EVAL_EXPANSION | A.EVAL_VALIDATE, max_iterations=max_iter,
+                                     expansion_cap=cap)
+        wexp, n = PK.expand(pt, L, state, want, cap)
+        assert n == wcounts["expansion"] == gcounts["expansion"]
+        assert np.array_equal(gexp, wexp), "expansion tuples differ"
+    else:
+        got, gcounts = fr.eval(L, state, flags=flags | A.EVAL_VALIDATE, max_iterations=max_iter)
+    if not np.array_equal(got, want):
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        r = int(bad[0])
+        S = int(ts.S.max())
+        g, w = unpack_result(L, got[r:r + 1], S), unpack_result(L, want[r:r + 1], S)
+        diff = {k: (g[k][0], w[k][0]) for k in g if not np.array_equal(g[k], w[k])}
+        raise AssertionError("%d/%d runs differ; first run %d: %s" % (len(bad), len(got), r, {k: (np.nonzero(np.atleast_1d(a != b))[0][:8], a, b) for k, (a, b) in diff.items()}))
+    assert gcounts == wcounts
+    return got
+
+
+def test_child_first_rule_matches_library(fr):
+    rng = np.random.default_rng(5)
+    ts = randgen.random_topologies(rng, 40, 1, 300)
+    slots = fr.put_topologies(ts)
+    cfs, _ = randgen.child_layout(ts)
+    for t in range(ts.count):
+        assert np.array_equal(fr.child_first(int(slots[t])), cfs[t])
+
+
+@pytest.mark.parametrize("cfg,n,S", [(2, 3000, 64), (3, 3000, 256), (4, 3000, 256), (5, 600, 1024),
+                                     (3, 500, 1), (3, 500, 2), (3, 500, 31), (3, 500, 32), (3, 500, 33),
+                                     (3, 500, 100), (4, 500, 200), (3, 300, 1000), (4, 300, 1023)])
+def test_synthetic_configs(fr, cfg, n, S):
+    ts = synth.topologies(cfg, 0, n, S)
+    slots = fr.put_topologies(ts)
+    pt = PK.PackedTopologies(ts, slots)
+    fields = ALL if cfg in (4, 5) else A.F_ALL_OUT
+    child = pt.max_child_nibbles()
+    L = make_layout(S, child, fields | (A.F_CHILD if child else 0))
+    cf = fr.child_first(int(slots[0])) if child else None
+    state = synth.state(cfg, 0, n, L, slots, ts, cf)
+    got = _compare(fr, ts, slots, L, state, expansion=(cfg == 5))
+    out = unpack_result(L, got, S)
+    assert out["ready"].any() or S < 3
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("mode", ["single", "fixpoint"])
+def test_random_adversarial(fr, seed, mode):
+    rng = np.random.default_rng(1000 + seed)
+    smax = [40, 257, 1024, 96, 600, 33][seed]
+    ts = randgen.random_topologies(rng, 60, 1, smax)
+    slots = fr.put_topologies(ts)
+    L, state, _ = randgen.random_state(rng, ts, slots, 4000, ALL, phase_mix=("any" if seed % 2 else "progress"))
+    _compare(fr, ts, slots, L, state, flags=(A.EVAL_FIXPOINT if mode == "fixpoint" else 0), expansion=True)
+
+
+def test_minimal_layout_outputs_only_ready_skip(fr):
+    rng = np.random.default_rng(77)
+    ts = randgen.random_topologies(rng, 30, 5, 200, parallel=False)
+    slots = fr.put_topologies(ts)
+    L, state, _ = randgen.random_state(rng, ts, slots, 2000, 0)
+    _compare(fr, ts, slots, L, state)
+
+
+def test_shared_topology_mode(fr):
+    """D << N: many runs per topology (records come from L2 instead of HBM)."""
+    ts = synth.topologies(3, 0, 8, 256)
+    slots = fr.put_topologies(ts)
+    n = 5000
+    L = make_layout(256, 0, A.F_ALL_OUT)
+    big = synth.topologies(3, 0, n, 256)  # only for flags-shaped state generation
+    state = synth.state(3, 0, n, L, np.asarray(slots)[np.arange(n) % 8], big)
+    # state was generated against `big`'s flags; for cfg 3 flags only carry allowFailure, which state ignores
+    _compare(fr, ts, slots, L, state)
+
+
+def test_invalid_slot_yields_marked_empty_result(fr):
+    ts = synth.topologies(3, 0, 4, 64)
+    slots = fr.put_topologies(ts)
+    L = make_layout(64, 0, 0)
+    state = synth.state(3, 0, 4, L, slots, ts)
+    state[2, 0:4] = np.frombuffer(np.uint32(0x7FFFFFF0).tobytes(), np.uint8)
+    with pytest.raises(A.FrontierError):
+        fr.eval(L, state, flags=A.EVAL_VALIDATE)
+    got, _ = fr.eval(L, state)   # without validation the kernel marks the run and carries on
+    hdr = got[:, 0:4].view("<u4")[:, 0]
+    assert hdr[2] == 0xFFFFFFFF and not got[2, 16:].any()
+    assert hdr[0] != 0xFFFFFFFF
+
+
+def test_topology_rejections(fr):
+    from bobrapet_b200.frontier import TopologySet
+    cyc = TopologySet([2], [2], [0, 1, 2], [1, 0], [0, 0])
+    with pytest.raises(A.FrontierError) as e:
+        fr.put_topologies(cyc)
+    assert e.value.status == A.BF_ETOPO and "cycle" in str(e.value)          # dag_test.go:321
+    selfloop = TopologySet([1], [1], [0, 1], [0], [0])
+    with pytest.raises(A.FrontierError):
+        fr.put_topologies(selfloop)
+    unknown = TopologySet([2], [1], [0, 0, 1], [7], [0, 0])
+    with pytest.raises(A.FrontierError) as e:
+        fr.put_topologies(unknown)
+    assert "unknown step dependency" in str(e.value)                          # dag_test.go:206
+
+
+def test_drop_and_reuse_slot(fr):
+    ts = synth.topologies(3, 100, 3, 64)
+    slots = fr.put_topologies(ts)
+    fr.drop_topology(int(slots[1]))
+    ts2 = synth.topologies(3, 200, 1, 64)
+    s2 = fr.put_topologies(ts2)
+    assert int(s2[0]) == int(slots[1])
+    L = make_layout(64, 0, A.F_ALL_OUT)
+    state = synth.state(3, 200, 1, L, s2, ts2)
+    pt = PK.PackedTopologies(ts2, s2)
+    want, _ = PK.evaluate(pt, L, state)
+    got, _ = fr.eval(L, state)
+    assert np.array_equal(got, want)
