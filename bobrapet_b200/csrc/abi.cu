@@ -22,7 +22,7 @@ namespace bf {
 cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, unsigned long long* offsets,
                              bf_expansion* out, unsigned long long cap, cudaStream_t stream, uint32_t* launches);
-int frontier_max_blocks_per_sm(uint32_t threads, uint32_t smem_bytes);
+int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
 }  // namespace bf
 
 namespace {
@@ -57,6 +57,7 @@ struct bf_ctx {
   bool slots_dirty = true;
   uint32_t max_rec_bytes = 0;
   uint32_t n_alive = 0;
+  uint32_t n_with_parallel = 0;  // live topologies that have parallel steps
 
   // host-API staging
   uint8_t* d_state = nullptr; size_t d_state_cap = 0;
@@ -67,6 +68,10 @@ struct bf_ctx {
   uint32_t* d_exp_counts = nullptr; size_t d_exp_counts_cap = 0;
   unsigned long long* d_offsets = nullptr; size_t d_offsets_cap = 0;
   unsigned long long* d_block_sums = nullptr; size_t d_block_sums_cap = 0;
+
+  // cached shared-memory plan (recomputed when the layout or the largest record changes)
+  uint32_t plan_key_stride = 0, plan_key_words = 0, plan_key_rec = 0, plan_key_variant = 0xFFFFFFFFu;
+  uint32_t plan_stages = 0, plan_wpb = 0, plan_per_sm = 0;
 
   bf_stats stats{};
 };
@@ -181,7 +186,12 @@ void build_record(const bf_topology& t, const RecPlan& p, uint8_t* rec) {
   memset(rec, 0, p.rec_bytes);
   const uint32_t S = t.n_steps, E = t.n_edges, W = p.W;
   bf::TopoHeader h{};
-  h.S = (uint16_t)S; h.W = (uint16_t)W; h.E = (uint16_t)E; h.P = (uint16_t)t.n_parallel;
+  h.S = (uint16_t)S; h.W = (uint16_t)W; h.P = (uint16_t)t.n_parallel;
+  {
+    uint32_t md = 0;
+    for (uint32_t i = 0; i < S; ++i) { const uint32_t d = t.row_ptr[i + 1] - t.row_ptr[i]; if (d > md) md = d; }
+    h.max_deg = (uint16_t)(md > 0xFFFF ? 0xFFFF : md);
+  }
   h.child_nibbles = (uint16_t)p.child_nibbles;
   h.off_col = p.off_col; h.off_planes = p.off_planes; h.off_par = p.off_par; h.rec_bytes = p.rec_bytes;
   uint16_t* rp = reinterpret_cast<uint16_t*>(rec + sizeof(bf::TopoHeader));
@@ -294,6 +304,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   P.counts = (b.flags & BF_EVAL_NO_COUNTS) ? nullptr : d_counts;
   P.n_slots = (uint32_t)c->slots_host.size();
   P.n_runs = b.n_runs; P.flags = b.flags; P.max_iter = b.max_iterations;
+  P.any_parallel = c->n_with_parallel != 0;
   P.words = L.words;
   P.state_stride = L.state_stride; P.off_phase = L.off_phase; P.off_cond = L.off_cond;
   P.off_decision = L.off_decision; P.off_child = L.off_child;
@@ -318,32 +329,42 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   // ---- shared-memory plan ----
   P.topo_buf_bytes = round_up(c->max_rec_bytes, 16);
   P.stage_bytes = L.state_stride + P.topo_buf_bytes;
-  P.work_bytes = round_up(52 * L.words, 16) + round_up(32 * L.words, 16);
-  const uint32_t budget = 227u * 1024u - 128u;
-  uint32_t best_st = 0, best_wpb = 0, best_score = 0;
-  const char* env_st = getenv("BF_STAGES");
-  const char* env_w = getenv("BF_WARPS");
-  for (uint32_t st = 8; st >= 1; --st) {
-    if (env_st && (uint32_t)atoi(env_st) != st) continue;
-    const uint32_t per_warp = st * P.stage_bytes + P.work_bytes + 64;
-    uint32_t wpb = budget / per_warp;
-    if (wpb > 16) wpb = 16;
-    if (env_w && (uint32_t)atoi(env_w) < wpb) wpb = (uint32_t)atoi(env_w);
-    if (wpb == 0) continue;
-    // enough bytes in flight to cover HBM latency (Little: ~45 KB/SM), then as many warps as fit
-    uint32_t inflight_kb = wpb * (st - 1) * P.stage_bytes / 1024u;
-    if (inflight_kb > 96) inflight_kb = 96;
-    const uint32_t score = inflight_kb + wpb * 8 + (st <= 4 ? 1 : 0);
-    if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; }
+  P.work_bytes = round_up(4 * L.words, 16) + 32 * L.words + 16;  // mFAIL words + status bytes (+ clamp guard)
+  const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | (L.fields << 16);
+  if (c->plan_wpb == 0 || c->plan_key_stride != L.state_stride || c->plan_key_words != L.words ||
+      c->plan_key_rec != c->max_rec_bytes || c->plan_key_variant != variant) {
+    const uint32_t budget = 227u * 1024u - 128u;
+    uint32_t best_st = 0, best_wpb = 0, best_score = 0;
+    const char* env_st = getenv("BF_STAGES");
+    const char* env_w = getenv("BF_WARPS");
+    for (uint32_t st = 8; st >= 1; --st) {
+      if (env_st && (uint32_t)atoi(env_st) != st) continue;
+      const uint32_t per_warp = st * P.stage_bytes + P.work_bytes + 64;
+      uint32_t wpb = budget / per_warp;
+      if (wpb > 16) wpb = 16;
+      if (env_w && (uint32_t)atoi(env_w) < wpb) wpb = (uint32_t)atoi(env_w);
+      if (wpb == 0) continue;
+      // enough bytes in flight to cover HBM latency (Little: ~45 KB/SM), then as many warps as fit
+      uint32_t inflight_kb = wpb * (st - 1) * P.stage_bytes / 1024u;
+      if (inflight_kb > 96) inflight_kb = 96;
+      const uint32_t score = inflight_kb + wpb * 8 + (st <= 4 ? 1 : 0);
+      if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; }
+    }
+    if (best_wpb == 0) return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
+    const uint32_t smem_try = 128 + best_wpb * (best_st * P.stage_bytes + P.work_bytes + 64);
+    int per_sm_q = bf::frontier_max_blocks_per_sm(P, best_wpb * 32, smem_try);
+    if (per_sm_q < 1) per_sm_q = 1;
+    const char* env_b = getenv("BF_BLOCKS_PER_SM");
+    if (env_b && atoi(env_b) >= 1 && atoi(env_b) < per_sm_q) per_sm_q = atoi(env_b);
+    c->plan_stages = best_st; c->plan_wpb = best_wpb; c->plan_per_sm = (uint32_t)per_sm_q;
+    c->plan_key_stride = L.state_stride; c->plan_key_words = L.words; c->plan_key_rec = c->max_rec_bytes;
+    c->plan_key_variant = variant;
   }
-  if (best_wpb == 0) return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
+  const uint32_t best_st = c->plan_stages, best_wpb = c->plan_wpb;
+  const int per_sm = (int)c->plan_per_sm;
   P.stages = best_st;
   P.warps_per_block = best_wpb;
   const uint32_t smem = 128 + best_wpb * (best_st * P.stage_bytes + P.work_bytes + 64);
-  int per_sm = bf::frontier_max_blocks_per_sm(best_wpb * 32, smem);
-  if (per_sm < 1) per_sm = 1;
-  const char* env_b = getenv("BF_BLOCKS_PER_SM");
-  if (env_b && atoi(env_b) >= 1 && atoi(env_b) < per_sm) per_sm = atoi(env_b);
   uint32_t grid = (uint32_t)c->sm_count * (uint32_t)per_sm;
   const uint32_t need_blocks = (b.n_runs + best_wpb - 1) / best_wpb;
   if (grid > need_blocks) grid = need_blocks ? need_blocks : 1;
@@ -394,6 +415,7 @@ int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_
     off += plans[i].rec_bytes;
     slots_out[i] = slot;
     c->n_alive++;
+    if (m.P) c->n_with_parallel++;
   }
   c->arena_used = base + total;
   c->slots_dirty = true;
@@ -475,6 +497,7 @@ int bf_topology_drop(bf_ctx* c, uint32_t slot) {
   std::lock_guard<std::mutex> g(c->mu);
   if (slot >= c->meta.size() || !c->meta[slot].alive) return fail(c, BF_ETOPO, "drop of an unknown slot");
   c->meta[slot].alive = false;
+  if (c->meta[slot].P) c->n_with_parallel--;
   c->slots_host[slot] = bf::Slot{0, 0, 0};
   c->free_slots.push_back(slot);
   c->n_alive--;
@@ -556,9 +579,9 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
       if (m.S > L.steps_max) return fail(c, BF_EINVAL, "run " + std::to_string(r) + ": topology larger than layout.steps_max");
       if (L.off_child != BF_OFF_NONE && m.child_nibbles > L.child_nibbles)
         return fail(c, BF_EINVAL, "run " + std::to_string(r) + ": child area too small");
-      const uint8_t* ph = reinterpret_cast<const uint8_t*>(h) + L.off_phase;
-      for (uint32_t i = 0; i < m.S; ++i)
-        if (((ph[i >> 1] >> ((i & 1u) * 4u)) & 0xFu) == BF_PHASE_RESERVED)
+      const uint32_t* ph = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(h) + L.off_phase);
+      for (uint32_t w = 0; w < (m.S + 31) / 32; ++w)
+        if (ph[w] & ph[L.words + w] & ph[2 * L.words + w] & ph[3 * L.words + w])
           return fail(c, BF_EINVAL, "run " + std::to_string(r) + ": reserved phase code 15");
     }
   }

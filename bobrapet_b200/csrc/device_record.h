@@ -22,7 +22,7 @@ namespace bf {
 struct TopoHeader {
   uint16_t S;          // steps
   uint16_t W;          // ceil(S/32)
-  uint16_t E;          // edges
+  uint16_t max_deg;    // largest in-degree (the kernel's straight-line walk covers <= 4; E = row_ptr[S])
   uint16_t P;          // parallel descs
   uint16_t n_main, n_comp, n_final;
   uint16_t child_nibbles;  // total child nibbles of all descs
@@ -61,6 +61,7 @@ struct KParams {
   uint32_t n_runs;
   uint32_t flags;               // BF_EVAL_*
   uint32_t max_iter;
+  uint32_t any_parallel;        // some live topology has `parallel` steps (selects the CH kernel variants)
   // layout (bf_layout)
   uint32_t words;
   uint32_t state_stride, off_phase, off_cond, off_decision, off_child;

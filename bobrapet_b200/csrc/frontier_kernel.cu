@@ -11,13 +11,16 @@
 // bit planes (one u32 word = 32 steps), after which every classification of
 // buildStateMaps (dag.go:3358-3391), the gate/sleep/wait rewrite (dag.go:1455-1547),
 // fail-fast / compensation marking and group selection (dag.go:422-511) are a
-// handful of LOP3s per 32 steps, held by lanes 0..W-1.  The dependency walk of
-// findReadySteps (dag.go:2711-2733) then runs one step per lane over the CSR row in
-// shared memory against a per-step status byte, and __ballot_sync folds the 32
-// per-step verdicts of a trip straight into one word of the ready / skip bit masks.
+// handful of LOP3s per 32 steps, held by lanes 0..W-1, and the per-run reductions of
+// group selection are ONE redux.or.  The dependency walk of findReadySteps
+// (dag.go:2711-2733) then runs one step per lane over the CSR row in shared memory
+// against a per-step status byte, and __ballot_sync folds the 32 per-step verdicts of a
+// trip straight into one word of the ready / skip bit masks.
 //
-// Integer only; no tensor cores.  HBM-bound: ~3 KB in, 80 B out per run at the
-// BASELINE configuration.  See DESIGN.md for the roofline accounting.
+// The kernel is compiled in 16 variants <CD, CH, FX, XO> (cond/decision codes present,
+// parallel steps present, device fixpoint, extra outputs) so the common pass carries
+// no dead work.  Integer only; no tensor cores.  HBM-bound: ~3 KB in, 80 B out per run
+// at the BASELINE configuration.  See DESIGN.md for the roofline accounting.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -26,17 +29,18 @@
 
 namespace bf {
 
+#define DI __device__ __forceinline__
+constexpr uint32_t FULL = 0xffffffffu;
+
 // ------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+DI uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+DI void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+DI void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+DI uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -47,118 +51,123 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+DI void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+DI void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
+DI void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 template <int IMM>
-__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+DI uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r;
   asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(IMM));
   return r;
 }
 // 16-entry boolean table over a bit-sliced 4-bit code: 3 LOP3 for 32 steps.
 template <uint32_t T16>
-__device__ __forceinline__ uint32_t plut(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
+DI uint32_t plut(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
   const uint32_t lo = lop3<(T16 & 0xFF)>(p2, p1, p0);
   const uint32_t hi = lop3<((T16 >> 8) & 0xFF)>(p2, p1, p0);
   return lop3<0xCA>(p3, hi, lo);  // p3 ? hi : lo
 }
 // set the code of the steps in mask m to the constant CODE
 template <int CODE>
-__device__ __forceinline__ void pset(uint32_t m, uint32_t& p0, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+DI void pset(uint32_t m, uint32_t& p0, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
   p0 = (CODE & 1) ? (p0 | m) : (p0 & ~m);
   p1 = (CODE & 2) ? (p1 | m) : (p1 & ~m);
   p2 = (CODE & 4) ? (p2 | m) : (p2 & ~m);
   p3 = (CODE & 8) ? (p3 | m) : (p3 & ~m);
 }
-
-// gather bits 0,4,8,..,28 of x into the low byte
-__device__ __forceinline__ uint32_t squeeze4(uint32_t x) {
+DI uint32_t squeeze4(uint32_t x) {  // bits 0,4,..,28 -> low byte
   x = (x | (x >> 3)) & 0x03030303u;
   x = (x | (x >> 6)) & 0x000F000Fu;
   x = (x | (x >> 12)) & 0xFFu;
   return x;
 }
-// gather bits 0,2,4,..,30 of x into the low half
-__device__ __forceinline__ uint32_t squeeze2(uint32_t x) {
+DI uint32_t squeeze2(uint32_t x) {  // bits 0,2,..,30 -> low half
   x = (x | (x >> 1)) & 0x33333333u;
   x = (x | (x >> 2)) & 0x0F0F0F0Fu;
   x = (x | (x >> 4)) & 0x00FF00FFu;
   x = (x | (x >> 8)) & 0xFFFFu;
   return x;
 }
-// inverse of squeeze4: byte -> bits 0,4,..,28
-__device__ __forceinline__ uint32_t spread4(uint32_t x) {
+DI uint32_t spread4(uint32_t x) {  // inverse of squeeze4
   x = (x | (x << 12)) & 0x000F000Fu;
   x = (x | (x << 6)) & 0x03030303u;
   x = (x | (x << 3)) & 0x11111111u;
   return x;
 }
-// low nibble -> one 0/1 byte per bit
-__device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
-
-__device__ __forceinline__ uint32_t get_nibble(const uint8_t* base, uint32_t i) {
-  uint32_t v = (base[i >> 1] >> ((i & 1u) * 4u)) & 0xFu;
+DI uint32_t bits4_to_bytes(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }  // 4 bits -> 4 0/1 bytes
+DI uint32_t get_nibble(const uint8_t* base, uint32_t i) {
+  const uint32_t v = (base[i >> 1] >> ((i & 1u) * 4u)) & 0xFu;
   return v == 15u ? 0u : v;
 }
+DI uint32_t redux_or(uint32_t v) { return __reduce_or_sync(FULL, v); }
+DI uint32_t redux_add(uint32_t v) { return __reduce_add_sync(FULL, v); }
 
-struct RunCtx {
-  uint32_t lane;
-  uint32_t Wt;      // words of this topology
-  uint32_t S;
-  const uint8_t* sr;  // state record (smem)
-  const uint8_t* tr;  // topology record (smem)
-  const uint16_t* row_ptr;
-  const uint16_t* col;
-  uint8_t* st;       // status bytes [32*Wt]
-};
+// ------------------------------------------------------------------ stage D
+// One step per lane per trip over the CSR rows of the candidate steps, visiting only the
+// 32-step words that hold a candidate.  Status byte of a dependency: bit0 = not satisfied,
+// bit1 = failed dependency.  The first four deps of a row are fetched branch-free (index
+// clamped into the status array, verdict masked by the row length); longer rows exist only
+// when the topology header says so.  FIXUP adds the "set Failed earlier in this same loop"
+// visibility rule (dag.go:2744/2810 mutate stepStates while `completed` stays as built at :497).
+DI uint32_t bmsk_clamp(uint32_t pos, uint32_t width) {
+  uint32_t r;
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(pos), "r"(width));
+  return r;
+}
 
-// Stage D: one step per lane per trip; returns via smem words.  FIXUP adds the
-// "Failed earlier in this same loop" visibility rule (dag.go:2744/2810 mutate
-// stepStates while `completed` stays as built at :497).
 template <bool FIXUP>
-__device__ __forceinline__ void walk_deps(const RunCtx& c, const uint32_t* mCAND, const uint32_t* mFAIL,
-                                          uint32_t failed_class, uint32_t& met_w, uint32_t& fd_w) {
+DI void walk_deps(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_deg, const uint16_t* __restrict__ row_ptr,
+                  const uint16_t* __restrict__ col, const uint8_t* __restrict__ st, const uint32_t* mFAIL,
+                  uint32_t failed_class, uint32_t& met_w, uint32_t& fd_w) {
   met_w = 0;
   fd_w = 0;
-  for (uint32_t j = 0; j < c.Wt; ++j) {
-    const uint32_t candw = mCAND[j];
-    if (candw == 0) continue;  // warp-uniform
-    const uint32_t i = j * 32 + c.lane;
-    const bool cand = (candw >> c.lane) & 1u;
-    uint32_t acc = 0;
+  uint32_t todo = __ballot_sync(FULL, CAND != 0);  // words with at least one candidate step
+  while (todo) {
+    const uint32_t j = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t candw = __shfl_sync(FULL, CAND, j);
+    const bool cand = (candw >> lane) & 1u;
+    const uint32_t i = j * 32 + lane;
+    uint32_t e0 = 0, n = 0;
     if (cand) {
-      uint32_t e = c.row_ptr[i];
-      const uint32_t e1 = c.row_ptr[i + 1];
-      if (!FIXUP) {
-        for (; e + 4 <= e1; e += 4) {
-          const uint32_t a = c.col[e], b = c.col[e + 1], cc = c.col[e + 2], d = c.col[e + 3];
-          acc |= c.st[a] | c.st[b] | c.st[cc] | c.st[d];
-        }
-        for (; e < e1; ++e) acc |= c.st[c.col[e]];
-      } else {
-        for (; e < e1; ++e) {
-          const uint32_t d = c.col[e];
-          uint32_t s = c.st[d];
-          if (d < i && ((mFAIL[d >> 5] >> (d & 31u)) & 1u)) s = failed_class;
-          acc |= s;
-        }
-      }
+      e0 = row_ptr[i];
+      n = row_ptr[i + 1] - e0;
     }
-    const uint32_t fdb = __ballot_sync(0xffffffffu, cand && (acc & 2u));
-    const uint32_t metb = __ballot_sync(0xffffffffu, cand && acc == 0u);
-    if (c.lane == j) {
+    const uint16_t* cp = col + e0;
+    bool unmet, fdp;
+    if (!FIXUP) {
+      const uint32_t x0 = cp[0], x1 = cp[1], x2 = cp[2], x3 = cp[3];  // may run past the row: masked below
+      const uint32_t s0 = st[min(x0, zidx)], s1 = st[min(x1, zidx)], s2 = st[min(x2, zidx)], s3 = st[min(x3, zidx)];
+      uint32_t w = ((s3 * 256u + s2) * 256u + s1) * 256u + s0;
+      w &= bmsk_clamp(0u, n * 8u);
+      if (max_deg > 4) {  // warp-uniform
+        for (uint32_t e = 4; e < n; ++e) w |= st[cp[e]];
+      }
+      unmet = (w & 0x01010101u) != 0;
+      fdp = (w & 0x02020202u) != 0;
+    } else {
+      uint32_t acc = 0;
+      for (uint32_t e = 0; e < n; ++e) {
+        const uint32_t d = cp[e];
+        uint32_t sb = st[d];
+        if (d < i && ((mFAIL[d >> 5] >> (d & 31u)) & 1u)) sb = failed_class;
+        acc |= sb;
+      }
+      unmet = (acc & 1u) != 0;
+      fdp = (acc & 2u) != 0;
+    }
+    const uint32_t fdb = __ballot_sync(FULL, fdp);
+    const uint32_t metb = __ballot_sync(FULL, cand && !unmet);
+    if (lane == j) {
       fd_w = fdb;
       met_w = metb;
     }
@@ -167,174 +176,141 @@ __device__ __forceinline__ void walk_deps(const RunCtx& c, const uint32_t* mCAND
 
 extern __shared__ __align__(128) uint8_t smem_raw[];
 
+// CD: cond and/or decision codes present   CH: topologies with `parallel` steps may occur (stage H, expansion count)
+// FX: device-side fixpoint (BF_EVAL_FIXPOINT)   XO: any of fail/needs_cond/skip_dep/phase_out requested
+template <bool CD, bool CH, bool FX, bool XO>
 __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t WPB = P.warps_per_block;
   const uint32_t ST = P.stages;
-  const uint32_t FULL = 0xffffffffu;
 
   // ---- shared memory carve-up: [block counters 128 B][warp regions] ----
   unsigned long long* blk_counts = reinterpret_cast<unsigned long long*>(smem_raw);
   const uint32_t ring_bytes = ST * P.stage_bytes;
   const uint32_t per_warp = ring_bytes + P.work_bytes + 64;  // + mbarriers (<= 8 stages)
-  uint8_t* wbase = smem_raw + 128 + warp * per_warp;
-  uint32_t* work = reinterpret_cast<uint32_t*>(wbase + ring_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + ring_bytes + P.work_bytes);
+  uint8_t* const wbase = smem_raw + 128 + warp * per_warp;
+  const uint32_t bars = smem_u32(wbase + ring_bytes + P.work_bytes);
+  const uint32_t ring = smem_u32(wbase);
 
   if (threadIdx.x < 4) blk_counts[threadIdx.x] = 0ull;
   if (lane == 0) {
-    for (uint32_t s = 0; s < ST; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    for (uint32_t s = 0; s < ST; ++s) mbar_init(bars + 8 * s, 1);
     fence_barrier_init();
   }
   __syncthreads();
 
-  const uint32_t gw = blockIdx.x * WPB + warp;
-  const uint32_t G = gridDim.x * WPB;
+  const uint32_t gw = blockIdx.x * P.warps_per_block + warp;
+  const uint32_t G = gridDim.x * P.warps_per_block;
   const uint32_t N = P.n_runs;
   const uint32_t my_runs = gw < N ? (N - gw + G - 1) / G : 0;
+  const size_t state_step = (size_t)G * P.state_stride;
+  const size_t result_step = (size_t)G * P.result_stride;
 
-  const bool has_cond = P.off_cond != BF_OFF_NONE;
-  const bool has_dec = P.off_decision != BF_OFF_NONE;
-  const bool has_child = P.off_child != BF_OFF_NONE;
-  const bool fixpoint = (P.flags & BF_EVAL_FIXPOINT) != 0;
+  // ---- producer state (used by lane 0): two-level prefetch slot id -> slot entry -> TMA ----
+  const uint8_t* src_state = P.state + (size_t)gw * P.state_stride;  // state record of issue index ni
+  uint32_t ni = 0, is = 0;   // next issue index, its stage
+  uint64_t ent_addr = 0;     // slot entry for issue index ni
+  uint32_t ent_bytes = 0;
+  uint32_t sid_q = 0xFFFFFFFFu;  // slot id for issue index ni+1
+  uint32_t ok_bits = 0;          // bit s: stage s holds a staged topology record
 
-  // ---- producer state (lane 0): two-level prefetch of slot id -> slot entry ----
-  uint32_t ni = 0;          // next issue index
-  Slot ent_q = {0, 0, 0};   // entry for issue index ni
-  uint32_t sid_q = 0;       // slot id for issue index ni+1
-  uint32_t ok_bits = 0;     // bit s: stage s holds a staged topology record
-  auto load_sid = [&](uint32_t n) -> uint32_t {
-    if (n >= my_runs) return 0xFFFFFFFFu;
-    const uint8_t* hdr = P.state + (size_t)(gw + n * G) * P.state_stride;
-    return __ldg(reinterpret_cast<const uint32_t*>(hdr));
-  };
-  auto load_ent = [&](uint32_t sid) -> Slot {
-    Slot e = {0, 0, 0};
+  auto load_ent = [&](uint32_t sid) {
+    ent_addr = 0;
+    ent_bytes = 0;
     if (sid < P.n_slots) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.slots + sid));
-      e.addr = (uint64_t)v.x | ((uint64_t)v.y << 32);
-      e.bytes = v.z;
-      e.S = v.w;
+      ent_addr = (uint64_t)v.x | ((uint64_t)v.y << 32);
+      ent_bytes = v.z;
     }
-    return e;
   };
-  auto issue = [&]() {
-    // copies for issue index ni into stage ni % ST
+  auto issue = [&]() {  // lane 0 only
     if (ni < my_runs) {
-      const uint32_t s = ni % ST;
-      uint8_t* buf = wbase + s * P.stage_bytes;
-      const uint32_t bar = smem_u32(&bars[s]);
-      const uint8_t* src_state = P.state + (size_t)(gw + ni * G) * P.state_stride;
-      const bool ok = ent_q.addr != 0 && ent_q.bytes <= P.topo_buf_bytes;
-      const uint32_t tb = ok ? ent_q.bytes : 0u;
-      ok_bits = ok ? (ok_bits | (1u << s)) : (ok_bits & ~(1u << s));
+      const uint32_t buf = ring + is * P.stage_bytes;
+      const uint32_t bar = bars + 8 * is;
+      const bool ok = ent_addr != 0 && ent_bytes <= P.topo_buf_bytes;
+      const uint32_t tb = ok ? ent_bytes : 0u;
+      ok_bits = ok ? (ok_bits | (1u << is)) : (ok_bits & ~(1u << is));
       mbar_expect_tx(bar, P.state_stride + tb);
-      bulk_g2s(smem_u32(buf), src_state, P.state_stride, bar);
-      if (ok) bulk_g2s(smem_u32(buf + P.state_stride), reinterpret_cast<const void*>(ent_q.addr), tb, bar);
+      bulk_g2s(buf, src_state, P.state_stride, bar);
+      if (ok) bulk_g2s(buf + P.state_stride, reinterpret_cast<const void*>(ent_addr), tb, bar);
     }
-    ent_q = load_ent(sid_q);
-    sid_q = load_sid(ni + 2);
+    load_ent(sid_q);  // entry for ni+1 (consumed by the next issue)
+    sid_q = (ni + 2 < my_runs) ? __ldg(reinterpret_cast<const uint32_t*>(src_state + 2 * state_step)) : 0xFFFFFFFFu;
+    src_state += state_step;
     ++ni;
+    is = (is + 1 == ST) ? 0 : is + 1;
   };
-  if (lane == 0) {
-    ent_q = load_ent(load_sid(0));
-    sid_q = load_sid(1);
+  if (lane == 0 && my_runs != 0) {
+    load_ent(__ldg(reinterpret_cast<const uint32_t*>(src_state)));
+    sid_q = my_runs > 1 ? __ldg(reinterpret_cast<const uint32_t*>(src_state + state_step)) : 0xFFFFFFFFu;
     for (uint32_t s = 0; s < ST; ++s) issue();
   }
 
-  // per-warp running totals (lane-uniform)
-  uint32_t tot_ready = 0, tot_skip = 0, tot_exp = 0, tot_evals = 0;
+  // scratch (per warp): fix-up fail mask words, then one status byte per step (+16 clamp guard)
+  const uint32_t Wmax = P.words;
+  uint32_t* const mFAIL = reinterpret_cast<uint32_t*>(wbase + ring_bytes);
+  uint8_t* const st = wbase + ring_bytes + ((4u * Wmax + 15u) & ~15u);
 
-  for (uint32_t k = 0; k < my_runs; ++k) {
-    const uint32_t s = k % ST;
-    const uint32_t r = gw + k * G;
-    mbar_wait(smem_u32(&bars[s]), (k / ST) & 1u);
+  const bool has_cond = CD && P.off_cond != BF_OFF_NONE;
+  const bool has_dec = CD && P.off_decision != BF_OFF_NONE;
+  const bool has_child = CH && P.off_child != BF_OFF_NONE;
 
-    const uint8_t* sr = wbase + s * P.stage_bytes;
+  uint32_t tot_ready = 0, tot_skip = 0, tot_exp = 0, tot_evals = 0;  // lane-uniform
+  uint32_t cs = 0, cpar = 0;                                         // consumer stage / parity
+  uint8_t* rr = P.result + (size_t)gw * P.result_stride;
+  uint32_t r = gw;
+
+  for (uint32_t k = 0; k < my_runs; ++k, rr += result_step, r += G) {
+    mbar_wait(bars + 8 * cs, cpar);
+    const uint8_t* sr = wbase + cs * P.stage_bytes;
     const uint8_t* tr = sr + P.state_stride;
-    const uint32_t rflags = sr[4];
-    const uint64_t registered = *reinterpret_cast<const uint64_t*>(sr + 8);
-    // Was a topology staged for this run?  (the producer lane knows)
-    bool topo_ok = (__shfl_sync(FULL, ok_bits, 0) >> s) & 1u;
-    if (topo_ok) topo_ok = reinterpret_cast<const TopoHeader*>(tr)->W <= P.words;
-    uint8_t* rr = P.result + (size_t)r * P.result_stride;
+    const bool staged = (__shfl_sync(FULL, ok_bits, 0) >> cs) & 1u;
+    cs = (cs + 1 == ST) ? 0 : cs + 1;
+    cpar ^= (cs == 0);
 
-    if (!topo_ok) {  // dead / out-of-range slot: empty result, summary all-ones
-      for (uint32_t x = lane; x < P.result_stride / 4; x += 32)
-        reinterpret_cast<uint32_t*>(rr)[x] = x == 0 ? 0xFFFFFFFFu : 0u;
+    const uint4 h0 = *reinterpret_cast<const uint4*>(tr);        // TopoHeader, first half
+    const uint32_t S = h0.x & 0xFFFFu, Wt = h0.x >> 16;          // S, W
+    const uint32_t max_deg = h0.y & 0xFFFFu, nP = h0.y >> 16;    // max_deg, P
+    const uint32_t n_main = h0.z & 0xFFFFu, n_comp = h0.z >> 16, n_final = h0.w & 0xFFFFu;
+    if (!staged || Wt > Wmax) {  // dead / out-of-range slot: empty result, summary all-ones
+      for (uint32_t x = lane; x < P.result_stride / 4; x += 32) reinterpret_cast<uint32_t*>(rr)[x] = x == 0 ? 0xFFFFFFFFu : 0u;
       if (P.exp_counts && lane == 0) P.exp_counts[r] = 0;
       __syncwarp();
       if (lane == 0) issue();
       continue;
     }
+    const uint4 h1 = *reinterpret_cast<const uint4*>(tr + 16);   // off_col, off_planes, off_par, rec_bytes
+    const uint32_t rflags = sr[4];
 
-    const TopoHeader th = *reinterpret_cast<const TopoHeader*>(tr);
-    const uint32_t S = th.S, Wt = th.W;
-    const uint32_t* splanes = reinterpret_cast<const uint32_t*>(tr + th.off_planes);
-
-    uint32_t* pl = work;                 // [4][Wt] phase planes
-    uint32_t* cpl = pl + 4 * P.words;    // [2][Wt] cond planes
-    uint32_t* dpl = cpl + 2 * P.words;   // [2][Wt] decision planes
-    uint32_t* mU = dpl + 2 * P.words;
-    uint32_t* mFD = mU + P.words;
-    uint32_t* mCAND = mFD + P.words;
-    uint32_t* mREADY = mCAND + P.words;
-    uint32_t* mFAIL = mREADY + P.words;
-    uint8_t* st = reinterpret_cast<uint8_t*>(work) + ((52u * P.words + 15u) & ~15u);  // 13 word arrays above
-
-    // ---------------- stage A: transpose packed codes into bit planes ----------------
-    {
-      const uint32_t* pw = reinterpret_cast<const uint32_t*>(sr + P.off_phase);
-      for (uint32_t m = lane; m < 4 * Wt; m += 32) {
-        uint32_t w = pw[m];
-        uint32_t f = w & (w >> 1);
-        f = f & (f >> 2) & 0x11111111u;  // nibble == 15 (reserved) -> 0
-        w &= ~(f * 15u);
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          reinterpret_cast<uint8_t*>(pl + b * Wt)[m] = (uint8_t)squeeze4((w >> b) & 0x11111111u);
-      }
-      if (has_cond) {
-        const uint32_t* cw = reinterpret_cast<const uint32_t*>(sr + P.off_cond);
-        for (uint32_t m = lane; m < 2 * Wt; m += 32) {
-          const uint32_t w = cw[m];
-          reinterpret_cast<uint16_t*>(cpl)[m] = (uint16_t)squeeze2(w & 0x55555555u);
-          reinterpret_cast<uint16_t*>(cpl + Wt)[m] = (uint16_t)squeeze2((w >> 1) & 0x55555555u);
-        }
-      }
-      if (has_dec) {
-        const uint32_t* dw = reinterpret_cast<const uint32_t*>(sr + P.off_decision);
-        for (uint32_t m = lane; m < 2 * Wt; m += 32) {
-          const uint32_t w = dw[m];
-          reinterpret_cast<uint16_t*>(dpl)[m] = (uint16_t)squeeze2(w & 0x55555555u);
-          reinterpret_cast<uint16_t*>(dpl + Wt)[m] = (uint16_t)squeeze2((w >> 1) & 0x55555555u);
-        }
-      }
-    }
-    __syncwarp();
-
-    // static planes + validity for word `lane`
+    // ---------------- planes of word `lane`: dynamic codes (state record) + static flags (topology) ----------------
     const bool act = lane < Wt;
     uint32_t t0 = 0, t1 = 0, t2 = 0, AF = 0, TS = 0, HASIF = 0, G1 = 0, G2 = 0, VALID = 0;
     uint32_t c0 = 0, c1 = 0, d0 = 0, d1 = 0;
-    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;  // input planes (for the "changed" flag)
+    uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     if (act) {
-      t0 = splanes[PL_T0 * Wt + lane]; t1 = splanes[PL_T1 * Wt + lane]; t2 = splanes[PL_T2 * Wt + lane];
-      AF = splanes[PL_AF * Wt + lane]; TS = splanes[PL_TS * Wt + lane]; HASIF = splanes[PL_HASIF * Wt + lane];
-      G1 = splanes[PL_G1 * Wt + lane]; G2 = splanes[PL_G2 * Wt + lane];
+      const uint32_t* sp = reinterpret_cast<const uint32_t*>(tr + h1.y) + lane;
+      if (CD || FX || CH) { t0 = sp[PL_T0 * Wt]; t1 = sp[PL_T1 * Wt]; t2 = sp[PL_T2 * Wt]; }
+      AF = sp[PL_AF * Wt];
+      if (CD) TS = sp[PL_TS * Wt];
+      if (XO) HASIF = sp[PL_HASIF * Wt];
+      G1 = sp[PL_G1 * Wt]; G2 = sp[PL_G2 * Wt];
       const uint32_t rem = S - lane * 32;
       VALID = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
-      if (has_cond) { c0 = cpl[lane]; c1 = cpl[Wt + lane]; }
-      if (has_dec) { d0 = dpl[lane]; d1 = dpl[Wt + lane]; }
-      q0 = pl[lane] & VALID; q1 = pl[Wt + lane] & VALID; q2 = pl[2 * Wt + lane] & VALID; q3 = pl[3 * Wt + lane] & VALID;
-      pl[lane] = q0; pl[Wt + lane] = q1; pl[2 * Wt + lane] = q2; pl[3 * Wt + lane] = q3;
+      const uint32_t* pw = reinterpret_cast<const uint32_t*>(sr + P.off_phase) + lane;
+      p0 = pw[0]; p1 = pw[Wmax]; p2 = pw[2 * Wmax]; p3 = pw[3 * Wmax];
+      const uint32_t keep = VALID & ~(p0 & p1 & p2 & p3);   // steps >= S and the reserved code 15 read as 0
+      p0 &= keep; p1 &= keep; p2 &= keep; p3 &= keep;
+      if (CD) {
+        if (has_cond) { const uint32_t* cw = reinterpret_cast<const uint32_t*>(sr + P.off_cond) + lane; c0 = cw[0]; c1 = cw[Wmax]; }
+        if (has_dec) { const uint32_t* dw = reinterpret_cast<const uint32_t*>(sr + P.off_decision) + lane; d0 = dw[0]; d1 = dw[Wmax]; }
+      }
     }
+    const uint32_t q0 = p0, q1 = p1, q2 = p2, q3 = p3;  // input planes (for the "changed" flag)
     const uint32_t GM = VALID & ~G1 & ~G2;
-    const uint32_t SYNC_T = t0 & (t1 | t2);            // sleep(3) | wait(5) | gate(7)
-    const uint32_t T_COND = t0 & ~t1 & ~t2;            // 1
-    const uint32_t T_PAR = ~t0 & t1 & ~t2 & VALID;     // 2
-    const uint32_t T_STOP = ~t0 & ~t1 & t2 & VALID;    // 4
+    const uint32_t SYNC_T = t0 & (t1 | t2);          // sleep(3) | wait(5) | gate(7)
+    const uint32_t T_COND = t0 & ~t1 & ~t2;          // 1
+    const uint32_t T_PAR = ~t0 & t1 & ~t2 & VALID;   // 2
+    const uint32_t T_STOP = ~t0 & ~t1 & t2 & VALID;  // 4
 
     const bool fail_fast = rflags & BF_RF_FAIL_FAST;
     const bool realtime = rflags & BF_RF_REALTIME;
@@ -343,101 +319,144 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
 
     uint32_t acc_ready = 0, acc_skip = 0, acc_fail = 0, acc_needs = 0, acc_skipdep = 0;
     uint32_t summary = 0, iters = 0;
-    const uint32_t cap = fixpoint ? (P.max_iter ? P.max_iter : S + 1) : 1u;
-
-    RunCtx rc;
-    rc.lane = lane; rc.Wt = Wt; rc.S = S; rc.sr = sr; rc.tr = tr;
-    rc.row_ptr = reinterpret_cast<const uint16_t*>(tr + sizeof(TopoHeader));
-    rc.col = reinterpret_cast<const uint16_t*>(tr + th.off_col);
-    rc.st = st;
+    bool marked = false;  // some phase was rewritten (lane-uniform)
+    const uint32_t cap = FX ? (P.max_iter ? P.max_iter : S + 1) : 1u;
+    const uint16_t* row_ptr = reinterpret_cast<const uint16_t*>(tr + sizeof(TopoHeader));
+    const uint16_t* col = reinterpret_cast<const uint16_t*>(tr + h1.x);
+    const uint32_t zidx = 32 * Wt;  // clamp target of the branch-free walk (inside the status array's guard)
 
     for (uint32_t it = 0; it < cap; ++it) {
       ++iters;
       // ---------------- stage H: parallel join (dag.go:1131-1198) ----------------
-      if (has_child && th.P != 0) {
-        __syncwarp();
-        const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + th.off_par);
+      if (CH && has_child && nP != 0) {
+        const uint64_t registered = *reinterpret_cast<const uint64_t*>(sr + 8);
+        const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + h1.z);
         const uint8_t* child = sr + P.off_child;
-        for (uint32_t q = 0; q < th.P; ++q) {
-          const ParDesc d = pd[q];
+        for (uint32_t q = 0; q < nP; ++q) {
           if (!((registered >> q) & 1ull)) continue;
+          const ParDesc d = pd[q];
           const uint32_t wj = d.step >> 5, wb = d.step & 31u;
-          const uint32_t ph = ((pl[wj] >> wb) & 1u) | (((pl[Wt + wj] >> wb) & 1u) << 1) |
-                              (((pl[2 * Wt + wj] >> wb) & 1u) << 2) | (((pl[3 * Wt + wj] >> wb) & 1u) << 3);
+          const uint32_t ph = ((__shfl_sync(FULL, p0, wj) >> wb) & 1u) | (((__shfl_sync(FULL, p1, wj) >> wb) & 1u) << 1) |
+                              (((__shfl_sync(FULL, p2, wj) >> wb) & 1u) << 2) | (((__shfl_sync(FULL, p3, wj) >> wb) & 1u) << 3);
           if (ph == 0 || ((BF_LUT_TERMINAL >> ph) & 1u)) continue;
           const uint32_t* allow = reinterpret_cast<const uint32_t*>(tr + d.allow_off);
           bool all_done = true, any_failed = false;
           for (uint32_t b = lane; b < d.branches; b += 32) {
-            const uint32_t cp = get_nibble(child, d.child_first + b);
-            const bool done = cp != 0 && ((BF_LUT_TERMINAL >> cp) & 1u);
-            const bool okc = cp == BF_PHASE_SUCCEEDED || cp == BF_PHASE_SKIPPED || ((allow[b >> 5] >> (b & 31u)) & 1u);
+            const uint32_t cph = get_nibble(child, d.child_first + b);
+            const bool done = cph != 0 && ((BF_LUT_TERMINAL >> cph) & 1u);
+            const bool okc = cph == BF_PHASE_SUCCEEDED || cph == BF_PHASE_SKIPPED || ((allow[b >> 5] >> (b & 31u)) & 1u);
             all_done = all_done && done;
             any_failed = any_failed || (done && !okc);
           }
           all_done = __all_sync(FULL, all_done);
           any_failed = __any_sync(FULL, any_failed);
-          if (all_done && lane == 0) {
-            uint32_t a = pl[wj], b = pl[Wt + wj], c = pl[2 * Wt + wj], e = pl[3 * Wt + wj];
-            const uint32_t m = 1u << wb;
-            if (any_failed) pset<BF_PHASE_FAILED>(m, a, b, c, e); else pset<BF_PHASE_SUCCEEDED>(m, a, b, c, e);
-            pl[wj] = a; pl[Wt + wj] = b; pl[2 * Wt + wj] = c; pl[3 * Wt + wj] = e;
+          if (all_done) {
+            marked = true;
+            if (lane == wj) {  // the lane that owns word wj rewrites its planes
+              const uint32_t m = 1u << wb;
+              if (any_failed) pset<BF_PHASE_FAILED>(m, p0, p1, p2, p3); else pset<BF_PHASE_SUCCEEDED>(m, p0, p1, p2, p3);
+            }
           }
-          __syncwarp();
         }
       }
 
-      // ---------------- stage B: classification on planes (lanes < Wt) ----------------
-      uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-      if (act) { p0 = pl[lane]; p1 = pl[Wt + lane]; p2 = pl[2 * Wt + lane]; p3 = pl[3 * Wt + lane]; }
-
-      if (has_dec) {  // stage G: gate / sleep / wait sync (dag.go:1469-1533, 1235-1277, 1327-1437)
-        const uint32_t syn = SYNC_T & plut<BF_LUT_RUNNING>(p0, p1, p2, p3);
-        const uint32_t n0 = d0;
-        const uint32_t n1 = d0 & ~(d1 & TS);
-        const uint32_t n2 = d1 & (~d0 | TS);
-        const uint32_t n3 = ~(d0 ^ d1);
-        p0 = (p0 & ~syn) | (n0 & syn);
-        p1 = (p1 & ~syn) | (n1 & syn);
-        p2 = (p2 & ~syn) | (n2 & syn);
-        p3 = (p3 & ~syn) | (n3 & syn);
+      // ---------------- stage G: gate / sleep / wait sync (dag.go:1469-1533, 1235-1277, 1327-1437) ----------------
+      if (CD) {
+        if (has_dec) {
+          const uint32_t syn = SYNC_T & plut<BF_LUT_RUNNING>(p0, p1, p2, p3);
+          const uint32_t n0 = d0;
+          const uint32_t n1 = d0 & ~(d1 & TS);
+          const uint32_t n2 = d1 & (~d0 | TS);
+          const uint32_t n3 = ~(d0 ^ d1);
+          p0 = (p0 & ~syn) | (n0 & syn);
+          p1 = (p1 & ~syn) | (n1 & syn);
+          p2 = (p2 & ~syn) | (n2 & syn);
+          p3 = (p3 & ~syn) | (n3 & syn);
+        }
       }
 
+      // ---------------- stage B: classification (dag.go:3377-3388, 2020-2033) ----------------
       uint32_t TERM = plut<BF_LUT_TERMINAL>(p0, p1, p2, p3);
       uint32_t COMPL = plut<BF_LUT_COMPLETED0>(p0, p1, p2, p3) | (TERM & AF);
-      uint32_t RUN = plut<BF_LUT_RUNNING>(p0, p1, p2, p3);
       uint32_t RUNQ = plut<BF_LUT_RUNNING_Q>(p0, p1, p2, p3);
       uint32_t FAILED = TERM & ~COMPL;
       uint32_t group;
       uint32_t sum = 0;
       if (host_group) {
         group = (rflags >> BF_RF_HOST_GROUP_SHIFT) & 3u;
-      } else {  // stage I: dag.go:422-495
-        bool amf = __any_sync(FULL, (FAILED & GM) != 0);
-        if (fail_fast && amf) {  // markFailFastSkipped dag.go:3289-3312
-          const uint32_t m = GM & ~COMPL & ~RUNQ & ~TERM;
-          pset<BF_PHASE_SKIPPED>(m, p0, p1, p2, p3);
-          TERM |= m; COMPL |= m; RUN &= ~m;
+      } else if ((n_comp | n_final) == 0) {
+        // ---------------- stage I, stories with main steps only (dag.go:422-431, 482-495) ----------------
+        const uint32_t DONE = COMPL | FAILED;
+        const uint32_t mark_ff = GM & ~COMPL & ~RUNQ & ~TERM;  // markFailFastSkipped candidates (:3289-3312)
+        bool amf = __any_sync(FULL, FAILED != 0);
+        const bool do_ff = fail_fast && amf;
+        bool main_done;
+        if (do_ff) {
+          marked = marked || __any_sync(FULL, mark_ff != 0);
+          pset<BF_PHASE_SKIPPED>(mark_ff, p0, p1, p2, p3);
+          TERM |= mark_ff; COMPL |= mark_ff;
+          main_done = !__any_sync(FULL, (GM & ~DONE & ~mark_ff) != 0);
+        } else {
+          main_done = !__any_sync(FULL, (GM & ~DONE) != 0);
         }
-        bool main_done = th.n_main == 0 || !__any_sync(FULL, (GM & ~(COMPL | FAILED)) != 0);
         if (!main_done && realtime && topo_term) {  // dag.go:436-464
           const uint32_t m = GM & (p0 | p1 | p2 | p3) & ~TERM;
+          marked = marked || __any_sync(FULL, m != 0);
+          pset<BF_PHASE_FAILED>(m, p0, p1, p2, p3);
+          TERM |= m; COMPL |= m & AF; FAILED |= m & ~AF; RUNQ &= ~m;
+          main_done = true;
+          amf = __any_sync(FULL, FAILED != 0);
+        }
+        group = main_done ? BF_GROUP_DONE : BF_GROUP_MAIN;
+        sum = (main_done ? BF_SUM_MAIN_DONE : 0u) | (amf ? BF_SUM_MAIN_FAILED : 0u) | BF_SUM_COMP_DONE | BF_SUM_FINAL_DONE;
+      } else {
+        // ---------------- stage I, general: dag.go:422-495, all reductions in one redux.or ----------------
+        uint32_t RUN = plut<BF_LUT_RUNNING>(p0, p1, p2, p3);
+        const uint32_t DONE = COMPL | FAILED;
+        const uint32_t mark_ff = GM & ~COMPL & ~RUNQ & ~TERM;           // markFailFastSkipped candidates (:3289-3312)
+        const uint32_t mark_cs = G1 & ~COMPL & ~RUN & ~FAILED & ~TERM;   // markCompensationsSkipped candidates (:3314-3342)
+        uint32_t bits = ((FAILED & GM) != 0 ? 1u : 0u)                   // any main failed
+                        | ((GM & ~DONE) != 0 ? 2u : 0u)                  // main not done (no marking)
+                        | ((GM & ~DONE & ~mark_ff) != 0 ? 4u : 0u)       // main not done even after fail-fast marking
+                        | ((G1 & ~DONE) != 0 ? 8u : 0u)                  // comp not done (no marking)
+                        | ((G1 & ~DONE & ~mark_cs) != 0 ? 16u : 0u)      // comp not done after comp-skip marking
+                        | ((G2 & ~DONE) != 0 ? 32u : 0u)                 // finally not done
+                        | ((FAILED & G1) != 0 ? 64u : 0u)
+                        | ((FAILED & G2) != 0 ? 128u : 0u)
+                        | (mark_ff != 0 ? 256u : 0u)
+                        | (mark_cs != 0 ? 512u : 0u);
+        bits = redux_or(bits);
+        bool amf = bits & 1u;
+        const bool do_ff = fail_fast && amf;
+        if (do_ff) {
+          marked = marked || (bits & 256u);
+          pset<BF_PHASE_SKIPPED>(mark_ff, p0, p1, p2, p3);
+          TERM |= mark_ff; COMPL |= mark_ff; RUN &= ~mark_ff;
+        }
+        bool main_done = n_main == 0 || !(bits & (do_ff ? 4u : 2u));
+        const bool acf = bits & 64u;
+        if (!main_done && realtime && topo_term) {  // dag.go:436-464 (rare: its own reduction)
+          const uint32_t m = GM & (p0 | p1 | p2 | p3) & ~TERM;
+          marked = marked || __any_sync(FULL, m != 0);
           pset<BF_PHASE_FAILED>(m, p0, p1, p2, p3);
           TERM |= m; COMPL |= m & AF; FAILED |= m & ~AF; RUN &= ~m; RUNQ &= ~m;
           main_done = true;
           amf = __any_sync(FULL, (FAILED & GM) != 0);
         }
-        if (main_done && !amf && th.n_comp != 0) {  // markCompensationsSkipped dag.go:3314-3342
-          const uint32_t m = G1 & ~COMPL & ~RUN & ~FAILED & ~TERM;
-          pset<BF_PHASE_SKIPPED>(m, p0, p1, p2, p3);
-          TERM |= m; COMPL |= m;
+        bool comp_done;
+        if (main_done && !amf && n_comp != 0) {
+          marked = marked || (bits & 512u);
+          pset<BF_PHASE_SKIPPED>(mark_cs, p0, p1, p2, p3);
+          TERM |= mark_cs; COMPL |= mark_cs;
+          comp_done = !(bits & 16u);
+        } else {
+          comp_done = n_comp == 0 || !(bits & 8u);
         }
-        const bool comp_done = th.n_comp == 0 || !__any_sync(FULL, (G1 & ~(COMPL | FAILED)) != 0);
-        const bool final_done = th.n_final == 0 || !__any_sync(FULL, (G2 & ~(COMPL | FAILED)) != 0);
-        const bool acf = __any_sync(FULL, (FAILED & G1) != 0);
-        const bool aff = __any_sync(FULL, (FAILED & G2) != 0);
+        const bool final_done = n_final == 0 || !(bits & 32u);
+        const bool aff = bits & 128u;
         if (!main_done) group = BF_GROUP_MAIN;
-        else if (amf && th.n_comp != 0 && !comp_done) group = BF_GROUP_COMPENSATION;
-        else if (th.n_final != 0 && !final_done) group = BF_GROUP_FINALLY;
+        else if (amf && n_comp != 0 && !comp_done) group = BF_GROUP_COMPENSATION;
+        else if (n_final != 0 && !final_done) group = BF_GROUP_FINALLY;
         else group = BF_GROUP_DONE;
         sum = (main_done ? BF_SUM_MAIN_DONE : 0u) | (amf ? BF_SUM_MAIN_FAILED : 0u) |
               (comp_done ? BF_SUM_COMP_DONE : 0u) | (final_done ? BF_SUM_FINAL_DONE : 0u) |
@@ -452,114 +471,114 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
         const bool skip_on_failed = group == BF_GROUP_MAIN && !fail_fast;
         const uint32_t GSEL = group == BF_GROUP_MAIN ? GM : (group == BF_GROUP_COMPENSATION ? G1 : G2);
         const uint32_t SAT = COMPL | (realtime ? plut<BF_LUT_RT_SAT>(p0, p1, p2, p3) : 0u) | (allow_failed ? TERM : 0u);
+        const uint32_t U = ~SAT;
         const uint32_t FD = skip_on_failed ? (TERM & ~SAT) : 0u;
         const uint32_t CAND = GSEL & ~COMPL & ~RUNQ & ~TERM;
-        if (act) { mU[lane] = ~SAT; mFD[lane] = FD; mCAND[lane] = CAND; }
-        __syncwarp();
         // ------------- stage C: masks -> one status byte per step (bit0 unmet, bit1 failed-dep) -------------
-        for (uint32_t m = lane; m < 4 * Wt; m += 32) {
-          const uint32_t ub = reinterpret_cast<const uint8_t*>(mU)[m];
-          const uint32_t fb = reinterpret_cast<const uint8_t*>(mFD)[m];
+        __syncwarp();
+        for (uint32_t m0 = 0; m0 < 4 * Wt; m0 += 32) {  // uniform trip count: every lane takes part in the shuffles
+          const uint32_t m = m0 + lane;
+          const uint32_t src = (m >> 2) & 31u, sh = (m & 3u) * 8u;
+          const uint32_t ub = __shfl_sync(FULL, U, src) >> sh;
+          const uint32_t fb = __shfl_sync(FULL, FD, src) >> sh;
           uint2 v;
           v.x = bits4_to_bytes(ub & 0xFu) | (bits4_to_bytes(fb & 0xFu) << 1);
-          v.y = bits4_to_bytes(ub >> 4) | (bits4_to_bytes(fb >> 4) << 1);
-          reinterpret_cast<uint2*>(st)[m] = v;
+          v.y = bits4_to_bytes((ub >> 4) & 0xFu) | (bits4_to_bytes((fb >> 4) & 0xFu) << 1);
+          if (m < 4 * Wt) reinterpret_cast<uint2*>(st)[m] = v;
         }
         __syncwarp();
         // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
         uint32_t met_w, fd_w;
-        walk_deps<false>(rc, mCAND, mFAIL, 0u, met_w, fd_w);
-        uint32_t ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
-        uint32_t skipc_w = met_w & c0 & ~c1;    // BF_COND_SKIP
-        uint32_t fail_w = met_w & c0 & c1;      // BF_COND_FAIL (HOLD = c1 & ~c0: nothing)
-        if (__any_sync(FULL, fail_w != 0)) {
-          // A step set Failed inside the loop is visible to LATER steps of the list only; iterate
-          // to the unique fixed point (at most one extra round per chained failure).
-          const uint32_t fclass = allow_failed ? 0u : (skip_on_failed ? 3u : 1u);
-          for (uint32_t round = 0; round <= S; ++round) {
-            __syncwarp();
-            if (act) mFAIL[lane] = fail_w;
-            __syncwarp();
-            walk_deps<true>(rc, mCAND, mFAIL, fclass, met_w, fd_w);
-            const uint32_t nf = met_w & c0 & c1;
-            const bool same = !__any_sync(FULL, nf != fail_w);
-            fail_w = nf;
-            if (same) break;
+        walk_deps<false>(lane, CAND, zidx, max_deg, row_ptr, col, st, mFAIL, 0u, met_w, fd_w);
+        uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
+        if (CD) {
+          ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
+          skipc_w = met_w & c0 & ~c1;    // BF_COND_SKIP
+          fail_w = met_w & c0 & c1;      // BF_COND_FAIL (HOLD = c1 & ~c0: nothing)
+          if (__any_sync(FULL, fail_w != 0)) {
+            // A step set Failed inside the loop is visible to LATER steps of the list only; iterate
+            // to the unique fixed point (one extra round per chained failure).
+            marked = true;
+            const uint32_t fclass = allow_failed ? 0u : (skip_on_failed ? 3u : 1u);
+            for (uint32_t round = 0; round <= S; ++round) {
+              __syncwarp();
+              if (act) mFAIL[lane] = fail_w;
+              __syncwarp();
+              walk_deps<true>(lane, CAND, zidx, max_deg, row_ptr, col, st, mFAIL, fclass, met_w, fd_w);
+              const uint32_t nf = met_w & c0 & c1;
+              const bool same = !__any_sync(FULL, nf != fail_w);
+              fail_w = nf;
+              if (same) break;
+            }
+            ready_w = met_w & ~c0 & ~c1;
+            skipc_w = met_w & c0 & ~c1;
           }
-          ready_w = met_w & ~c0 & ~c1;
-          skipc_w = met_w & c0 & ~c1;
         }
         it_ready = ready_w;
         it_skip = fd_w | skipc_w;
         it_fail = fail_w;
-        acc_needs |= realtime ? 0u : (met_w & HASIF);
-        acc_skipdep |= fd_w;
-        pset<BF_PHASE_FAILED>(fail_w, p0, p1, p2, p3);  // dag.go:2745-2747, 2810-2812
+        if (XO) {
+          acc_needs |= realtime ? 0u : (met_w & HASIF);
+          acc_skipdep |= fd_w;
+        }
+        if (CD) pset<BF_PHASE_FAILED>(fail_w, p0, p1, p2, p3);  // dag.go:2745-2747, 2810-2812
       }
       acc_ready |= it_ready; acc_skip |= it_skip; acc_fail |= it_fail;
 
-      bool more = false;
-      if (fixpoint && group != BF_GROUP_DONE) {
-        // ------------- launch effects (dag.go:1735-1775, step_executor.go:132-185) -------------
-        pset<BF_PHASE_SKIPPED>(it_skip, p0, p1, p2, p3);
-        const uint32_t none_or_q = ~(p0 | p1 | p2 | p3) | (~p0 & p1 & p2 & p3);  // code 0 or 14
-        const uint32_t rd = it_ready;
-        pset<BF_PHASE_SUCCEEDED>(rd & T_COND, p0, p1, p2, p3);
-        pset<BF_PHASE_PAUSED>(rd & SYNC_T, p0, p1, p2, p3);
-        pset<BF_PHASE_RUNNING>(rd & T_PAR, p0, p1, p2, p3);
-        pset<BF_PHASE_RUNNING>(rd & ~T_COND & ~SYNC_T & ~T_PAR & ~T_STOP & none_or_q, p0, p1, p2, p3);
-        const bool progress = __any_sync(FULL, (it_ready | it_skip) != 0);
-        const bool stop_ready = __any_sync(FULL, (it_ready & T_STOP) != 0);
-        more = progress && !stop_ready;
-      }
-      __syncwarp();
-      if (act) { pl[lane] = p0; pl[Wt + lane] = p1; pl[2 * Wt + lane] = p2; pl[3 * Wt + lane] = p3; }
-      __syncwarp();
-      if (!more) break;
+      if (!FX) break;
+      if (group == BF_GROUP_DONE) break;
+      // ------------- launch effects (dag.go:1735-1775, step_executor.go:132-185) -------------
+      const uint32_t o0 = p0, o1 = p1, o2 = p2, o3 = p3;
+      pset<BF_PHASE_SKIPPED>(it_skip, p0, p1, p2, p3);
+      const uint32_t none_or_q = ~(p0 | p1 | p2 | p3) | (~p0 & p1 & p2 & p3);  // code 0 or 14
+      pset<BF_PHASE_SUCCEEDED>(it_ready & T_COND, p0, p1, p2, p3);
+      pset<BF_PHASE_PAUSED>(it_ready & SYNC_T, p0, p1, p2, p3);
+      pset<BF_PHASE_RUNNING>(it_ready & T_PAR, p0, p1, p2, p3);
+      pset<BF_PHASE_RUNNING>(it_ready & ~T_COND & ~SYNC_T & ~T_PAR & ~T_STOP & none_or_q, p0, p1, p2, p3);
+      const uint32_t fl = redux_or(((it_ready | it_skip) != 0 ? 1u : 0u) | ((it_ready & T_STOP) != 0 ? 2u : 0u) |
+                                   (((p0 ^ o0) | (p1 ^ o1) | (p2 ^ o2) | (p3 ^ o3)) != 0 ? 4u : 0u));
+      marked = marked || (fl & 4u);
+      if ((fl & 3u) != 1u) break;  // no progress, or a ready `stop` step hands the run to the host
     }
 
     // ---------------- stage E: result record ----------------
-    uint32_t fp0 = 0, fp1 = 0, fp2 = 0, fp3 = 0;
-    if (act) { fp0 = pl[lane]; fp1 = pl[Wt + lane]; fp2 = pl[2 * Wt + lane]; fp3 = pl[3 * Wt + lane]; }
-    const bool changed = __any_sync(FULL, ((fp0 ^ q0) | (fp1 ^ q1) | (fp2 ^ q2) | (fp3 ^ q3)) != 0);
-    const uint32_t n_ready = __reduce_add_sync(FULL, (uint32_t)__popc(acc_ready));
-    const uint32_t n_skip = __reduce_add_sync(FULL, (uint32_t)__popc(acc_skip));
+    const uint32_t n_ready = redux_add((uint32_t)__popc(acc_ready));
+    const uint32_t n_skip = redux_add((uint32_t)__popc(acc_skip));
     uint32_t n_exp = 0;
-    if (th.P != 0) {
-      if (act) mREADY[lane] = acc_ready;
-      __syncwarp();
-      const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + th.off_par);
+    if (CH && nP != 0) {
+      const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + h1.z);
       uint32_t mine = 0;
-      for (uint32_t q = lane; q < th.P; q += 32) {
-        const uint32_t stp = pd[q].step;
-        if ((mREADY[stp >> 5] >> (stp & 31u)) & 1u) mine += pd[q].branches;
+      for (uint32_t q0i = 0; q0i < nP; q0i += 32) {  // uniform trip count (shuffles inside)
+        const uint32_t q = q0i + lane;
+        const uint32_t stp = q < nP ? pd[q].step : 0u;
+        const uint32_t w = __shfl_sync(FULL, acc_ready, stp >> 5);
+        if (q < nP && ((w >> (stp & 31u)) & 1u)) mine += pd[q].branches;
       }
-      n_exp = __reduce_add_sync(FULL, mine);
+      n_exp = redux_add(mine);
     }
+    // G rewrites (decision codes) are not tracked by `marked`: compare planes when they can occur
+    bool changed = marked;
+    if (CD) changed = __any_sync(FULL, ((p0 ^ q0) | (p1 ^ q1) | (p2 ^ q2) | (p3 ^ q3)) != 0);
     summary |= (changed ? BF_SUM_PHASE_CHANGED : 0u) | (iters << BF_SUM_ITER_SHIFT);
     if (lane == 0) {
       *reinterpret_cast<uint4*>(rr) = make_uint4(summary, n_ready, n_skip, n_exp);
       if (P.exp_counts) P.exp_counts[r] = n_exp;
     }
-    if (lane < P.words) {
+    if (lane < Wmax) {
       reinterpret_cast<uint32_t*>(rr + P.off_ready)[lane] = acc_ready;
       reinterpret_cast<uint32_t*>(rr + P.off_skip)[lane] = acc_skip;
-      if (P.off_fail != BF_OFF_NONE) reinterpret_cast<uint32_t*>(rr + P.off_fail)[lane] = acc_fail;
-      if (P.off_needs_cond != BF_OFF_NONE) reinterpret_cast<uint32_t*>(rr + P.off_needs_cond)[lane] = acc_needs;
-      if (P.off_skip_dep != BF_OFF_NONE) reinterpret_cast<uint32_t*>(rr + P.off_skip_dep)[lane] = acc_skipdep;
-    }
-    if (P.off_phase_out != BF_OFF_NONE) {
-      uint32_t* po = reinterpret_cast<uint32_t*>(rr + P.off_phase_out);
-      for (uint32_t m = lane; m < 4 * P.words; m += 32) {
-        uint32_t w = 0;
-        if (m < 4 * Wt) {
-#pragma unroll
-          for (int b = 0; b < 4; ++b) w |= spread4(reinterpret_cast<const uint8_t*>(pl + b * Wt)[m]) << b;
+      if (XO) {
+        if (P.off_fail != BF_OFF_NONE) reinterpret_cast<uint32_t*>(rr + P.off_fail)[lane] = acc_fail;
+        if (P.off_needs_cond != BF_OFF_NONE) reinterpret_cast<uint32_t*>(rr + P.off_needs_cond)[lane] = acc_needs;
+        if (P.off_skip_dep != BF_OFF_NONE) reinterpret_cast<uint32_t*>(rr + P.off_skip_dep)[lane] = acc_skipdep;
+        if (P.off_phase_out != BF_OFF_NONE) {
+          uint32_t* po = reinterpret_cast<uint32_t*>(rr + P.off_phase_out) + lane;
+          po[0] = p0; po[Wmax] = p1; po[2 * Wmax] = p2; po[3 * Wmax] = p3;
         }
-        po[m] = w;
       }
     }
-    for (uint32_t x = P.result_tail / 4 + lane; x < P.result_stride / 4; x += 32) reinterpret_cast<uint32_t*>(rr)[x] = 0u;
+    if (P.result_tail != P.result_stride)
+      for (uint32_t x = P.result_tail / 4 + lane; x < P.result_stride / 4; x += 32) reinterpret_cast<uint32_t*>(rr)[x] = 0u;
     tot_ready += n_ready; tot_skip += n_skip; tot_exp += n_exp; tot_evals += S;
 
     __syncwarp();  // every lane is done with this stage's buffers
@@ -579,27 +598,56 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
   }
 }
 
-// Host-side launcher (called from abi.cu).
+// ------------------------------------------------------------------ host-side dispatch
+typedef void (*KernelFn)(const KParams);
+static KernelFn pick_kernel(bool cd, bool ch, bool fx, bool xo) {
+  static const KernelFn table[16] = {
+      frontier_kernel<false, false, false, false>, frontier_kernel<false, false, false, true>,
+      frontier_kernel<false, false, true, false>,  frontier_kernel<false, false, true, true>,
+      frontier_kernel<false, true, false, false>,  frontier_kernel<false, true, false, true>,
+      frontier_kernel<false, true, true, false>,   frontier_kernel<false, true, true, true>,
+      frontier_kernel<true, false, false, false>,  frontier_kernel<true, false, false, true>,
+      frontier_kernel<true, false, true, false>,   frontier_kernel<true, false, true, true>,
+      frontier_kernel<true, true, false, false>,   frontier_kernel<true, true, false, true>,
+      frontier_kernel<true, true, true, false>,    frontier_kernel<true, true, true, true>,
+  };
+  return table[(cd ? 8 : 0) | (ch ? 4 : 0) | (fx ? 2 : 0) | (xo ? 1 : 0)];
+}
+
+static KernelFn kernel_for(const KParams& P) {
+  const bool cd = P.off_cond != BF_OFF_NONE || P.off_decision != BF_OFF_NONE;
+  const bool ch = P.any_parallel != 0;  // join needs the child area; the expansion count needs only the descs
+  const bool fx = (P.flags & BF_EVAL_FIXPOINT) != 0;
+  const bool xo = P.off_fail != BF_OFF_NONE || P.off_needs_cond != BF_OFF_NONE || P.off_skip_dep != BF_OFF_NONE ||
+                  P.off_phase_out != BF_OFF_NONE;
+  return pick_kernel(cd, ch, fx, xo);
+}
+
 cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream) {
-  static bool attr_set[64] = {};
+  KernelFn fn = kernel_for(P);
+  static KernelFn configured[8][16] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    e = cudaFuncSetAttribute(frontier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  bool known = false;
+  if (dev >= 0 && dev < 8)
+    for (int i = 0; i < 16; ++i) known = known || configured[dev][i] == fn;
+  if (!known) {
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set[dev] = true;
+    if (dev >= 0 && dev < 8)
+      for (int i = 0; i < 16; ++i)
+        if (configured[dev][i] == nullptr) { configured[dev][i] = fn; break; }
   }
-  frontier_kernel<<<grid, P.warps_per_block * 32, smem_bytes, stream>>>(P);
+  fn<<<grid, P.warps_per_block * 32, smem_bytes, stream>>>(P);
   return cudaGetLastError();
 }
 
-
-int frontier_max_blocks_per_sm(uint32_t threads, uint32_t smem_bytes) {
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
-  cudaFuncSetAttribute(frontier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frontier_kernel, (int)threads, smem_bytes) != cudaSuccess) return 1;
+int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes) {
+  int n = 0;
+  KernelFn fn = kernel_for(P);
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, (int)threads, smem_bytes) != cudaSuccess) return 1;
   return n;
 }
 

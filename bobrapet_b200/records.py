@@ -22,18 +22,31 @@ def make_layout(steps_max: int, child_nibbles: int = 0, fields: int = 0) -> A.La
 
 
 def _pack_nibbles(codes: np.ndarray, n_bytes: int) -> np.ndarray:
-    """codes [N, S] (values 0..15) -> [N, n_bytes] with step i at byte i/2, low nibble first."""
+    """codes [N, C] (values 0..15) -> [N, n_bytes] with item i at byte i/2, low nibble first (child area)."""
     n, s = codes.shape
     buf = np.zeros((n, n_bytes * 2), dtype=np.uint8)
     buf[:, :s] = codes
     return (buf[:, 0::2] | (buf[:, 1::2] << 4)).astype(np.uint8)
 
 
-def _pack_2bit(codes: np.ndarray, n_bytes: int) -> np.ndarray:
+def _pack_planes(codes: np.ndarray, words: int, nbits: int) -> np.ndarray:
+    """codes [N, S] -> [N, nbits*words*4] uint8: plane b (bit b of every code) = `words` little-endian u32,
+    step i at bit i%32 of word i/32."""
     n, s = codes.shape
-    buf = np.zeros((n, n_bytes * 4), dtype=np.uint8)
+    buf = np.zeros((n, words * 32), dtype=np.uint8)
     buf[:, :s] = codes
-    return (buf[:, 0::4] | (buf[:, 1::4] << 2) | (buf[:, 2::4] << 4) | (buf[:, 3::4] << 6)).astype(np.uint8)
+    planes = [np.packbits((buf >> b) & 1, axis=1, bitorder="little") for b in range(nbits)]
+    return np.concatenate(planes, axis=1)
+
+
+def _unpack_planes(raw: np.ndarray, words: int, nbits: int, s: int) -> np.ndarray:
+    """inverse of _pack_planes -> codes [N, s]"""
+    n = raw.shape[0]
+    codes = np.zeros((n, words * 32), dtype=np.uint8)
+    for b in range(nbits):
+        bits = np.unpackbits(np.ascontiguousarray(raw[:, b * words * 4:(b + 1) * words * 4]), axis=1, bitorder="little")
+        codes |= (bits << b).astype(np.uint8)
+    return codes[:, :s]
 
 
 def pack_state(L: A.Layout, slots: np.ndarray, run_flags: np.ndarray, phase: np.ndarray,
@@ -42,7 +55,7 @@ def pack_state(L: A.Layout, slots: np.ndarray, run_flags: np.ndarray, phase: np.
                out: Optional[np.ndarray] = None) -> np.ndarray:
     """Build [N, state_stride] uint8 state records.
 
-    phase/cond/decision are [N, S] code arrays (S <= steps_max); child is [N, child_nibbles]
+    phase/cond/decision are [N, S] code arrays (S <= steps_max), stored bit-sliced; child is [N, child_nibbles]
     phase codes laid out by bf_topology_child_first; registered is [N] uint64."""
     n = int(slots.shape[0])
     rec = out if out is not None else np.zeros((n, L.state_stride), dtype=np.uint8)
@@ -51,15 +64,15 @@ def pack_state(L: A.Layout, slots: np.ndarray, run_flags: np.ndarray, phase: np.
     if registered is not None:
         rec[:, 8:16] = np.ascontiguousarray(registered, dtype="<u8").view(np.uint8).reshape(n, 8)
     W = L.words
-    rec[:, L.off_phase:L.off_phase + W * 16] = _pack_nibbles(phase, W * 16)
+    rec[:, L.off_phase:L.off_phase + W * 16] = _pack_planes(phase, W, 4)
     if L.off_cond != A.OFF_NONE:
         if cond is None:
             cond = np.zeros_like(phase)
-        rec[:, L.off_cond:L.off_cond + W * 8] = _pack_2bit(cond, W * 8)
+        rec[:, L.off_cond:L.off_cond + W * 8] = _pack_planes(cond, W, 2)
     if L.off_decision != A.OFF_NONE:
         if decision is None:
             decision = np.zeros_like(phase)
-        rec[:, L.off_decision:L.off_decision + W * 8] = _pack_2bit(decision, W * 8)
+        rec[:, L.off_decision:L.off_decision + W * 8] = _pack_planes(decision, W, 2)
     if L.off_child != A.OFF_NONE and child is not None and L.child_nibbles:
         nb = (L.child_nibbles + 1) // 2
         rec[:, L.off_child:L.off_child + nb] = _pack_nibbles(child, nb)
@@ -82,11 +95,7 @@ def unpack_result(L: A.Layout, result: np.ndarray, s: int) -> Dict[str, np.ndarr
         if off != A.OFF_NONE:
             out[name] = _unpack_bits(np.ascontiguousarray(result[:, off:off + W * 4]), s)
     if L.off_phase_out != A.OFF_NONE:
-        pb = result[:, L.off_phase_out:L.off_phase_out + W * 16]
-        codes = np.empty((n, W * 32), dtype=np.uint8)
-        codes[:, 0::2] = pb & 0xF
-        codes[:, 1::2] = pb >> 4
-        out["phase_out"] = codes[:, :s]
+        out["phase_out"] = _unpack_planes(result[:, L.off_phase_out:L.off_phase_out + W * 16], W, 4, s)
     return out
 
 

@@ -113,7 +113,12 @@ void synth_topologies(uint32_t cfg, uint64_t run_lo, uint32_t n, uint32_t S, uin
 }
 
 static inline void put_nib(uint8_t* a, uint32_t i, uint32_t v) { a[i >> 1] |= (uint8_t)(v << ((i & 1u) * 4u)); }
-static inline void put_2b(uint8_t* a, uint32_t i, uint32_t v) { a[i >> 2] |= (uint8_t)(v << ((i & 3u) * 2u)); }
+/* bit-sliced code: plane b at base + b*W words */
+static inline void put_code(uint8_t* base, uint32_t W, int nbits, uint32_t i, uint32_t v) {
+  uint32_t* w = (uint32_t*)base;
+  for (int b = 0; b < nbits; ++b)
+    if ((v >> b) & 1u) w[(uint32_t)b * W + (i >> 5)] |= 1u << (i & 31u);
+}
 
 /* State records for runs [run_lo, run_lo+n) into `state` (n * L->state_stride bytes, zeroed here).
  * slots[r] is written to the header; flags[] are the topology's step flags (n*S) (for gate/if/parallel
@@ -143,12 +148,12 @@ void synth_state(uint32_t cfg, uint64_t run_lo, uint32_t n, uint32_t S, const bf
       if (cd) {
         uint32_t c = BF_COND_PASS;
         if (fl[i] & BF_SF_HAS_IF) { const uint32_t v = below(&st, 100); c = v < 60 ? BF_COND_PASS : v < 85 ? BF_COND_SKIP : BF_COND_HOLD; }
-        put_2b(cd, i, c);
+        put_code(cd, L->words, 2, i, c);
       }
       if (dc) {
         uint32_t d = BF_DEC_PENDING;
         if (ty == BF_STEP_GATE) { const uint32_t v = below(&st, 100); d = v < 40 ? BF_DEC_PENDING : v < 90 ? BF_DEC_SUCCEED : v < 98 ? BF_DEC_FAIL : BF_DEC_TIMED_OUT; }
-        put_2b(dc, i, d);
+        put_code(dc, L->words, 2, i, d);
       }
       if (ty == BF_STEP_PARALLEL && q < P) {
         if (i < p && code == BF_PHASE_SUCCEEDED && below(&st, 100) < 30) code = BF_PHASE_RUNNING;
@@ -167,7 +172,7 @@ void synth_state(uint32_t cfg, uint64_t run_lo, uint32_t n, uint32_t S, const bf
         }
         q++;
       }
-      put_nib(ph, i, code);
+      put_code(ph, L->words, 4, i, code);
     }
   }
 }

@@ -50,7 +50,7 @@ typedef enum bf_status {
 } bf_status;
 
 /* ---------------------------------------------------------- phase encoding */
-/* 4-bit code per (run, step).  Order = declaration order of enums.Phase
+/* 4-bit code per (run, step), stored bit-sliced (see "record layout").  Order = declaration order of enums.Phase
  * (pkg/enums/enums.go:44-97); 0 = "no StepState entry".  Code 14 folds the
  * "queued" bit into the nibble: phase Pending whose message starts with one of
  * the four "Queued due to ..." prefixes (dag.go:103-108, isConcurrencyQueued
@@ -110,7 +110,7 @@ enum { BF_GROUP_MAIN = 0, BF_GROUP_COMPENSATION = 1, BF_GROUP_FINALLY = 2, BF_GR
 #define BF_RF_HOST_GROUP_SHIFT 4        /* bits 4-5: BF_GROUP_* when BF_RF_HOST_GROUP   */
 
 /* ----------------------------------------------------- cond / decision codes */
-/* 2 bits per (run, step), packed 4 per byte, LSB first.                      */
+/* 2 bits per (run, step), stored as 2 bit planes.                            */
 enum {
   BF_COND_PASS = 0, /* no `if`, realtime, or evaluated true and `with` refs fresh (dag.go:2741,2837,2844) */
   BF_COND_SKIP = 1, /* evaluated false and refs not stale (dag.go:2820-2832)                            */
@@ -151,21 +151,27 @@ typedef struct bf_topology {
 
 /* ------------------------------------------------------------ record layout */
 /* Dynamic state travels as ONE record per run (so the host->device copy is a
- * single contiguous transfer and the kernel stages a run with one bulk copy):
+ * single contiguous transfer and the kernel stages a run with one bulk copy).
+ * Per-step codes are BIT-SLICED: a k-bit code is stored as k bit planes of
+ * `words` u32 each, step i = bit (i%32) of word i/32 of every plane, plane b
+ * holding bit b of the code.  Same size as nibble packing (4 bits/step for the
+ * phase), but 32 steps are classified by a handful of bitwise ops and no
+ * transposition is ever needed on either side.
  *
- *   offset 0   bf_run_header (16 B)
- *   off_phase  phase nibbles, step i at byte i/2, low nibble first  (words*16 B)
- *   off_cond   cond codes, 2 bits, step i at byte i/4               (words*8 B)  optional
- *   off_decision decision codes, same packing                        (words*8 B)  optional
- *   off_child  child StepRun phase nibbles of parallel steps, desc p starts at
- *              nibble child_first[p] (assigned by bf_topology_put; branch order) optional
+ *   offset 0     bf_run_header (16 B)
+ *   off_phase    phase code, 4 planes: plane b at off_phase + b*words*4     (words*16 B)
+ *   off_cond     cond code, 2 planes                                        (words*8 B)  optional
+ *   off_decision decision code, 2 planes                                    (words*8 B)  optional
+ *   off_child    child StepRun phase NIBBLES of parallel steps (branch order), desc p
+ *                starts at nibble child_first[p] (assigned by bf_topology_put),
+ *                child c at byte c/2, low nibble first                                   optional
  *
  * Results likewise, one record per run:
  *
  *   offset 0   bf_result_header (16 B)
  *   off_ready / off_skip / off_fail / off_needs_cond / off_skip_dep  bit masks,
  *              step i = bit (i%32) of u32 word i/32  (words*4 B each)
- *   off_phase_out  phase nibbles after this pass's status mutations  (words*16 B)
+ *   off_phase_out  phase code after this pass's status mutations, 4 planes  (words*16 B)
  *
  * All strides are multiples of 16 bytes.                                      */
 typedef struct bf_run_header {

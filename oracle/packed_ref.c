@@ -45,11 +45,18 @@ static inline int lut(unsigned table, int p) { return (int)((table >> p) & 1u); 
 static inline int is_term(int p) { return lut(BF_LUT_TERMINAL, p); }
 
 static inline int get_nib(const uint8_t* a, uint32_t i) { return (a[i >> 1] >> ((i & 1u) * 4u)) & 0xF; }
-static inline void set_nib(uint8_t* a, uint32_t i, int v) {
-  uint8_t sh = (uint8_t)((i & 1u) * 4u);
-  a[i >> 1] = (uint8_t)((a[i >> 1] & ~(0xFu << sh)) | ((unsigned)v << sh));
+/* bit-sliced code access: plane b at base + b*W words, step i = bit i%32 of word i/32 */
+static inline int get_code(const uint8_t* base, uint32_t W, int nbits, uint32_t i) {
+  const uint32_t* w = (const uint32_t*)base;
+  int v = 0;
+  for (int b = 0; b < nbits; ++b) v |= (int)((w[(uint32_t)b * W + (i >> 5)] >> (i & 31u)) & 1u) << b;
+  return v;
 }
-static inline int get_2b(const uint8_t* a, uint32_t i) { return (a[i >> 2] >> ((i & 3u) * 2u)) & 3; }
+static inline void set_code(uint8_t* base, uint32_t W, int nbits, uint32_t i, int v) {
+  uint32_t* w = (uint32_t*)base;
+  for (int b = 0; b < nbits; ++b)
+    if ((v >> b) & 1) w[(uint32_t)b * W + (i >> 5)] |= 1u << (i & 31u);
+}
 static inline int get_bit(const uint8_t* a, uint32_t i) { return (a[i >> 3] >> (i & 7u)) & 1; }
 static inline void set_mask(uint32_t* m, uint32_t i) { m[i >> 5] |= 1u << (i & 31u); }
 static inline int tst_mask(const uint32_t* m, uint32_t i) { return (int)((m[i >> 5] >> (i & 31u)) & 1u); }
@@ -86,7 +93,7 @@ static void eval_run(const orc_topology* T, const bf_layout* L, const uint8_t* s
   int changed = 0;
 
   for (uint32_t i = 0; i < S; ++i) {
-    int p = get_nib(in_phase, i);
+    int p = get_code(in_phase, W, 4, i);
     if (p == BF_PHASE_RESERVED) p = BF_PHASE_NONE;
     s->phase[i] = (uint8_t)p;
     s->fail_now[i] = 0;
@@ -111,7 +118,7 @@ static void eval_run(const orc_topology* T, const bf_layout* L, const uint8_t* s
         int p = s->phase[i];
         if (!lut(BF_LUT_RUNNING, p)) continue; /* exists, non-terminal, Paused|Running|Pending: dag.go:1469-1475 */
         int np;
-        switch (get_2b(dec, i)) {
+        switch (get_code(dec, W, 2, i)) {
           case BF_DEC_SUCCEED: np = BF_PHASE_SUCCEEDED; break;                         /* :1502, :1253, :1412 */
           case BF_DEC_FAIL: np = BF_PHASE_FAILED; break;                               /* :1508 */
           case BF_DEC_TIMED_OUT: np = (f & BF_SF_ON_TIMEOUT_SKIP) ? BF_PHASE_SKIPPED : BF_PHASE_TIMEOUT; break; /* :1655-1668 */
@@ -258,7 +265,7 @@ static void eval_run(const orc_topology* T, const bf_layout* L, const uint8_t* s
         }
         if (any_unmet) continue;
         if ((f & BF_SF_HAS_IF) && !realtime) set_mask(s->needs_cond, i);
-        int c = cond ? get_2b(cond, i) : BF_COND_PASS;
+        int c = cond ? get_code(cond, W, 2, i) : BF_COND_PASS;
         if (c == BF_COND_PASS) {
           set_mask(s->it_ready, i); any_ready = 1;
           if ((f & BF_SF_TYPE_MASK) == BF_STEP_STOP) stop_ready = 1;
@@ -314,7 +321,7 @@ static void eval_run(const orc_topology* T, const bf_layout* L, const uint8_t* s
   if (L->off_phase_out != BF_OFF_NONE) {
     uint8_t* po = rrec + L->off_phase_out;
     memset(po, 0, W * 16);
-    for (uint32_t i = 0; i < S; ++i) set_nib(po, i, s->phase[i]);
+    for (uint32_t i = 0; i < S; ++i) set_code(po, W, 4, i, s->phase[i]);
   }
   if (cnt) { cnt->ready += nr; cnt->skip += ns; cnt->expansion += n_exp; cnt->evals += S; }
 }
