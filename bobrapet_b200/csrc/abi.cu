@@ -333,29 +333,31 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | (L.fields << 16);
   if (c->plan_wpb == 0 || c->plan_key_stride != L.state_stride || c->plan_key_words != L.words ||
       c->plan_key_rec != c->max_rec_bytes || c->plan_key_variant != variant) {
+    // Plan: as many resident warps per SM as registers/shared memory allow (the pass is
+    // latency/issue bound before it is HBM bound), then ring depth: >= 2 stages keep the next
+    // run's TMA copies in flight under the current run's evaluation.
     const uint32_t budget = 227u * 1024u - 128u;
     uint32_t best_st = 0, best_wpb = 0, best_score = 0;
+    int per_sm_q = 1;
     const char* env_st = getenv("BF_STAGES");
     const char* env_w = getenv("BF_WARPS");
-    for (uint32_t st = 8; st >= 1; --st) {
+    const char* env_b = getenv("BF_BLOCKS_PER_SM");
+    for (uint32_t st = 1; st <= 4; ++st) {
       if (env_st && (uint32_t)atoi(env_st) != st) continue;
-      const uint32_t per_warp = st * P.stage_bytes + P.work_bytes + 64;
-      uint32_t wpb = budget / per_warp;
-      if (wpb > 16) wpb = 16;
-      if (env_w && (uint32_t)atoi(env_w) < wpb) wpb = (uint32_t)atoi(env_w);
-      if (wpb == 0) continue;
-      // enough bytes in flight to cover HBM latency (Little: ~45 KB/SM), then as many warps as fit
-      uint32_t inflight_kb = wpb * (st - 1) * P.stage_bytes / 1024u;
-      if (inflight_kb > 96) inflight_kb = 96;
-      const uint32_t score = inflight_kb + wpb * 8 + (st <= 4 ? 1 : 0);
-      if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; }
+      for (uint32_t wpb = 16; wpb >= 1; wpb = (wpb > 4 ? wpb - 4 : wpb - 1)) {
+        if (env_w && (uint32_t)atoi(env_w) != wpb) continue;
+        const uint32_t smem_try = 128 + wpb * (st * P.stage_bytes + P.work_bytes + 64);
+        if (smem_try > budget + 128) continue;
+        int ctas = bf::frontier_max_blocks_per_sm(P, wpb * 32, smem_try);
+        if (ctas < 1) continue;
+        if (env_b && atoi(env_b) >= 1 && atoi(env_b) < ctas) ctas = atoi(env_b);
+        const uint32_t warps_sm = (uint32_t)ctas * wpb;
+        const uint32_t depth = st >= 3 ? 2 : st - 1;           // 0, 1, 2, 2
+        const uint32_t score = warps_sm * 16 + depth * 24 + (wpb >= 8 ? 2 : 0) + (4 - st);
+        if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; per_sm_q = ctas; }
+      }
     }
     if (best_wpb == 0) return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
-    const uint32_t smem_try = 128 + best_wpb * (best_st * P.stage_bytes + P.work_bytes + 64);
-    int per_sm_q = bf::frontier_max_blocks_per_sm(P, best_wpb * 32, smem_try);
-    if (per_sm_q < 1) per_sm_q = 1;
-    const char* env_b = getenv("BF_BLOCKS_PER_SM");
-    if (env_b && atoi(env_b) >= 1 && atoi(env_b) < per_sm_q) per_sm_q = atoi(env_b);
     c->plan_stages = best_st; c->plan_wpb = best_wpb; c->plan_per_sm = (uint32_t)per_sm_q;
     c->plan_key_stride = L.state_stride; c->plan_key_words = L.words; c->plan_key_rec = c->max_rec_bytes;
     c->plan_key_variant = variant;
