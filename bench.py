@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--shared", type=int, default=0, help="shared-topology mode: D distinct topologies (0 = unique)")
     ap.add_argument("--ncu", action="store_true", help="profiling run: few passes, no e2e/cpu legs")
+    ap.add_argument("--no-graph", action="store_true", help="launch every pass eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--unroll", type=int, default=0, help="passes captured per CUDA graph (default 4*rot)")
     return ap.parse_args()
 
 
@@ -169,6 +171,7 @@ def main():
     import torch.distributed as dist
     from bobrapet_b200 import _abi as A, Frontier, synth
     from bobrapet_b200.records import make_layout
+    from bobrapet_b200.sharding import CountExchange, global_offsets
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -204,44 +207,68 @@ def main():
         del ts
     L = sets[0][0]
     stream = torch.cuda.current_stream()
-    comm_stream = torch.cuda.Stream() if world > 1 else None
-    gathered = [torch.zeros(4 * world, dtype=torch.int64, device=dev) for _ in range(ROT)] if world > 1 else None
+    exch = CountExchange(dev, world)
+    gathered = [exch.new_buffer() for _ in range(ROT)]
     launches = [0]
 
-    def one_pass(i):
+    def one_pass(i, st_):
         Lk, d_state, d_result, d_counts, _ = sets[i % ROT]
         d_counts.zero_()
-        fr.eval_device(Lk, n_runs, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), stream.cuda_stream)
+        fr.eval_device(Lk, n_runs, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), st_.cuda_stream)
         launches[0] += 1
         if world > 1:
             # the path's one collective: all-gather of the per-shard counts, overlapped with the next pass
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            comm_stream.wait_event(ev)
-            with torch.cuda.stream(comm_stream):
-                dist.all_gather_into_tensor(gathered[i % ROT], d_counts)
+            exch.gather(d_counts, gathered[i % ROT], st_)
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        one_pass(i)
+    work_stream = torch.cuda.Stream()
+    use_graph = not (args.no_graph or args.ncu)
+    U = args.unroll or 4 * ROT
+    U = max(ROT, (U // ROT) * ROT)
+    graph = None
+    with torch.cuda.stream(work_stream):
+        for i in range(max(args.warmup, ROT)):
+            one_pass(i, work_stream)
+        exch.join(work_stream)
     barrier()
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=work_stream, capture_error_mode="thread_local"):
+                for i in range(U):
+                    one_pass(i, work_stream)
+                exch.join(work_stream)
+            with torch.cuda.stream(work_stream):
+                graph.replay()  # one untimed replay
+            barrier()
+        except Exception as e:  # capture unsupported: fall back to eager launches
+            sys.stderr.write("bench: CUDA graph capture failed (%s); eager launches\n" % e)
+            graph = None
+            barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches[0] = 0
-    e0.record(stream)
-    for i in range(args.steps):
-        one_pass(i)
-    if world > 1:
-        stream.wait_stream(comm_stream)
-    e1.record(stream)
+    with torch.cuda.stream(work_stream):
+        e0.record(work_stream)
+        done = 0
+        if graph is not None:
+            while done + U <= args.steps:
+                graph.replay()
+                done += U
+                launches[0] += U
+        for i in range(done, args.steps):
+            one_pass(i, work_stream)
+        exch.join(work_stream)
+        e1.record(work_stream)
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
+    stream = torch.cuda.current_stream()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -250,6 +277,7 @@ def main():
     evals_per_pass = n_runs * S * n_gpus
     value = evals_per_pass * args.steps / (ms * 1e-3)
     counts_host = sets[(args.steps - 1) % ROT][3].cpu().numpy().tolist()
+    offsets = global_offsets(gathered[(args.steps - 1) % ROT], rank) if world > 1 else None
     timed_launches = launches[0]
 
     # ---- kernel-only duration for the roofline: event pair around each launch
@@ -324,16 +352,29 @@ def main():
                        "l2": "inputs %.0f MB/pass > 126 MB L2, rotated over %d disjoint copies" % (abytes / 1e6, ROT),
                        "parallelism": "runs sharded across %d GPU(s); one NCCL all-gather of counts per pass" % n_gpus,
                        "grid": st_stats["last_grid"], "block": st_stats["last_block"], "smem": st_stats["last_smem_bytes"],
-                       "stages": st_stats["last_stages"]},
+                       "stages": st_stats["last_stages"], "launch": ("cuda-graph x%d passes" % U) if graph is not None else "eager"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": timed_launches, "clocks": sampler.result(),
+            "global_counts_last_pass": (offsets["total"] if offsets else None),
             "counts_last_pass": {"ready": counts_host[0], "skip": counts_host[1], "expansion": counts_host[2], "evals": counts_host[3]},
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    # tear-down: release the captured graph (it holds NCCL work) before the process group; a rank that
+    # lingers here would only burn GPU time, so leave hard once everything is flushed.
+    graph = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     fr.close()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        try:
+            dist.barrier(device_ids=[local_rank])
+        except Exception:
+            pass
+        os._exit(0)
     return 0
 
 
