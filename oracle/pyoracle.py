@@ -884,11 +884,13 @@ def find_ready_steps(story: Optional[Story], steps: List[Step], step_states: Dic
 # launch effects (the host side of findAndLaunchReadySteps)
 # --------------------------------------------------------------------------
 def apply_launch_effects(srun: StoryRun, story: Story, res: ReadyResult, by_name: Dict[str, Step],
-                         now: float = 0.0) -> List[Tuple[str, str]]:
+                         now: float = 0.0, device_contract: bool = False) -> List[Tuple[str, str]]:
     """dag.go:1735-1775 + step_executor.go:132-185, 740-811, 1081-1106.
 
     Limiters (enforceStoryConcurrency/SchedulingLimits, dag.go:1713-1728) need
     cluster-wide LISTs and are a 'next' row; this models unlimited slots.
+    device_contract=True reproduces the packed fixpoint contract: a ready `stop` step is
+    NOT executed on the device (its phase comes from with.phase, host data) — the run is handed to the host.
     Returns the (parallel step, branch) expansion list in creation order."""
     expansion: List[Tuple[str, str]] = []
     for name in res.skipped:
@@ -917,6 +919,8 @@ def apply_launch_effects(srun: StoryRun, story: Story, res: ReadyResult, by_name
             _mark_step_state(srun, name, "Paused", "Waiting for gate decision.", now)
         elif step.type == "wait":
             _mark_step_state(srun, name, "Paused", "Waiting for condition.", now)
+        elif step.type == "stop" and device_contract:
+            continue
         elif step.type == "stop":
             w = step.with_ or {}
             phase = w.get("phase") or "Succeeded"
@@ -1040,8 +1044,9 @@ def run_dag_iterations(srun: StoryRun, story: Story, step_runs: Optional[List[St
                        evaluator: Optional[Evaluator] = None, vars_: Optional[Dict[str, Any]] = None,
                        now: float = 0.0, timers: Optional[StepTimers] = None,
                        stale: Optional[Callable[[str, str], bool]] = None,
-                       max_iterations: Optional[int] = None):
+                       max_iterations: Optional[int] = None, device_contract: bool = False):
     """dag.go:381-542 (fixpoint J) with launch effects and unlimited concurrency slots.
+    device_contract: a ready `stop` step ends the loop after its iteration (see apply_launch_effects).
     Returns (iterations_run, launched, skipped, expansion, final IterationResult)."""
     all_steps = all_story_steps(story)
     err = validate_runtime_dependency_graph(all_steps)
@@ -1059,9 +1064,11 @@ def run_dag_iterations(srun: StoryRun, story: Story, step_runs: Optional[List[St
         iters += 1
         if last.group == "finalize":
             break
-        expansion += apply_launch_effects(srun, story, last.ready, by_name, now)
+        expansion += apply_launch_effects(srun, story, last.ready, by_name, now, device_contract)
         launched += last.ready.ready
         skipped += last.ready.skipped
         if len(last.ready.ready) == 0 and len(last.ready.skipped) == 0:
+            break
+        if device_contract and any(by_name[n].type == "stop" and not by_name[n].ref for n in last.ready.ready):
             break
     return iters, launched, skipped, expansion, last
