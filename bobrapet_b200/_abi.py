@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbobrafrontier.so")
+LIB_PATH = os.environ.get("BF_LIB") or os.path.join(_HERE, "lib", "libbobrafrontier.so")  # BF_LIB: A/B builds
 
 BF_ABI_VERSION = 1
 BF_OK, BF_EINVAL, BF_ENOMEM, BF_ECUDA, BF_ENCCL, BF_ETOPO, BF_ENODEV = 0, -1, -2, -3, -4, -5, -6
@@ -89,7 +89,8 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("arena_used_bytes", C.c_uint64), ("arena_cap_bytes", C.c_uint64),
                 ("n_topologies", C.c_uint32), ("sm_count", C.c_uint32), ("last_grid", C.c_uint32),
-                ("last_block", C.c_uint32), ("last_smem_bytes", C.c_uint32), ("last_stages", C.c_uint32)]
+                ("last_block", C.c_uint32), ("last_smem_bytes", C.c_uint32), ("last_stages", C.c_uint32),
+                ("last_kernel", C.c_uint32), ("last_runs_per_trip", C.c_uint32)]
 
 
 # every symbol include/bobrafrontier.h declares: (name, restype, argtypes)

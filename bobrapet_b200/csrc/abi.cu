@@ -23,6 +23,8 @@ cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes
 cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, unsigned long long* offsets,
                              bf_expansion* out, unsigned long long cap, cudaStream_t stream, uint32_t* launches);
 int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
+cudaError_t launch_frontier_quad(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
+int frontier_quad_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
 }  // namespace bf
 
 namespace {
@@ -68,10 +70,11 @@ struct bf_ctx {
   uint32_t* d_exp_counts = nullptr; size_t d_exp_counts_cap = 0;
   unsigned long long* d_offsets = nullptr; size_t d_offsets_cap = 0;
   unsigned long long* d_block_sums = nullptr; size_t d_block_sums_cap = 0;
+  uint32_t* d_defer = nullptr; size_t d_defer_cap = 0;  // [0] = count, [1..] = run ids
 
   // cached shared-memory plan (recomputed when the layout or the largest record changes)
   uint32_t plan_key_stride = 0, plan_key_words = 0, plan_key_rec = 0, plan_key_variant = 0xFFFFFFFFu;
-  uint32_t plan_stages = 0, plan_wpb = 0, plan_per_sm = 0;
+  uint32_t plan_stages = 0, plan_wpb = 0, plan_per_sm = 0, plan_wq = 0, plan_lg = 0;
 
   bf_stats stats{};
 };
@@ -326,60 +329,128 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
     P.exp_counts = c->d_exp_counts;
   }
 
+  // ---- kernel choice: packed-lanes (R runs per warp trip) for single-pass batches without parallel
+  //      steps, the general one-run-per-warp kernel for fixpoint mode and parallel joins ----
+  // No parallel steps anywhere: packed-lanes only.  Only parallel-bearing topologies: general only.  Mixed:
+  // packed-lanes first, it defers the runs whose topology has parallel steps to a device list that the
+  // general kernel then takes (second launch; exits at once when the list is empty).
+  // Default: the general kernel (one run per warp).  The packed-lanes kernel executes ~17% fewer warp
+  // instructions per run but measured no faster (the same ~64 runs fit an SM's shared memory either way and
+  // its per-trip walk is longer), so it stays an opt-in experiment: BF_KERNEL=quad.
+  bool quad = false;
+  if (const char* env_k = getenv("BF_KERNEL")) {
+    if (!strcmp(env_k, "quad")) quad = !(b.flags & BF_EVAL_FIXPOINT) && c->n_with_parallel != c->n_alive;
+  }
+  uint32_t wq_min = 1, lg_min = 0;
+  while (wq_min < L.words) { wq_min <<= 1; lg_min++; }
+
   // ---- shared-memory plan ----
   P.topo_buf_bytes = round_up(c->max_rec_bytes, 16);
   P.stage_bytes = L.state_stride + P.topo_buf_bytes;
-  P.work_bytes = round_up(4 * L.words, 16) + 32 * L.words + 16;  // mFAIL words + status bytes (+ clamp guard)
-  const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | (L.fields << 16);
+  const uint32_t work_general = round_up(4 * L.words, 16) + 32 * L.words + 16;  // fix-up mask words + status bytes (+ clamp guard)
+  const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | ((uint32_t)quad << 9) | (L.fields << 16);
   if (c->plan_wpb == 0 || c->plan_key_stride != L.state_stride || c->plan_key_words != L.words ||
       c->plan_key_rec != c->max_rec_bytes || c->plan_key_variant != variant) {
-    // Plan: as many resident warps per SM as registers/shared memory allow (the pass is
-    // latency/issue bound before it is HBM bound), then ring depth: >= 2 stages keep the next
-    // run's TMA copies in flight under the current run's evaluation.
+    // Plan: as many resident warps (x runs per warp trip) per SM as registers / shared memory allow — the pass
+    // is latency/issue bound before it is HBM bound — then ring depth: >= 2 stages keep the next trip's TMA
+    // copies in flight under the current evaluation.
     const uint32_t budget = 227u * 1024u - 128u;
-    uint32_t best_st = 0, best_wpb = 0, best_score = 0;
+    uint32_t best_st = 0, best_wpb = 0, best_score = 0, best_wq = 0, best_lg = 0;
     int per_sm_q = 1;
     const char* env_st = getenv("BF_STAGES");
     const char* env_w = getenv("BF_WARPS");
     const char* env_b = getenv("BF_BLOCKS_PER_SM");
-    for (uint32_t st = 1; st <= 4; ++st) {
-      if (env_st && (uint32_t)atoi(env_st) != st) continue;
-      for (uint32_t wpb = 16; wpb >= 1; wpb = (wpb > 4 ? wpb - 4 : wpb - 1)) {
-        if (env_w && (uint32_t)atoi(env_w) != wpb) continue;
-        const uint32_t smem_try = 128 + wpb * (st * P.stage_bytes + P.work_bytes + 64);
-        if (smem_try > budget + 128) continue;
-        int ctas = bf::frontier_max_blocks_per_sm(P, wpb * 32, smem_try);
-        if (ctas < 1) continue;
-        if (env_b && atoi(env_b) >= 1 && atoi(env_b) < ctas) ctas = atoi(env_b);
-        const uint32_t warps_sm = (uint32_t)ctas * wpb;
-        const uint32_t depth = st >= 3 ? 2 : st - 1;           // 0, 1, 2, 2
-        const uint32_t score = warps_sm * 16 + depth * 24 + (wpb >= 8 ? 2 : 0) + (4 - st);
-        if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; per_sm_q = ctas; }
+    const char* env_q = getenv("BF_WQ");
+    for (int pass = quad ? 0 : 1; pass < 2 && best_wpb == 0; ++pass) {
+      const bool q = pass == 0;
+      for (uint32_t wq = q ? wq_min : 32u, lgq = q ? lg_min : 5u; wq <= 32u; wq <<= 1, ++lgq) {
+        if (q && env_q && (uint32_t)atoi(env_q) != wq) continue;
+        const uint32_t R = q ? 32u / wq : 1u;
+        P.wq = wq; P.wq_log2 = lgq;
+        P.work_bytes = q ? 1168u : work_general;
+        for (uint32_t st = 1; st <= 4; ++st) {
+          if (env_st && (uint32_t)atoi(env_st) != st) continue;
+          for (uint32_t wpb = 16; wpb >= 1; wpb = (wpb > 4 ? wpb - 4 : wpb - 1)) {
+            if (env_w && (uint32_t)atoi(env_w) != wpb) continue;
+            const uint32_t smem_try = 128 + wpb * (st * R * P.stage_bytes + P.work_bytes + 64);
+            if (smem_try > budget + 128) continue;
+            int ctas = q ? bf::frontier_quad_max_blocks_per_sm(P, wpb * 32, smem_try) : bf::frontier_max_blocks_per_sm(P, wpb * 32, smem_try);
+            if (ctas < 1) continue;
+            if (env_b && atoi(env_b) >= 1 && atoi(env_b) < ctas) ctas = atoi(env_b);
+            const uint32_t warps_sm = (uint32_t)ctas * wpb;
+            const uint32_t depth = st >= 3 ? 2 : st - 1;           // 0, 1, 2, 2
+            const uint32_t score = q ? (warps_sm * R > 128 ? 128 : warps_sm * R) * 8 + warps_sm * 2 + depth * 24 + (wpb >= 4 ? 2 : 0)
+                                     : warps_sm * 16 + depth * 24 + (wpb >= 8 ? 2 : 0) + (4 - st);
+            if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; per_sm_q = ctas; best_wq = wq; best_lg = lgq; }
+          }
+        }
+        if (!q) break;
       }
+      if (best_wpb == 0 && q) quad = false;  // the R-run stage does not fit: one run per warp
     }
     if (best_wpb == 0) return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
     c->plan_stages = best_st; c->plan_wpb = best_wpb; c->plan_per_sm = (uint32_t)per_sm_q;
+    c->plan_wq = quad ? best_wq : 0; c->plan_lg = best_lg;
     c->plan_key_stride = L.state_stride; c->plan_key_words = L.words; c->plan_key_rec = c->max_rec_bytes;
     c->plan_key_variant = variant;
+  }
+  quad = c->plan_wq != 0;
+  P.wq = quad ? c->plan_wq : 32u; P.wq_log2 = quad ? c->plan_lg : 5u;
+  P.work_bytes = quad ? 1168u : work_general;
+  const uint32_t R = quad ? 32u / P.wq : 1u;
+  const uint32_t stage_total = R * P.stage_bytes;
+  const bool two_tier = quad && c->n_with_parallel != 0;
+  if (two_tier) {
+    if (int rc = ensure_dev(c, c->d_defer, c->d_defer_cap, (size_t)b.n_runs + 1)) return rc;
+    P.defer_count = c->d_defer;
+    P.defer_list = c->d_defer + 1;
   }
   const uint32_t best_st = c->plan_stages, best_wpb = c->plan_wpb;
   const int per_sm = (int)c->plan_per_sm;
   P.stages = best_st;
   P.warps_per_block = best_wpb;
-  const uint32_t smem = 128 + best_wpb * (best_st * P.stage_bytes + P.work_bytes + 64);
+  const uint32_t smem = 128 + best_wpb * (best_st * stage_total + P.work_bytes + 64);
   uint32_t grid = (uint32_t)c->sm_count * (uint32_t)per_sm;
-  const uint32_t need_blocks = (b.n_runs + best_wpb - 1) / best_wpb;
+  const uint32_t trips = (b.n_runs + R - 1) / R;
+  const uint32_t need_blocks = (trips + best_wpb - 1) / best_wpb;
   if (grid > need_blocks) grid = need_blocks ? need_blocks : 1;
 
   if (b.n_runs) {
-    BF_CUDA(c, bf::launch_frontier(P, grid, smem, stream));
-    c->stats.kernel_launches += 1;
+    if (quad) {
+      if (two_tier) BF_CUDA(c, cudaMemsetAsync(c->d_defer, 0, sizeof(uint32_t), stream));
+      BF_CUDA(c, bf::launch_frontier_quad(P, grid, smem, stream));
+      c->stats.kernel_launches += 1;
+      if (two_tier) {
+        // second tier: the general kernel over the deferred runs (its own shared-memory plan)
+        bf::KParams P2 = P;
+        P2.defer_list = nullptr; P2.defer_count = nullptr;
+        P2.run_list = c->d_defer + 1; P2.run_list_count = c->d_defer;
+        P2.work_bytes = round_up(4 * L.words, 16) + 32 * L.words + 16;
+        uint32_t st2 = 2, wpb2 = 16;
+        const uint32_t budget2 = 227u * 1024u - 128u;
+        while (wpb2 > 1 && 128 + wpb2 * (st2 * P.stage_bytes + P2.work_bytes + 64) > budget2) wpb2 = wpb2 > 4 ? wpb2 - 4 : wpb2 - 1;
+        if (128 + wpb2 * (st2 * P.stage_bytes + P2.work_bytes + 64) > budget2) st2 = 1;
+        if (128 + wpb2 * (st2 * P.stage_bytes + P2.work_bytes + 64) > budget2)
+          return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
+        P2.stages = st2; P2.warps_per_block = wpb2;
+        const uint32_t smem2 = 128 + wpb2 * (st2 * P.stage_bytes + P2.work_bytes + 64);
+        uint32_t grid2 = (uint32_t)c->sm_count;
+        const uint32_t nb2 = (b.n_runs + wpb2 - 1) / wpb2;
+        if (grid2 > nb2) grid2 = nb2 ? nb2 : 1;
+        BF_CUDA(c, bf::launch_frontier(P2, grid2, smem2, stream));
+        c->stats.kernel_launches += 1;
+      }
+    } else {
+      BF_CUDA(c, bf::launch_frontier(P, grid, smem, stream));
+      c->stats.kernel_launches += 1;
+    }
     if (want_exp) {
       uint32_t nl = 0;
       BF_CUDA(c, bf::launch_expansion(P, c->d_block_sums, c->d_offsets, d_exp, b.expansion_cap, stream, &nl));
       c->stats.kernel_launches += nl;
     }
   }
+  c->stats.last_kernel = quad ? (two_tier ? 2u : 1u) : 0u; c->stats.last_runs_per_trip = R;
   c->stats.last_grid = grid; c->stats.last_block = best_wpb * 32; c->stats.last_smem_bytes = smem; c->stats.last_stages = best_st;
   return BF_OK;
 }
@@ -412,7 +483,7 @@ int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_
     m.alive = true; m.S = topos[i].n_steps; m.E = topos[i].n_edges; m.P = topos[i].n_parallel;
     m.bytes = plans[i].rec_bytes; m.offset = base + off; m.child_first = plans[i].child_first;
     m.child_nibbles = plans[i].child_nibbles;
-    c->slots_host[slot] = bf::Slot{(uint64_t)(uintptr_t)(c->arena + m.offset), m.bytes, m.S};
+    c->slots_host[slot] = bf::Slot{(uint64_t)(uintptr_t)(c->arena + m.offset), m.bytes, m.S | (m.P << 16)};
     if (m.bytes > c->max_rec_bytes) c->max_rec_bytes = m.bytes;
     off += plans[i].rec_bytes;
     slots_out[i] = slot;
@@ -480,7 +551,7 @@ void bf_destroy(bf_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
-  cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums);
+  cudaFree(c->d_defer); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums);
   delete c;
 }
 

@@ -47,7 +47,7 @@ static_assert(sizeof(ParDesc) == 16, "ParDesc must be 16 bytes");
 struct Slot {          // device slot table entry
   uint64_t addr;       // device address of the record (0 = dead slot)
   uint32_t bytes;      // rec_bytes
-  uint32_t S;
+  uint32_t meta;       // S | P << 16 (P = number of parallel descs)
 };
 static_assert(sizeof(Slot) == 16, "Slot must be 16 bytes");
 
@@ -57,6 +57,12 @@ struct KParams {
   const Slot* slots;
   unsigned long long* counts;   // bf_counts (4 x u64) or nullptr
   uint32_t* exp_counts;         // [n_runs] compact per-run expansion counts or nullptr
+  // two-tier dispatch: the packed-lanes kernel appends the runs it cannot take (topologies with
+  // parallel steps) to defer_list; the general kernel then runs over run_list[0..*run_list_count)
+  uint32_t* defer_list;
+  uint32_t* defer_count;
+  const uint32_t* run_list;
+  const uint32_t* run_list_count;
   uint32_t n_slots;
   uint32_t n_runs;
   uint32_t flags;               // BF_EVAL_*
@@ -73,6 +79,8 @@ struct KParams {
   uint32_t stage_bytes;         // state_stride + topo_buf_bytes (multiple of 16)
   uint32_t work_bytes;          // per-warp scratch
   uint32_t warps_per_block;
+  // packed-lanes kernel (frontier_quad.cu): words per run rounded up to a power of two
+  uint32_t wq, wq_log2;
 };
 
 }  // namespace bf

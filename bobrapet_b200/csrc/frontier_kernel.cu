@@ -21,95 +21,9 @@
 // parallel steps present, device fixpoint, extra outputs) so the common pass carries
 // no dead work.  Integer only; no tensor cores.  HBM-bound: ~3 KB in, 80 B out per run
 // at the BASELINE configuration.  See DESIGN.md for the roofline accounting.
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include "../../include/bobrafrontier.h"
-#include "device_record.h"
+#include "kernel_common.cuh"
 
 namespace bf {
-
-#define DI __device__ __forceinline__
-constexpr uint32_t FULL = 0xffffffffu;
-
-// ------------------------------------------------------------------ PTX helpers
-DI uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-DI void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-DI void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-DI uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-DI void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.
-DI void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-DI void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-template <int IMM>
-DI uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(IMM));
-  return r;
-}
-// 16-entry boolean table over a bit-sliced 4-bit code: 3 LOP3 for 32 steps.
-template <uint32_t T16>
-DI uint32_t plut(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
-  const uint32_t lo = lop3<(T16 & 0xFF)>(p2, p1, p0);
-  const uint32_t hi = lop3<((T16 >> 8) & 0xFF)>(p2, p1, p0);
-  return lop3<0xCA>(p3, hi, lo);  // p3 ? hi : lo
-}
-// set the code of the steps in mask m to the constant CODE
-template <int CODE>
-DI void pset(uint32_t m, uint32_t& p0, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
-  p0 = (CODE & 1) ? (p0 | m) : (p0 & ~m);
-  p1 = (CODE & 2) ? (p1 | m) : (p1 & ~m);
-  p2 = (CODE & 4) ? (p2 | m) : (p2 & ~m);
-  p3 = (CODE & 8) ? (p3 | m) : (p3 & ~m);
-}
-DI uint32_t squeeze4(uint32_t x) {  // bits 0,4,..,28 -> low byte
-  x = (x | (x >> 3)) & 0x03030303u;
-  x = (x | (x >> 6)) & 0x000F000Fu;
-  x = (x | (x >> 12)) & 0xFFu;
-  return x;
-}
-DI uint32_t squeeze2(uint32_t x) {  // bits 0,2,..,30 -> low half
-  x = (x | (x >> 1)) & 0x33333333u;
-  x = (x | (x >> 2)) & 0x0F0F0F0Fu;
-  x = (x | (x >> 4)) & 0x00FF00FFu;
-  x = (x | (x >> 8)) & 0xFFFFu;
-  return x;
-}
-DI uint32_t spread4(uint32_t x) {  // inverse of squeeze4
-  x = (x | (x << 12)) & 0x000F000Fu;
-  x = (x | (x << 6)) & 0x03030303u;
-  x = (x | (x << 3)) & 0x11111111u;
-  return x;
-}
-DI uint32_t bits4_to_bytes(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }  // 4 bits -> 4 0/1 bytes
-DI uint32_t get_nibble(const uint8_t* base, uint32_t i) {
-  const uint32_t v = (base[i >> 1] >> ((i & 1u) * 4u)) & 0xFu;
-  return v == 15u ? 0u : v;
-}
-DI uint32_t redux_or(uint32_t v) { return __reduce_or_sync(FULL, v); }
-DI uint32_t redux_add(uint32_t v) { return __reduce_add_sync(FULL, v); }
 
 // ------------------------------------------------------------------ stage D
 // One step per lane per trip over the CSR rows of the candidate steps, visiting only the
@@ -118,12 +32,6 @@ DI uint32_t redux_add(uint32_t v) { return __reduce_add_sync(FULL, v); }
 // clamped into the status array, verdict masked by the row length); longer rows exist only
 // when the topology header says so.  FIXUP adds the "set Failed earlier in this same loop"
 // visibility rule (dag.go:2744/2810 mutate stepStates while `completed` stays as built at :497).
-DI uint32_t bmsk_clamp(uint32_t pos, uint32_t width) {
-  uint32_t r;
-  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(pos), "r"(width));
-  return r;
-}
-
 template <bool FIXUP>
 DI void walk_deps(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_deg, const uint16_t* __restrict__ row_ptr,
                   const uint16_t* __restrict__ col, const uint8_t* __restrict__ st, const uint32_t* mFAIL,
@@ -178,7 +86,8 @@ extern __shared__ __align__(128) uint8_t smem_raw[];
 
 // CD: cond and/or decision codes present   CH: topologies with `parallel` steps may occur (stage H, expansion count)
 // FX: device-side fixpoint (BF_EVAL_FIXPOINT)   XO: any of fail/needs_cond/skip_dep/phase_out requested
-template <bool CD, bool CH, bool FX, bool XO>
+// LIST: second-tier run over P.run_list (runs deferred by the packed-lanes kernel)
+template <bool CD, bool CH, bool FX, bool XO, bool LIST>
 __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
@@ -201,19 +110,28 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
 
   const uint32_t gw = blockIdx.x * P.warps_per_block + warp;
   const uint32_t G = gridDim.x * P.warps_per_block;
-  const uint32_t N = P.n_runs;
+  // run-list mode (second tier after the packed-lanes kernel): the runs to take are run_list[0..count)
+  const uint32_t* const rlist = LIST ? P.run_list : nullptr;
+  const uint32_t N = LIST ? min(*reinterpret_cast<const volatile uint32_t*>(P.run_list_count), P.n_runs) : P.n_runs;
   const uint32_t my_runs = gw < N ? (N - gw + G - 1) / G : 0;
-  const size_t state_step = (size_t)G * P.state_stride;
-  const size_t result_step = (size_t)G * P.result_stride;
+  auto run_of = [&](uint32_t n) -> uint32_t {  // global run index of this warp's n-th run
+    const uint32_t idx = gw + n * G;
+    return LIST ? __ldg(rlist + idx) : idx;
+  };
 
-  // ---- producer state (used by lane 0): two-level prefetch slot id -> slot entry -> TMA ----
-  const uint8_t* src_state = P.state + (size_t)gw * P.state_stride;  // state record of issue index ni
+  // ---- producer state (used by lane 0): prefetch chain run id -> slot id -> slot entry -> TMA ----
   uint32_t ni = 0, is = 0;   // next issue index, its stage
+  uint32_t r_0 = 0, r_1 = 0, r_2 = 0;  // LIST: run ids of issue index ni, ni+1, ni+2
+  const size_t state_step = (size_t)G * P.state_stride;
+  const uint8_t* src_state = P.state + (size_t)gw * P.state_stride;  // !LIST: state record of issue index ni
   uint64_t ent_addr = 0;     // slot entry for issue index ni
   uint32_t ent_bytes = 0;
   uint32_t sid_q = 0xFFFFFFFFu;  // slot id for issue index ni+1
   uint32_t ok_bits = 0;          // bit s: stage s holds a staged topology record
 
+  auto load_sid = [&](uint32_t r) -> uint32_t {
+    return __ldg(reinterpret_cast<const uint32_t*>(P.state + (size_t)r * P.state_stride));
+  };
   auto load_ent = [&](uint32_t sid) {
     ent_addr = 0;
     ent_bytes = 0;
@@ -231,18 +149,27 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
       const uint32_t tb = ok ? ent_bytes : 0u;
       ok_bits = ok ? (ok_bits | (1u << is)) : (ok_bits & ~(1u << is));
       mbar_expect_tx(bar, P.state_stride + tb);
-      bulk_g2s(buf, src_state, P.state_stride, bar);
+      bulk_g2s(buf, LIST ? P.state + (size_t)r_0 * P.state_stride : src_state, P.state_stride, bar);
       if (ok) bulk_g2s(buf + P.state_stride, reinterpret_cast<const void*>(ent_addr), tb, bar);
     }
     load_ent(sid_q);  // entry for ni+1 (consumed by the next issue)
-    sid_q = (ni + 2 < my_runs) ? __ldg(reinterpret_cast<const uint32_t*>(src_state + 2 * state_step)) : 0xFFFFFFFFu;
-    src_state += state_step;
+    if (LIST) {
+      sid_q = (ni + 2 < my_runs) ? load_sid(r_2) : 0xFFFFFFFFu;
+      r_0 = r_1; r_1 = r_2;
+      r_2 = (ni + 3 < my_runs) ? run_of(ni + 3) : 0u;
+    } else {
+      sid_q = (ni + 2 < my_runs) ? __ldg(reinterpret_cast<const uint32_t*>(src_state + 2 * state_step)) : 0xFFFFFFFFu;
+      src_state += state_step;
+    }
     ++ni;
     is = (is + 1 == ST) ? 0 : is + 1;
   };
   if (lane == 0 && my_runs != 0) {
-    load_ent(__ldg(reinterpret_cast<const uint32_t*>(src_state)));
-    sid_q = my_runs > 1 ? __ldg(reinterpret_cast<const uint32_t*>(src_state + state_step)) : 0xFFFFFFFFu;
+    r_0 = run_of(0);
+    r_1 = my_runs > 1 ? run_of(1) : 0u;
+    r_2 = my_runs > 2 ? run_of(2) : 0u;
+    load_ent(load_sid(r_0));
+    sid_q = my_runs > 1 ? load_sid(r_1) : 0xFFFFFFFFu;
     for (uint32_t s = 0; s < ST; ++s) issue();
   }
 
@@ -257,10 +184,15 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
 
   uint32_t tot_ready = 0, tot_skip = 0, tot_exp = 0, tot_evals = 0;  // lane-uniform
   uint32_t cs = 0, cpar = 0;                                         // consumer stage / parity
-  uint8_t* rr = P.result + (size_t)gw * P.result_stride;
-  uint32_t r = gw;
+  uint32_t r_next = (LIST && my_runs != 0) ? run_of(0) : gw;
+  const size_t result_step = (size_t)G * P.result_stride;
+  uint8_t* rr_inc = P.result + (size_t)gw * P.result_stride;
 
-  for (uint32_t k = 0; k < my_runs; ++k, rr += result_step, r += G) {
+  for (uint32_t k = 0; k < my_runs; ++k, rr_inc += result_step) {
+    const uint32_t r = r_next;
+    if (LIST) { if (k + 1 < my_runs) r_next = run_of(k + 1); }  // issued one trip early: its latency hides under this run
+    else r_next = r + G;
+    uint8_t* const rr = LIST ? P.result + (size_t)r * P.result_stride : rr_inc;
     mbar_wait(bars + 8 * cs, cpar);
     const uint8_t* sr = wbase + cs * P.stage_bytes;
     const uint8_t* tr = sr + P.state_stride;
@@ -600,16 +532,17 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
 
 // ------------------------------------------------------------------ host-side dispatch
 typedef void (*KernelFn)(const KParams);
+template <bool LIST>
 static KernelFn pick_kernel(bool cd, bool ch, bool fx, bool xo) {
   static const KernelFn table[16] = {
-      frontier_kernel<false, false, false, false>, frontier_kernel<false, false, false, true>,
-      frontier_kernel<false, false, true, false>,  frontier_kernel<false, false, true, true>,
-      frontier_kernel<false, true, false, false>,  frontier_kernel<false, true, false, true>,
-      frontier_kernel<false, true, true, false>,   frontier_kernel<false, true, true, true>,
-      frontier_kernel<true, false, false, false>,  frontier_kernel<true, false, false, true>,
-      frontier_kernel<true, false, true, false>,   frontier_kernel<true, false, true, true>,
-      frontier_kernel<true, true, false, false>,   frontier_kernel<true, true, false, true>,
-      frontier_kernel<true, true, true, false>,    frontier_kernel<true, true, true, true>,
+      frontier_kernel<false, false, false, false, LIST>, frontier_kernel<false, false, false, true, LIST>,
+      frontier_kernel<false, false, true, false, LIST>,  frontier_kernel<false, false, true, true, LIST>,
+      frontier_kernel<false, true, false, false, LIST>,  frontier_kernel<false, true, false, true, LIST>,
+      frontier_kernel<false, true, true, false, LIST>,   frontier_kernel<false, true, true, true, LIST>,
+      frontier_kernel<true, false, false, false, LIST>,  frontier_kernel<true, false, false, true, LIST>,
+      frontier_kernel<true, false, true, false, LIST>,   frontier_kernel<true, false, true, true, LIST>,
+      frontier_kernel<true, true, false, false, LIST>,   frontier_kernel<true, true, false, true, LIST>,
+      frontier_kernel<true, true, true, false, LIST>,    frontier_kernel<true, true, true, true, LIST>,
   };
   return table[(cd ? 8 : 0) | (ch ? 4 : 0) | (fx ? 2 : 0) | (xo ? 1 : 0)];
 }
@@ -620,23 +553,23 @@ static KernelFn kernel_for(const KParams& P) {
   const bool fx = (P.flags & BF_EVAL_FIXPOINT) != 0;
   const bool xo = P.off_fail != BF_OFF_NONE || P.off_needs_cond != BF_OFF_NONE || P.off_skip_dep != BF_OFF_NONE ||
                   P.off_phase_out != BF_OFF_NONE;
-  return pick_kernel(cd, ch, fx, xo);
+  return P.run_list ? pick_kernel<true>(cd, ch, fx, xo) : pick_kernel<false>(cd, ch, fx, xo);
 }
 
 cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream) {
   KernelFn fn = kernel_for(P);
-  static KernelFn configured[8][16] = {};
+  static KernelFn configured[8][32] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   bool known = false;
   if (dev >= 0 && dev < 8)
-    for (int i = 0; i < 16; ++i) known = known || configured[dev][i] == fn;
+    for (int i = 0; i < 32; ++i) known = known || configured[dev][i] == fn;
   if (!known) {
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 8)
-      for (int i = 0; i < 16; ++i)
+      for (int i = 0; i < 32; ++i)
         if (configured[dev][i] == nullptr) { configured[dev][i] = fn; break; }
   }
   fn<<<grid, P.warps_per_block * 32, smem_bytes, stream>>>(P);

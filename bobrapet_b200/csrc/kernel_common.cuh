@@ -1,0 +1,169 @@
+// kernel_common.cuh — PTX / bit-plane helpers shared by the frontier kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bobrafrontier.h"
+#include "device_record.h"
+
+namespace bf {
+
+#define DI __device__ __forceinline__
+constexpr uint32_t FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------ PTX helpers
+DI uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+DI void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+DI void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+DI uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+DI void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.
+DI void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+DI void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+template <int IMM>
+DI uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(IMM));
+  return r;
+}
+// 16-entry boolean table over a bit-sliced 4-bit code: 3 LOP3 for 32 steps.
+template <uint32_t T16>
+DI uint32_t plut(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
+  const uint32_t lo = lop3<(T16 & 0xFF)>(p2, p1, p0);
+  const uint32_t hi = lop3<((T16 >> 8) & 0xFF)>(p2, p1, p0);
+  return lop3<0xCA>(p3, hi, lo);  // p3 ? hi : lo
+}
+// set the code of the steps in mask m to the constant CODE
+template <int CODE>
+DI void pset(uint32_t m, uint32_t& p0, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  p0 = (CODE & 1) ? (p0 | m) : (p0 & ~m);
+  p1 = (CODE & 2) ? (p1 | m) : (p1 & ~m);
+  p2 = (CODE & 4) ? (p2 | m) : (p2 & ~m);
+  p3 = (CODE & 8) ? (p3 | m) : (p3 & ~m);
+}
+DI uint32_t squeeze4(uint32_t x) {  // bits 0,4,..,28 -> low byte
+  x = (x | (x >> 3)) & 0x03030303u;
+  x = (x | (x >> 6)) & 0x000F000Fu;
+  x = (x | (x >> 12)) & 0xFFu;
+  return x;
+}
+DI uint32_t squeeze2(uint32_t x) {  // bits 0,2,..,30 -> low half
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+  x = (x | (x >> 4)) & 0x00FF00FFu;
+  x = (x | (x >> 8)) & 0xFFFFu;
+  return x;
+}
+DI uint32_t spread4(uint32_t x) {  // inverse of squeeze4
+  x = (x | (x << 12)) & 0x000F000Fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x;
+}
+DI uint32_t bits4_to_bytes(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }  // 4 bits -> 4 0/1 bytes
+DI uint32_t get_nibble(const uint8_t* base, uint32_t i) {
+  const uint32_t v = (base[i >> 1] >> ((i & 1u) * 4u)) & 0xFu;
+  return v == 15u ? 0u : v;
+}
+DI uint32_t redux_or(uint32_t v) { return __reduce_or_sync(FULL, v); }
+DI uint32_t redux_add(uint32_t v) { return __reduce_add_sync(FULL, v); }
+
+DI uint32_t bmsk_clamp(uint32_t pos, uint32_t width) {
+  uint32_t r;
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(pos), "r"(width));
+  return r;
+}
+
+// ---- shared-space accessors on 32-bit addresses (keeps the walk's address math in 32 bits) ----
+DI uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+DI uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+DI uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// keep a loop-invariant value in a register instead of letting the compiler rematerialise it from constants
+DI uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+
+// ------------------------------------------------------------------ stage D: the dependency walk
+// One step per lane over the CSR rows of the candidate steps (findReadySteps, dag.go:2711-2733), visiting only
+// the 32-step words that hold a candidate, TWO words per loop trip so two independent load chains overlap.
+// Status byte of a dependency: bit0 = not satisfied, bit1 = failed dependency.  The first four deps of a row
+// are fetched branch-free (index clamped into the status array, verdict masked by the row length); longer rows
+// exist only when the topology header says so.
+//
+// Lane l of the CAND mask = group g = l >> lg (one StoryRun of the trip), word j = l & (2^lg - 1):
+//   row_ptr of group g at rp0 + g*topo_buf (u16 entries), status bytes of group g at st0 + (g << (5+lg)),
+//   col_addr / meta are per-lane (group-uniform) values fetched from the word's owner lane.
+struct WalkOne {
+  bool cand, unmet, fdp;
+};
+DI WalkOne walk_word(uint32_t lane, uint32_t L, bool enable, uint32_t CAND, uint32_t lg, uint32_t col_addr, uint32_t meta,
+                     uint32_t rp0, uint32_t topo_buf, uint32_t st0) {
+  const uint32_t g = L >> lg, j = L & ((1u << lg) - 1u);
+  const uint32_t candw = __shfl_sync(FULL, CAND, L);
+  const uint32_t cola = __shfl_sync(FULL, col_addr, L);
+  const uint32_t mt = __shfl_sync(FULL, meta, L);  // zidx | max_deg << 16
+  const uint32_t zidx = mt & 0xFFFFu;
+  const uint32_t rpa = rp0 + g * topo_buf + (j * 32u + lane) * 2u;
+  const uint32_t sta = st0 + (g << (5u + lg));
+  WalkOne o;
+  o.cand = enable && ((candw >> lane) & 1u);
+  uint32_t e0 = 0, n = 0;
+  if (o.cand) {
+    e0 = lds_u16(rpa);
+    n = lds_u16(rpa + 2u) - e0;
+  }
+  const uint32_t cpa = cola + e0 * 2u;
+  const uint32_t x0 = lds_u16(cpa), x1 = lds_u16(cpa + 2u), x2 = lds_u16(cpa + 4u), x3 = lds_u16(cpa + 6u);  // may run past the row
+  const uint32_t s0 = lds_u8(sta + min(x0, zidx)), s1 = lds_u8(sta + min(x1, zidx)), s2 = lds_u8(sta + min(x2, zidx)),
+                 s3 = lds_u8(sta + min(x3, zidx));
+  uint32_t w = ((s3 * 256u + s2) * 256u + s1) * 256u + s0;
+  w &= bmsk_clamp(0u, n * 8u);
+  if ((mt >> 16) > 4u) {  // warp-uniform: some row of this topology is longer than 4
+    for (uint32_t e = 4; e < n; ++e) w |= lds_u8(sta + lds_u16(cpa + e * 2u));
+  }
+  o.unmet = (w & 0x01010101u) != 0;
+  o.fdp = (w & 0x02020202u) != 0;
+  return o;
+}
+
+DI void walk_deps2(uint32_t lane, uint32_t CAND, uint32_t lg, uint32_t col_addr, uint32_t meta, uint32_t rp0, uint32_t topo_buf,
+                   uint32_t st0, uint32_t& met_w, uint32_t& fd_w) {
+  met_w = 0;
+  fd_w = 0;
+  uint32_t todo = __ballot_sync(FULL, CAND != 0);  // (run, word) pairs with at least one candidate step
+  while (todo) {
+    const uint32_t L1 = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const bool two = todo != 0;
+    const uint32_t L2 = two ? __ffs(todo) - 1 : L1;
+    todo &= todo - 1;  // (0 & -1 == 0 when there was no second word)
+    const WalkOne a = walk_word(lane, L1, true, CAND, lg, col_addr, meta, rp0, topo_buf, st0);
+    const WalkOne b = walk_word(lane, L2, two, CAND, lg, col_addr, meta, rp0, topo_buf, st0);
+    const uint32_t fd1 = __ballot_sync(FULL, a.fdp), met1 = __ballot_sync(FULL, a.cand && !a.unmet);
+    const uint32_t fd2 = __ballot_sync(FULL, b.fdp), met2 = __ballot_sync(FULL, b.cand && !b.unmet);
+    if (lane == L1) { fd_w = fd1; met_w = met1; }
+    if (two && lane == L2) { fd_w = fd2; met_w = met2; }
+  }
+}
+
+}  // namespace bf

@@ -24,6 +24,17 @@ def fr():
     f.close()
 
 
+@pytest.fixture(params=["general", "quad"])
+def kernel(request, monkeypatch):
+    """general = the default one-run-per-warp kernel; quad = the opt-in packed-lanes kernel (R runs per warp trip,
+    runs whose topology has parallel steps deferred to the general kernel).  Both must equal the oracle."""
+    if request.param == "quad":
+        monkeypatch.setenv("BF_KERNEL", "quad")
+    else:
+        monkeypatch.delenv("BF_KERNEL", raising=False)
+    return request.param
+
+
 def _compare(fr, ts, slots, L, state, flags=0, max_iter=0, expansion=False):
     pt = PK.PackedTopologies(ts, slots)
     want, wcounts = PK.evaluate(pt, L, state, flags, max_iter, threads=8)
@@ -59,7 +70,7 @@ def test_child_first_rule_matches_library(fr):
 @pytest.mark.parametrize("cfg,n,S", [(2, 3000, 64), (3, 3000, 256), (4, 3000, 256), (5, 600, 1024),
                                      (3, 500, 1), (3, 500, 2), (3, 500, 31), (3, 500, 32), (3, 500, 33),
                                      (3, 500, 100), (4, 500, 200), (3, 300, 1000), (4, 300, 1023)])
-def test_synthetic_configs(fr, cfg, n, S):
+def test_synthetic_configs(fr, kernel, cfg, n, S):
     ts = synth.topologies(cfg, 0, n, S)
     slots = fr.put_topologies(ts)
     pt = PK.PackedTopologies(ts, slots)
@@ -84,7 +95,23 @@ def test_random_adversarial(fr, seed, mode):
     _compare(fr, ts, slots, L, state, flags=(A.EVAL_FIXPOINT if mode == "fixpoint" else 0), expansion=True)
 
 
-def test_minimal_layout_outputs_only_ready_skip(fr):
+@pytest.mark.parametrize("seed", range(8))
+def test_random_adversarial_no_parallel(fr, kernel, seed):
+    """all phase codes / groups / flags / FAIL codes, no parallel steps: the packed-lanes kernel's domain"""
+    rng = np.random.default_rng(5000 + seed)
+    smax = [40, 257, 1024, 96, 600, 33, 8, 130][seed]
+    ts = randgen.random_topologies(rng, 60, 1, smax, parallel=False)
+    slots = fr.put_topologies(ts)
+    n = [4000, 4001, 999, 4003, 1500, 4005, 4006, 4007][seed]
+    L, state, _ = randgen.random_state(rng, ts, slots, n, ALL if seed % 3 else (A.F_COND | A.F_ALL_OUT),
+                                       phase_mix=("any" if seed % 2 else "progress"))
+    _compare(fr, ts, slots, L, state)
+    st = fr.stats()
+    # the ctx also holds topologies with parallel steps (earlier tests): auto = packed lanes + deferred general
+    assert st["last_kernel"] == (0 if kernel == "general" else 2), st
+
+
+def test_minimal_layout_outputs_only_ready_skip(fr, kernel):
     rng = np.random.default_rng(77)
     ts = randgen.random_topologies(rng, 30, 5, 200, parallel=False)
     slots = fr.put_topologies(ts)
@@ -92,7 +119,7 @@ def test_minimal_layout_outputs_only_ready_skip(fr):
     _compare(fr, ts, slots, L, state)
 
 
-def test_shared_topology_mode(fr):
+def test_shared_topology_mode(fr, kernel):
     """D << N: many runs per topology (records come from L2 instead of HBM)."""
     ts = synth.topologies(3, 0, 8, 256)
     slots = fr.put_topologies(ts)
@@ -131,6 +158,27 @@ def test_topology_rejections(fr):
     with pytest.raises(A.FrontierError) as e:
         fr.put_topologies(unknown)
     assert "unknown step dependency" in str(e.value)                          # dag_test.go:206
+
+
+def test_packed_lanes_only_context(monkeypatch):
+    """a ctx whose topologies have no parallel steps runs the packed-lanes kernel alone (4 runs per trip at S=256)"""
+    monkeypatch.setenv("BF_KERNEL", "quad")
+    f = Frontier(0)
+    try:
+        ts = synth.topologies(4, 0, 3001, 256)
+        slots = f.put_topologies(ts)
+        L = make_layout(256, 0, ALL)
+        state = synth.state(4, 0, 3001, L, slots, ts)
+        _compare(f, ts, slots, L, state)
+        st = f.stats()
+        assert st["last_kernel"] == 1 and st["last_runs_per_trip"] == 4, st
+        ts2 = synth.topologies(2, 0, 777, 64)
+        s2 = f.put_topologies(ts2)
+        L2 = make_layout(64, 0, A.F_ALL_OUT)
+        _compare(f, ts2, s2, L2, synth.state(2, 0, 777, L2, s2, ts2))
+        assert f.stats()["last_runs_per_trip"] in (8, 16)  # the ctx-wide largest record bounds the stage
+    finally:
+        f.close()
 
 
 def test_drop_and_reuse_slot(fr):
