@@ -113,8 +113,11 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_arm(args, cfg, S, sample_runs, threads, reps):
-    """Time the CPU oracle (kind 'port') on a bounded sample of the workload."""
+def cpu_arm(args, cfg, S, sample_runs, threads, reps, impl="refshape"):
+    """Time a CPU restatement of the reference's per-iteration work on a bounded sample of the workload.
+
+    impl="refshape": oracle/refshape.cc — the reference's own data shapes (string-keyed maps, dependency graph
+    rebuilt per pass, buildStateMaps as often as dag.go calls it); impl="packed": oracle/packed_ref.c (bitmask)."""
     from bobrapet_b200 import _abi as A, synth
     from bobrapet_b200.records import make_layout
     from oracle import packed as PK
@@ -125,8 +128,18 @@ def cpu_arm(args, cfg, S, sample_runs, threads, reps):
     L = make_layout(S, child, fields)
     st = synth.state(cfg, 0, sample_runs, L, np.arange(sample_runs, dtype=np.uint32), ts,
                      pt.child_first[:int(ts.P[0])] if child else None)
-    PK.evaluate(pt, L, st, 0, 0, threads)  # warm
     times = []
+    if impl == "refshape":
+        rs = PK.RefShapeBatch(pt, L, st)  # object construction is untimed (the informer cache holds objects)
+        rs.run(threads)  # warm
+        evals = 0
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            _, evals = rs.run(threads)
+            times.append(time.perf_counter() - t0)
+        rs.close()
+        return evals, times
+    PK.evaluate(pt, L, st, 0, 0, threads)  # warm
     for _ in range(reps):
         t0 = time.perf_counter()
         _, counts = PK.evaluate(pt, L, st, 0, 0, threads)
@@ -148,7 +161,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample = args.cpu_sample_runs or 20_000
+        sample = args.cpu_sample_runs or min(20_000, 250 * cores)
         for _ in range(max(args.warmup, 0)):
             pass  # warm-up happens inside cpu_arm (one untimed pass)
         evals, times = cpu_arm(args, cfg, S, sample, cores, max(args.steps, 1))
@@ -158,9 +171,9 @@ def main():
                 "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / len(times), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 bitmask", "data": "synthetic",
                 "config": {"workload": "cfg%d: %d StoryRuns x %d steps sample of BASELINE configs[%d]" % (cfg, sample, S, cfg - 1),
-                           "impl_note": "reference is Go (no toolchain here): CPU oracle restatement oracle/packed_ref.c"},
+                           "impl_note": "reference is Go (no toolchain here): reference-shaped C++ restatement oracle/refshape.cc"},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": "%d StoryRuns x %d steps per step, %d threads" % (sample, S, cores)},
+                                 "sample": "oracle/refshape.cc, %d StoryRuns x %d steps per step, %d threads" % (sample, S, cores)},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -337,10 +350,15 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if not args.no_cpu and rank == 0 and world == 1:
-        sample = args.cpu_sample_runs or 20_000
-        evals, times = cpu_arm(args, cfg, S, sample, cores, 5)
+        sample = args.cpu_sample_runs or min(20_000, 250 * cores)
+        evals, times = cpu_arm(args, cfg, S, sample, cores, 3, "refshape")
+        ev8, t8 = cpu_arm(args, cfg, S, sample, min(8, cores), 3, "refshape")
+        evp, tp = cpu_arm(args, cfg, S, sample, cores, 5, "packed")
         cpu = {"value": evals / float(np.median(times)), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "oracle/packed_ref.c on %d StoryRuns x %d steps, %d threads, median of 5 (Go reference not buildable here)" % (sample, S, cores)}
+               "sample": "oracle/refshape.cc (reference-shaped: string-keyed maps, per-pass graph rebuild) on %d StoryRuns x %d steps, "
+                         "%d threads, median of 3; the Go reference itself cannot be built here" % (sample, S, cores),
+               "at_8_threads": ev8 / float(np.median(t8)),   # the reference's default MaxConcurrentReconciles
+               "packed_cpu": {"value": evp / float(np.median(tp)), "threads": cores, "impl": "oracle/packed_ref.c (bitmask)"}}
 
     if rank == 0:
         line = {

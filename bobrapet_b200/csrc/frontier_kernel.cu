@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
         for (uint32_t q = 0; q < nP; ++q) {
           if (!((registered >> q) & 1ull)) continue;
           const ParDesc d = pd[q];
+          if (d.branches == 0) continue;  // no children to wait for (dag.go:1140-1143)
           const uint32_t wj = d.step >> 5, wb = d.step & 31u;
           const uint32_t ph = ((__shfl_sync(FULL, p0, wj) >> wb) & 1u) | (((__shfl_sync(FULL, p1, wj) >> wb) & 1u) << 1) |
                               (((__shfl_sync(FULL, p2, wj) >> wb) & 1u) << 2) | (((__shfl_sync(FULL, p3, wj) >> wb) & 1u) << 3);

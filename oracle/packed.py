@@ -120,3 +120,55 @@ def expand(pt: PackedTopologies, L, state: np.ndarray, result: np.ndarray, cap: 
     if rc != 0:
         raise RuntimeError("orc_packed_expand failed: %d" % rc)
     return out[:min(cap, n_out.value)], int(n_out.value)
+
+
+# ---------------------------------------------------------------------------------------------
+# refshape.cc — the reference-SHAPED restatement (string-keyed maps, per-pass graph rebuild)
+# ---------------------------------------------------------------------------------------------
+_RS = None
+
+
+def _rs():
+    global _RS
+    if _RS is None:
+        so = os.path.join(_HERE, "_build", "librefshape.so")
+        src = os.path.join(_HERE, "refshape.cc")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(so), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread",
+                                   "-I" + os.path.join(_HERE, "..", "include"), src, "-o", so])
+        lib = C.CDLL(so)
+        lib.orc_refshape_build.restype = C.c_void_p
+        lib.orc_refshape_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.orc_refshape_run.restype = C.c_uint64
+        lib.orc_refshape_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.orc_refshape_free.restype = None
+        lib.orc_refshape_free.argtypes = [C.c_void_p]
+        _RS = lib
+    return _RS
+
+
+class RefShapeBatch:
+    """Object-form Stories / StoryRuns rebuilt from packed records; run() = one runDagIterations iteration each."""
+
+    def __init__(self, pt: PackedTopologies, L, state: np.ndarray):
+        self.pt, self.L, self.n = pt, L, int(state.shape[0])
+        self.h = _rs().orc_refshape_build(pt.table.ctypes.data, pt.n_slots, C.addressof(L), self.n, state.ctypes.data)
+        if not self.h:
+            raise RuntimeError("orc_refshape_build failed (bad slot)")
+
+    def run(self, threads: int = 1):
+        result = np.zeros((self.n, self.L.result_stride), dtype=np.uint8)
+        evals = _rs().orc_refshape_run(self.h, result.ctypes.data, threads)
+        return result, int(evals)
+
+    def close(self):
+        if self.h:
+            _rs().orc_refshape_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -133,7 +133,7 @@ static void eval_run(const orc_topology* T, const bf_layout* L, const uint8_t* s
         const bf_parallel_desc* d = &T->parallel[q];
         int p = s->phase[d->step];
         if (p == BF_PHASE_NONE || is_term(p)) continue;         /* :1136-1139 */
-        if (!((registered >> q) & 1ull)) continue;              /* :1140-1143 */
+        if (!((registered >> q) & 1ull) || d->branches == 0) continue; /* :1140-1143: no registered children */
         int all_done = 1, any_failed = 0;
         for (uint32_t b = 0; b < d->branches; ++b) {
           int cp = get_nib(child, T->child_first[q] + b);

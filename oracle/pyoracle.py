@@ -966,16 +966,15 @@ def run_dag_iteration(srun: StoryRun, story: Story, step_runs: Optional[List[Ste
                       host_group: Optional[str] = None, dep_order: str = "failed_first",
                       offloaded_policy: str = "fail") -> IterationResult:
     """One pass of the loop body dag.go:393-540 up to and including findReadySteps
-    (no launch effects).  host_group != None reproduces contract tier K1: the caller
-    has applied G/H/I and supplies the group."""
+    (no launch effects).  host_group != None reproduces contract tier K1 (BF_RF_HOST_GROUP): the caller
+    supplies the group and stage I (fail-fast / compensation marking, group selection) is skipped."""
     vars_ = vars_ if vars_ is not None else {"inputs": {}, "steps": {}}
     all_steps = all_story_steps(story)
+    check_sync_gates(srun, story, all_steps, now, timers)                      # dag.go:409
+    check_sync_sleep_steps(srun, story, all_steps, now, timers)                # :412
+    check_sync_wait_steps(srun, story, all_steps, evaluator, vars_, now, timers, offloaded_policy)  # :415
+    check_sync_parallel_steps(srun, all_steps, step_runs, now)                 # :418
     if host_group is None:
-        check_sync_gates(srun, story, all_steps, now, timers)                      # dag.go:409
-        check_sync_sleep_steps(srun, story, all_steps, now, timers)                # :412
-        check_sync_wait_steps(srun, story, all_steps, evaluator, vars_, now, timers, offloaded_policy)  # :415
-        check_sync_parallel_steps(srun, all_steps, step_runs, now)                 # :418
-
         main_completed, main_running, main_failed, _ = build_state_maps(story.steps, srun.step_states)  # :422
         clear_concurrency_queued_steps(main_running, srun.step_states)
         if should_fail_fast(story) and len(main_failed) > 0:                        # :424
