@@ -25,6 +25,8 @@ cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, u
 int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
 cudaError_t launch_frontier_quad(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
 int frontier_quad_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
+cudaError_t launch_validate(const Slot* slots, const uint32_t* slot_ids, uint32_t n, uint32_t n_slots, uint32_t* status,
+                            cudaStream_t stream);
 }  // namespace bf
 
 namespace {
@@ -114,7 +116,7 @@ struct RecPlan {
   std::vector<uint32_t> child_first, allow_off;
 };
 
-int plan_record(const bf_topology& t, RecPlan& p, std::string& why) {
+int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_kahn = true) {
   if (t.n_steps == 0 || t.n_steps > BF_MAX_STEPS) { why = "n_steps out of range (1..1024)"; return BF_ETOPO; }
   if (t.n_edges > BF_MAX_EDGES) { why = "n_edges exceeds 65535"; return BF_ETOPO; }
   if (!t.row_ptr || !t.step_flags || (t.n_edges && !t.col_idx)) { why = "null topology array"; return BF_EINVAL; }
@@ -127,7 +129,7 @@ int plan_record(const bf_topology& t, RecPlan& p, std::string& why) {
   for (uint32_t e = 0; e < E; ++e)
     if (t.col_idx[e] >= S) { why = "unknown step dependency (col_idx >= S)"; return BF_ETOPO; }  // dag.go:3087-3098
   // acyclicity (Kahn), dag.go:3100-3145.  indegree[i] = number of deps of i.
-  {
+  if (host_kahn) {
     std::vector<uint32_t> indeg(S), head(S + 1, 0), out(E), stack;
     for (uint32_t i = 0; i < S; ++i) indeg[i] = t.row_ptr[i + 1] - t.row_ptr[i];
     for (uint32_t e = 0; e < E; ++e) head[t.col_idx[e] + 1]++;
@@ -455,12 +457,12 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   return BF_OK;
 }
 
-int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_t* slots_out) {
+int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_t* slots_out, bool host_kahn = true) {
   std::vector<RecPlan> plans(count);
   size_t total = 0;
   std::string why;
   for (uint32_t i = 0; i < count; ++i) {
-    const int rc = plan_record(topos[i], plans[i], why);
+    const int rc = plan_record(topos[i], plans[i], why, host_kahn);
     if (rc != BF_OK) return fail(c, rc, "topology " + std::to_string(i) + ": " + why);
     total += plans[i].rec_bytes;
   }
@@ -565,9 +567,49 @@ int bf_topology_put_many(bf_ctx* c, const bf_topology* topos, uint32_t count, ui
 
 int bf_topology_put(bf_ctx* c, const bf_topology* topo, uint32_t* slot_out) { return bf_topology_put_many(c, topo, 1, slot_out); }
 
-int bf_topology_drop(bf_ctx* c, uint32_t slot) {
-  if (!c) return BF_EINVAL;
+static int check_locked(bf_ctx* c, const uint32_t* slots, uint32_t count, uint32_t* status_out) {
+  if (count == 0) return BF_OK;
+  if (int rc = sync_slots(c, c->stream)) return rc;
+  uint32_t* d_ids = nullptr;
+  uint32_t* d_status = nullptr;
+  BF_CUDA(c, cudaMalloc(&d_ids, (size_t)count * 4));
+  if (cudaMalloc(&d_status, (size_t)count * 4) != cudaSuccess) { cudaFree(d_ids); return fail(c, BF_ENOMEM, "cudaMalloc status"); }
+  cudaError_t e = cudaMemcpyAsync(d_ids, slots, (size_t)count * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = bf::launch_validate(c->slots_dev, d_ids, count, (uint32_t)c->slots_host.size(), d_status, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(status_out, d_status, (size_t)count * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_ids);
+  cudaFree(d_status);
+  if (e != cudaSuccess) return cuda_fail(c, e, "device validation");
+  c->stats.kernel_launches += 1;
+  return BF_OK;
+}
+
+int bf_topology_check(bf_ctx* c, const uint32_t* slots, uint32_t count, uint32_t* status_out) {
+  if (!c || (count && (!slots || !status_out))) return BF_EINVAL;
   std::lock_guard<std::mutex> g(c->mu);
+  BF_CUDA(c, cudaSetDevice(c->device));
+  return check_locked(c, slots, count, status_out);
+}
+
+static int drop_locked(bf_ctx* c, uint32_t slot);
+
+int bf_topology_put_many_checked_on_device(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_t* slots_out,
+                                           uint32_t* status_out) {
+  if (!c || (count && (!topos || !slots_out || !status_out))) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  BF_CUDA(c, cudaSetDevice(c->device));
+  if (int rc = put_many_locked(c, topos, count, slots_out, /*host_kahn=*/false)) return rc;
+  if (int rc = check_locked(c, slots_out, count, status_out)) return rc;
+  for (uint32_t i = 0; i < count; ++i)
+    if (status_out[i] & 1u) {  // "dependency cycle detected", dag.go:3145
+      drop_locked(c, slots_out[i]);
+      slots_out[i] = 0xFFFFFFFFu;
+    }
+  return BF_OK;
+}
+
+static int drop_locked(bf_ctx* c, uint32_t slot) {
   if (slot >= c->meta.size() || !c->meta[slot].alive) return fail(c, BF_ETOPO, "drop of an unknown slot");
   c->meta[slot].alive = false;
   if (c->meta[slot].P) c->n_with_parallel--;
@@ -580,6 +622,12 @@ int bf_topology_drop(bf_ctx* c, uint32_t slot) {
     c->max_rec_bytes = 0;
   }
   return BF_OK;
+}
+
+int bf_topology_drop(bf_ctx* c, uint32_t slot) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  return drop_locked(c, slot);
 }
 
 int bf_topology_child_first(const bf_ctx* c, uint32_t slot, uint32_t* out, uint32_t cap) {

@@ -96,6 +96,24 @@ class Frontier:
         self._check(rc, "bf_topology_put_many")
         return slots
 
+    def put_topologies_checked_on_device(self, ts: TopologySet):
+        """Bulk upload with acyclicity checked by the device kernel -> (slots, status words)."""
+        desc = ts.descriptors()
+        slots = np.zeros(ts.count, dtype=np.uint32)
+        status = np.zeros(ts.count, dtype=np.uint32)
+        rc = self._lib.bf_topology_put_many_checked_on_device(
+            self._ctx, desc.ctypes.data_as(C.POINTER(A.Topology)), ts.count, slots.ctypes.data_as(C.POINTER(C.c_uint32)),
+            status.ctypes.data_as(C.POINTER(C.c_uint32)))
+        self._check(rc, "bf_topology_put_many_checked_on_device")
+        return slots, status
+
+    def check_topologies(self, slots) -> np.ndarray:
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        status = np.zeros(slots.shape[0], dtype=np.uint32)
+        self._check(self._lib.bf_topology_check(self._ctx, slots.ctypes.data_as(C.POINTER(C.c_uint32)), slots.shape[0],
+                                                status.ctypes.data_as(C.POINTER(C.c_uint32))), "bf_topology_check")
+        return status
+
     def drop_topology(self, slot: int):
         self._check(self._lib.bf_topology_drop(self._ctx, int(slot)), "bf_topology_drop")
 

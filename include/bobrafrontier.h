@@ -276,6 +276,14 @@ void bf_destroy(bf_ctx* ctx);
 int bf_topology_put(bf_ctx* ctx, const bf_topology* topo, uint32_t* slot_out);
 /* Bulk form: `count` topologies, one bf_topology each; slots_out[count].      */
 int bf_topology_put_many(bf_ctx* ctx, const bf_topology* topos, uint32_t count, uint32_t* slots_out);
+/* Device-validated bulk upload: unknown deps are still checked on the host, acyclicity is
+ * checked by a kernel over the uploaded records (one warp per topology, level-synchronous peeling) instead of
+ * the host's Kahn pass.  status_out[i]: bit 0 = cycle detected (the topology is dropped, slots_out[i] =
+ * 0xFFFFFFFF), bits 8.. = number of dependency levels.  Returns BF_OK even when some topologies are cyclic. */
+int bf_topology_put_many_checked_on_device(bf_ctx* ctx, const bf_topology* topos, uint32_t count, uint32_t* slots_out,
+                                           uint32_t* status_out);
+/* Re-validate already uploaded topologies on the device (status words as above; 0xFFFFFFFF = unknown slot). */
+int bf_topology_check(bf_ctx* ctx, const uint32_t* slots, uint32_t count, uint32_t* status_out);
 int bf_topology_drop(bf_ctx* ctx, uint32_t slot);
 /* Nibble offset of parallel desc p's children inside the child area.          */
 int bf_topology_child_first(const bf_ctx* ctx, uint32_t slot, uint32_t* child_first_out, uint32_t cap);
