@@ -25,6 +25,10 @@ cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, u
 int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
 cudaError_t launch_frontier_quad(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
 int frontier_quad_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
+uint32_t split_entry_bytes(const KParams& P);
+int walk_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
+cudaError_t launch_classify(const KParams& P, uint32_t sm_count, cudaStream_t stream);
+cudaError_t launch_walk(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_validate(const Slot* slots, const uint32_t* slot_ids, uint32_t n, uint32_t n_slots, uint32_t* status,
                             cudaStream_t stream);
 }  // namespace bf
@@ -58,6 +62,8 @@ struct bf_ctx {
   std::vector<bf::Slot> slots_host;
   bf::Slot* slots_dev = nullptr;
   size_t slots_dev_cap = 0;
+  std::vector<bf::SlotInfo> info_host;
+  bf::SlotInfo* info_dev = nullptr;
   bool slots_dirty = true;
   uint32_t max_rec_bytes = 0;
   uint32_t n_alive = 0;
@@ -73,6 +79,9 @@ struct bf_ctx {
   unsigned long long* d_offsets = nullptr; size_t d_offsets_cap = 0;
   unsigned long long* d_block_sums = nullptr; size_t d_block_sums_cap = 0;
   uint32_t* d_defer = nullptr; size_t d_defer_cap = 0;  // [0] = count, [1..] = run ids
+  uint8_t* d_walk = nullptr; size_t d_walk_cap = 0;      // phase-1 -> phase-2 entries
+  uint32_t* d_walk_count = nullptr;
+  uint32_t max_csr_bytes = 0;
 
   // cached shared-memory plan (recomputed when the layout or the largest record changes)
   uint32_t plan_key_stride = 0, plan_key_words = 0, plan_key_rec = 0, plan_key_variant = 0xFFFFFFFFu;
@@ -255,7 +264,10 @@ int grow_arena(bf_ctx* c, size_t need_total) {
   c->arena = na;
   c->arena_cap = ncap;
   for (size_t s = 0; s < c->meta.size(); ++s)
-    if (c->meta[s].alive) c->slots_host[s].addr = (uint64_t)(uintptr_t)(c->arena + c->meta[s].offset);
+    if (c->meta[s].alive) {
+      c->slots_host[s].addr = (uint64_t)(uintptr_t)(c->arena + c->meta[s].offset);
+      c->info_host[s].addr = c->slots_host[s].addr;
+    }
   c->slots_dirty = true;
   return BF_OK;
 }
@@ -270,9 +282,14 @@ int sync_slots(bf_ctx* c, cudaStream_t stream) {
     BF_CUDA(c, cudaMalloc(&np, ncap * sizeof(bf::Slot)));
     if (c->slots_dev) cudaFree(c->slots_dev);
     c->slots_dev = np;
+    bf::SlotInfo* ip = nullptr;
+    BF_CUDA(c, cudaMalloc(&ip, ncap * sizeof(bf::SlotInfo)));
+    if (c->info_dev) cudaFree(c->info_dev);
+    c->info_dev = ip;
     c->slots_dev_cap = ncap;
   }
   if (n) BF_CUDA(c, cudaMemcpyAsync(c->slots_dev, c->slots_host.data(), n * sizeof(bf::Slot), cudaMemcpyHostToDevice, stream));
+  if (n) BF_CUDA(c, cudaMemcpyAsync(c->info_dev, c->info_host.data(), n * sizeof(bf::SlotInfo), cudaMemcpyHostToDevice, stream));
   BF_CUDA(c, cudaStreamSynchronize(stream));
   c->slots_dirty = false;
   return BF_OK;
@@ -339,9 +356,78 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   // Default: the general kernel (one run per warp).  The packed-lanes kernel executes ~17% fewer warp
   // instructions per run but measured no faster (the same ~64 runs fit an SM's shared memory either way and
   // its per-trip walk is longer), so it stays an opt-in experiment: BF_KERNEL=quad.
-  bool quad = false;
+  bool quad = false, split = false;
   if (const char* env_k = getenv("BF_KERNEL")) {
+    if (!strcmp(env_k, "split")) split = !(b.flags & BF_EVAL_FIXPOINT) && c->n_with_parallel != c->n_alive;
     if (!strcmp(env_k, "quad")) quad = !(b.flags & BF_EVAL_FIXPOINT) && c->n_with_parallel != c->n_alive;
+  }
+  if (split) {
+    // ---- two-phase path: classify every run, walk only the runs that have candidate steps ----
+    P.wq = 1; P.wq_log2 = 0;
+    while (P.wq < L.words) { P.wq <<= 1; P.wq_log2++; }
+    P.slot_info = c->info_dev;
+    P.walk_entry_bytes = bf::split_entry_bytes(P);
+    if (int rc = ensure_dev(c, c->d_walk, c->d_walk_cap, (size_t)b.n_runs * P.walk_entry_bytes + 16)) return rc;
+    if (!c->d_walk_count) BF_CUDA(c, cudaMalloc(&c->d_walk_count, 16));
+    P.walk_entries = c->d_walk; P.walk_count = c->d_walk_count;
+    const bool tiered = c->n_with_parallel != 0;
+    if (tiered) {
+      if (int rc = ensure_dev(c, c->d_defer, c->d_defer_cap, (size_t)b.n_runs + 1)) return rc;
+      P.defer_count = c->d_defer; P.defer_list = c->d_defer + 1;
+      BF_CUDA(c, cudaMemsetAsync(c->d_defer, 0, sizeof(uint32_t), stream));
+    }
+    BF_CUDA(c, cudaMemsetAsync(c->d_walk_count, 0, sizeof(uint32_t), stream));
+    // phase-2 shared-memory plan: stage = entry + CSR block
+    P.topo_buf_bytes = round_up(c->max_csr_bytes, 16);
+    P.work_bytes = round_up(4 * L.words, 16) + 32 * L.words + 16;
+    const uint32_t stage2 = P.walk_entry_bytes + P.topo_buf_bytes;
+    const uint32_t budget = 227u * 1024u - 128u;
+    uint32_t st = 2, wpb = 16;
+    if (const char* e = getenv("BF_STAGES")) st = (uint32_t)atoi(e);
+    if (const char* e = getenv("BF_WARPS")) wpb = (uint32_t)atoi(e);
+    if (st < 1) st = 1;
+    if (st > 8) st = 8;
+    while (wpb > 1 && 128 + wpb * (st * stage2 + P.work_bytes + 64) > budget / 2) wpb = wpb > 4 ? wpb - 4 : wpb - 1;  // aim at 2 CTAs per SM
+    while (st > 1 && 128 + wpb * (st * stage2 + P.work_bytes + 64) > budget) --st;
+    if (128 + wpb * (st * stage2 + P.work_bytes + 64) > budget) return fail(c, BF_ETOPO, "CSR block does not fit shared memory");
+    P.stages = st; P.warps_per_block = wpb;
+    const uint32_t smem2 = 128 + wpb * (st * stage2 + P.work_bytes + 64);
+    int per_sm = bf::walk_max_blocks_per_sm(P, wpb * 32, smem2);
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid2 = (uint32_t)c->sm_count * (uint32_t)per_sm;
+    const uint32_t nb2 = (b.n_runs + wpb - 1) / wpb;
+    if (grid2 > nb2) grid2 = nb2 ? nb2 : 1;
+    if (b.n_runs) {
+      BF_CUDA(c, bf::launch_classify(P, (uint32_t)c->sm_count, stream));
+      BF_CUDA(c, bf::launch_walk(P, grid2, smem2, stream));
+      c->stats.kernel_launches += 2;
+      if (tiered) {  // third tier: runs whose topology has parallel steps -> general kernel over the defer list
+        bf::KParams P2 = P;
+        P2.defer_list = nullptr; P2.defer_count = nullptr;
+        P2.run_list = c->d_defer + 1; P2.run_list_count = c->d_defer;
+        P2.topo_buf_bytes = round_up(c->max_rec_bytes, 16);
+        P2.stage_bytes = L.state_stride + P2.topo_buf_bytes;
+        uint32_t st3 = 2, wpb3 = 16;
+        while (wpb3 > 1 && 128 + wpb3 * (st3 * P2.stage_bytes + P2.work_bytes + 64) > budget) wpb3 = wpb3 > 4 ? wpb3 - 4 : wpb3 - 1;
+        if (128 + wpb3 * (st3 * P2.stage_bytes + P2.work_bytes + 64) > budget) st3 = 1;
+        if (128 + wpb3 * (st3 * P2.stage_bytes + P2.work_bytes + 64) > budget)
+          return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
+        P2.stages = st3; P2.warps_per_block = wpb3;
+        uint32_t grid3 = (uint32_t)c->sm_count;
+        const uint32_t nb3 = (b.n_runs + wpb3 - 1) / wpb3;
+        if (grid3 > nb3) grid3 = nb3 ? nb3 : 1;
+        BF_CUDA(c, bf::launch_frontier(P2, grid3, 128 + wpb3 * (st3 * P2.stage_bytes + P2.work_bytes + 64), stream));
+        c->stats.kernel_launches += 1;
+      }
+      if (want_exp) {
+        uint32_t nl = 0;
+        BF_CUDA(c, bf::launch_expansion(P, c->d_block_sums, c->d_offsets, d_exp, b.expansion_cap, stream, &nl));
+        c->stats.kernel_launches += nl;
+      }
+    }
+    c->stats.last_kernel = tiered ? 4u : 3u; c->stats.last_runs_per_trip = 32u / P.wq;
+    c->stats.last_grid = grid2; c->stats.last_block = wpb * 32; c->stats.last_smem_bytes = smem2; c->stats.last_stages = st;
+    return BF_OK;
   }
   uint32_t wq_min = 1, lg_min = 0;
   while (wq_min < L.words) { wq_min <<= 1; lg_min++; }
@@ -480,13 +566,26 @@ int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_
   for (uint32_t i = 0; i < count; ++i) {
     uint32_t slot;
     if (!c->free_slots.empty()) { slot = c->free_slots.back(); c->free_slots.pop_back(); }
-    else { slot = (uint32_t)c->meta.size(); c->meta.emplace_back(); c->slots_host.push_back(bf::Slot{0, 0, 0}); }
+    else { slot = (uint32_t)c->meta.size(); c->meta.emplace_back(); c->slots_host.push_back(bf::Slot{0, 0, 0}); c->info_host.push_back(bf::SlotInfo{0, 0, 0, 0, 0, 0, 0}); }
     TopoMeta& m = c->meta[slot];
     m.alive = true; m.S = topos[i].n_steps; m.E = topos[i].n_edges; m.P = topos[i].n_parallel;
     m.bytes = plans[i].rec_bytes; m.offset = base + off; m.child_first = plans[i].child_first;
     m.child_nibbles = plans[i].child_nibbles;
     c->slots_host[slot] = bf::Slot{(uint64_t)(uintptr_t)(c->arena + m.offset), m.bytes, m.S | (m.P << 16)};
     if (m.bytes > c->max_rec_bytes) c->max_rec_bytes = m.bytes;
+    {
+      const bf::TopoHeader* th = reinterpret_cast<const bf::TopoHeader*>(staging.data() + off);
+      bf::SlotInfo si;
+      si.addr = c->slots_host[slot].addr;
+      si.csr_bytes = th->off_planes - (uint32_t)sizeof(bf::TopoHeader);
+      si.off_planes = th->off_planes;
+      si.s_w = (uint32_t)th->S | ((uint32_t)th->W << 16);
+      si.deg_p = (uint32_t)th->max_deg | ((uint32_t)th->P << 16);
+      si.main_comp = (uint32_t)th->n_main | ((uint32_t)th->n_comp << 16);
+      si.n_final = th->n_final;
+      c->info_host[slot] = si;
+      if (si.csr_bytes > c->max_csr_bytes) c->max_csr_bytes = si.csr_bytes;
+    }
     off += plans[i].rec_bytes;
     slots_out[i] = slot;
     c->n_alive++;
@@ -553,7 +652,7 @@ void bf_destroy(bf_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
-  cudaFree(c->d_defer); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums);
+  cudaFree(c->d_defer); cudaFree(c->d_walk); cudaFree(c->d_walk_count); cudaFree(c->info_dev); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums);
   delete c;
 }
 
@@ -614,12 +713,14 @@ static int drop_locked(bf_ctx* c, uint32_t slot) {
   c->meta[slot].alive = false;
   if (c->meta[slot].P) c->n_with_parallel--;
   c->slots_host[slot] = bf::Slot{0, 0, 0};
+  c->info_host[slot] = bf::SlotInfo{0, 0, 0, 0, 0, 0, 0};
   c->free_slots.push_back(slot);
   c->n_alive--;
   c->slots_dirty = true;
   if (c->n_alive == 0) {  // arena is a bump allocator: it resets when the last topology goes
     c->arena_used = 0;
     c->max_rec_bytes = 0;
+    c->max_csr_bytes = 0;
   }
   return BF_OK;
 }

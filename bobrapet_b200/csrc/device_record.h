@@ -51,6 +51,31 @@ struct Slot {          // device slot table entry
 };
 static_assert(sizeof(Slot) == 16, "Slot must be 16 bytes");
 
+// Wide slot entry for the two-phase path (frontier_split.cu): everything phase 1 needs about a topology
+// without touching its record header.
+struct SlotInfo {
+  uint64_t addr;        // record address (0 = dead slot)
+  uint32_t csr_bytes;   // bytes of row_ptr + col_idx (record bytes [32, off_planes))
+  uint32_t off_planes;
+  uint32_t s_w;         // S | W << 16
+  uint32_t deg_p;       // max_deg | P << 16
+  uint32_t main_comp;   // n_main | n_comp << 16
+  uint32_t n_final;
+};
+static_assert(sizeof(SlotInfo) == 32, "SlotInfo must be 32 bytes");
+
+// Phase-1 -> phase-2 hand-over entry header (followed by W-word arrays: CAND, U, FD [, c0, c1] [, HIF] [, p0..p3])
+struct WalkEntry {
+  uint64_t csr_addr;    // record address + 32 (row_ptr); col_idx follows, 16-byte aligned
+  uint32_t csr_bytes;
+  uint32_t run;
+  uint32_t meta;        // Wt | max_deg << 16
+  uint32_t summary;     // result-header summary computed by phase 1
+  uint32_t fclass;      // status class of a step set Failed in the loop (0 sat, 1 unmet, 3 unmet+failed-dep)
+  uint32_t col_off;     // byte offset of col_idx inside the CSR block
+};
+static_assert(sizeof(WalkEntry) == 32, "WalkEntry must be 32 bytes");
+
 struct KParams {
   const uint8_t* state;
   uint8_t* result;
@@ -63,6 +88,11 @@ struct KParams {
   uint32_t* defer_count;
   const uint32_t* run_list;
   const uint32_t* run_list_count;
+  // two-phase path
+  const SlotInfo* slot_info;
+  uint8_t* walk_entries;        // [n_runs * walk_entry_bytes], compacted by phase 1
+  uint32_t* walk_count;
+  uint32_t walk_entry_bytes;
   uint32_t n_slots;
   uint32_t n_runs;
   uint32_t flags;               // BF_EVAL_*

@@ -25,63 +25,6 @@
 
 namespace bf {
 
-// ------------------------------------------------------------------ stage D
-// One step per lane per trip over the CSR rows of the candidate steps, visiting only the
-// 32-step words that hold a candidate.  Status byte of a dependency: bit0 = not satisfied,
-// bit1 = failed dependency.  The first four deps of a row are fetched branch-free (index
-// clamped into the status array, verdict masked by the row length); longer rows exist only
-// when the topology header says so.  FIXUP adds the "set Failed earlier in this same loop"
-// visibility rule (dag.go:2744/2810 mutate stepStates while `completed` stays as built at :497).
-template <bool FIXUP>
-DI void walk_deps(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_deg, const uint16_t* __restrict__ row_ptr,
-                  const uint16_t* __restrict__ col, const uint8_t* __restrict__ st, const uint32_t* mFAIL,
-                  uint32_t failed_class, uint32_t& met_w, uint32_t& fd_w) {
-  met_w = 0;
-  fd_w = 0;
-  uint32_t todo = __ballot_sync(FULL, CAND != 0);  // words with at least one candidate step
-  while (todo) {
-    const uint32_t j = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const uint32_t candw = __shfl_sync(FULL, CAND, j);
-    const bool cand = (candw >> lane) & 1u;
-    const uint32_t i = j * 32 + lane;
-    uint32_t e0 = 0, n = 0;
-    if (cand) {
-      e0 = row_ptr[i];
-      n = row_ptr[i + 1] - e0;
-    }
-    const uint16_t* cp = col + e0;
-    bool unmet, fdp;
-    if (!FIXUP) {
-      const uint32_t x0 = cp[0], x1 = cp[1], x2 = cp[2], x3 = cp[3];  // may run past the row: masked below
-      const uint32_t s0 = st[min(x0, zidx)], s1 = st[min(x1, zidx)], s2 = st[min(x2, zidx)], s3 = st[min(x3, zidx)];
-      uint32_t w = ((s3 * 256u + s2) * 256u + s1) * 256u + s0;
-      w &= bmsk_clamp(0u, n * 8u);
-      if (max_deg > 4) {  // warp-uniform
-        for (uint32_t e = 4; e < n; ++e) w |= st[cp[e]];
-      }
-      unmet = (w & 0x01010101u) != 0;
-      fdp = (w & 0x02020202u) != 0;
-    } else {
-      uint32_t acc = 0;
-      for (uint32_t e = 0; e < n; ++e) {
-        const uint32_t d = cp[e];
-        uint32_t sb = st[d];
-        if (d < i && ((mFAIL[d >> 5] >> (d & 31u)) & 1u)) sb = failed_class;
-        acc |= sb;
-      }
-      unmet = (acc & 1u) != 0;
-      fdp = (acc & 2u) != 0;
-    }
-    const uint32_t fdb = __ballot_sync(FULL, fdp);
-    const uint32_t metb = __ballot_sync(FULL, cand && !unmet);
-    if (lane == j) {
-      fd_w = fdb;
-      met_w = metb;
-    }
-  }
-}
-
 extern __shared__ __align__(128) uint8_t smem_raw[];
 
 // CD: cond and/or decision codes present   CH: topologies with `parallel` steps may occur (stage H, expansion count)
@@ -422,7 +365,7 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
         __syncwarp();
         // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
         uint32_t met_w, fd_w;
-        walk_deps<false>(lane, CAND, zidx, max_deg, row_ptr, col, st, mFAIL, 0u, met_w, fd_w);
+        walk_rows<false>(lane, CAND, zidx, max_deg, row_ptr, col, st, mFAIL, 0u, met_w, fd_w);
         uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
         if (CD) {
           ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
@@ -437,7 +380,7 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
               __syncwarp();
               if (act) mFAIL[lane] = fail_w;
               __syncwarp();
-              walk_deps<true>(lane, CAND, zidx, max_deg, row_ptr, col, st, mFAIL, fclass, met_w, fd_w);
+              walk_rows<true>(lane, CAND, zidx, max_deg, row_ptr, col, st, mFAIL, fclass, met_w, fd_w);
               const uint32_t nf = met_w & c0 & c1;
               const bool same = !__any_sync(FULL, nf != fail_w);
               fail_w = nf;

@@ -103,7 +103,103 @@ DI uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%
 // keep a loop-invariant value in a register instead of letting the compiler rematerialise it from constants
 DI uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 
-// ------------------------------------------------------------------ stage D: the dependency walk
+// ------------------------------------------------------------------ stage D: the dependency walk (one run per warp)
+// One step per lane per trip over the CSR rows of the candidate steps, visiting only the 32-step words that hold
+// a candidate.  Status byte of a dependency: bit0 = not satisfied, bit1 = failed dependency.  The first four deps of
+// a row are fetched branch-free (index clamped into the status array, verdict masked by the row length); longer rows
+// exist only when the topology header says so.  FIXUP adds the "set Failed earlier in this same loop" visibility
+// rule (dag.go:2744/2810 mutate stepStates while `completed` stays as built at :497).
+template <bool FIXUP>
+DI void walk_rows(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_deg, const uint16_t* __restrict__ row_ptr,
+                  const uint16_t* __restrict__ col, const uint8_t* __restrict__ st, const uint32_t* mFAIL,
+                  uint32_t failed_class, uint32_t& met_w, uint32_t& fd_w) {
+  met_w = 0;
+  fd_w = 0;
+  uint32_t todo = __ballot_sync(FULL, CAND != 0);  // words with at least one candidate step
+  while (todo) {
+    const uint32_t j = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t candw = __shfl_sync(FULL, CAND, j);
+    const bool cand = (candw >> lane) & 1u;
+    const uint32_t i = j * 32 + lane;
+    uint32_t e0 = 0, n = 0;
+    if (cand) {
+      e0 = row_ptr[i];
+      n = row_ptr[i + 1] - e0;
+    }
+    const uint16_t* cp = col + e0;
+    bool unmet, fdp;
+    if (!FIXUP) {
+      const uint32_t x0 = cp[0], x1 = cp[1], x2 = cp[2], x3 = cp[3];  // may run past the row: masked below
+      const uint32_t s0 = st[min(x0, zidx)], s1 = st[min(x1, zidx)], s2 = st[min(x2, zidx)], s3 = st[min(x3, zidx)];
+      uint32_t w = ((s3 * 256u + s2) * 256u + s1) * 256u + s0;
+      w &= bmsk_clamp(0u, n * 8u);
+      if (max_deg > 4) {  // warp-uniform
+        for (uint32_t e = 4; e < n; ++e) w |= st[cp[e]];
+      }
+      unmet = (w & 0x01010101u) != 0;
+      fdp = (w & 0x02020202u) != 0;
+    } else {
+      uint32_t acc = 0;
+      for (uint32_t e = 0; e < n; ++e) {
+        const uint32_t d = cp[e];
+        uint32_t sb = st[d];
+        if (d < i && ((mFAIL[d >> 5] >> (d & 31u)) & 1u)) sb = failed_class;
+        acc |= sb;
+      }
+      unmet = (acc & 1u) != 0;
+      fdp = (acc & 2u) != 0;
+    }
+    const uint32_t fdb = __ballot_sync(FULL, fdp);
+    const uint32_t metb = __ballot_sync(FULL, cand && !unmet);
+    if (lane == j) {
+      fd_w = fdb;
+      met_w = metb;
+    }
+  }
+}
+
+
+// Same walk with explicit 32-bit shared addresses (ld.shared), for kernels whose CSR / status arrays are given
+// as shared-window addresses: keeps every address computation a single 32-bit add.
+DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_deg, uint32_t rp_addr, uint32_t col_addr,
+                    uint32_t st_addr, uint32_t& met_w, uint32_t& fd_w) {
+  met_w = 0;
+  fd_w = 0;
+  uint32_t todo = __ballot_sync(FULL, CAND != 0);
+  const uint32_t rp_lane = rp_addr + lane * 2u;
+  while (todo) {
+    const uint32_t j = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t candw = __shfl_sync(FULL, CAND, j);
+    const bool cand = (candw >> lane) & 1u;
+    uint32_t e0 = 0, n = 0;
+    if (cand) {
+      const uint32_t a = rp_lane + j * 64u;
+      e0 = lds_u16(a);
+      n = lds_u16(a + 2u) - e0;
+    }
+    const uint32_t cpa = col_addr + e0 * 2u;
+    uint32_t x0, x1, x2, x3;
+    asm volatile("ld.shared.u16 %0, [%4];\n\tld.shared.u16 %1, [%4+2];\n\tld.shared.u16 %2, [%4+4];\n\tld.shared.u16 %3, [%4+6];"
+                 : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(cpa));  // may run past the row: masked below
+    const uint32_t s0 = lds_u8(st_addr + min(x0, zidx)), s1 = lds_u8(st_addr + min(x1, zidx)),
+                   s2 = lds_u8(st_addr + min(x2, zidx)), s3 = lds_u8(st_addr + min(x3, zidx));
+    uint32_t w = ((s3 * 256u + s2) * 256u + s1) * 256u + s0;
+    w &= bmsk_clamp(0u, n * 8u);
+    if (max_deg > 4) {  // warp-uniform
+      for (uint32_t e = 4; e < n; ++e) w |= lds_u8(st_addr + lds_u16(cpa + e * 2u));
+    }
+    const uint32_t fdb = __ballot_sync(FULL, (w & 0x02020202u) != 0);
+    const uint32_t metb = __ballot_sync(FULL, cand && (w & 0x01010101u) == 0);
+    if (lane == j) {
+      fd_w = fdb;
+      met_w = metb;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the same walk for packed lanes (R runs per trip)
 // One step per lane over the CSR rows of the candidate steps (findReadySteps, dag.go:2711-2733), visiting only
 // the 32-step words that hold a candidate, TWO words per loop trip so two independent load chains overlap.
 // Status byte of a dependency: bit0 = not satisfied, bit1 = failed dependency.  The first four deps of a row

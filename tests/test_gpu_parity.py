@@ -24,12 +24,13 @@ def fr():
     f.close()
 
 
-@pytest.fixture(params=["general", "quad"])
+@pytest.fixture(params=["general", "quad", "split"])
 def kernel(request, monkeypatch):
     """general = the default one-run-per-warp kernel; quad = the opt-in packed-lanes kernel (R runs per warp trip,
-    runs whose topology has parallel steps deferred to the general kernel).  Both must equal the oracle."""
-    if request.param == "quad":
-        monkeypatch.setenv("BF_KERNEL", "quad")
+    runs whose topology has parallel steps deferred to the general kernel); split = the two-phase path (classify
+    every run, walk only runs with candidates).  All must equal the oracle."""
+    if request.param in ("quad", "split"):
+        monkeypatch.setenv("BF_KERNEL", request.param)
     else:
         monkeypatch.delenv("BF_KERNEL", raising=False)
     return request.param
@@ -108,7 +109,7 @@ def test_random_adversarial_no_parallel(fr, kernel, seed):
     _compare(fr, ts, slots, L, state)
     st = fr.stats()
     # the ctx also holds topologies with parallel steps (earlier tests): auto = packed lanes + deferred general
-    assert st["last_kernel"] == (0 if kernel == "general" else 2), st
+    assert st["last_kernel"] == {"general": 0, "quad": 2, "split": 4}[kernel], st
 
 
 def test_minimal_layout_outputs_only_ready_skip(fr, kernel):
