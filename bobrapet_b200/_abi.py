@@ -90,7 +90,8 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("arena_used_bytes", C.c_uint64), ("arena_cap_bytes", C.c_uint64),
                 ("n_topologies", C.c_uint32), ("sm_count", C.c_uint32), ("last_grid", C.c_uint32),
                 ("last_block", C.c_uint32), ("last_smem_bytes", C.c_uint32), ("last_stages", C.c_uint32),
-                ("last_kernel", C.c_uint32), ("last_runs_per_trip", C.c_uint32)]
+                ("last_kernel", C.c_uint32), ("last_runs_per_trip", C.c_uint32),
+                ("last_eval_chunks", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 # every symbol include/bobrafrontier.h declares: (name, restype, argtypes)

@@ -52,6 +52,11 @@ struct bf_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  // bf_eval pipeline: H2D copies, kernels and D2H copies of consecutive run chunks overlap on three streams
+  static constexpr uint32_t kMaxChunks = 32;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
+  bool pipe_ready = false;
   std::mutex mu;
   std::string err;
 
@@ -73,6 +78,7 @@ struct bf_ctx {
   uint8_t* d_state = nullptr; size_t d_state_cap = 0;
   uint8_t* d_result = nullptr; size_t d_result_cap = 0;
   unsigned long long* d_counts = nullptr;
+  bf_counts* h_counts = nullptr;  // pinned landing zone for the counts block (a pageable target would make the copy synchronous)
   bf_expansion* d_exp = nullptr; size_t d_exp_cap = 0;
   // scratch shared by both entry points
   uint32_t* d_exp_counts = nullptr; size_t d_exp_counts_cap = 0;
@@ -634,7 +640,8 @@ int bf_create(bf_ctx** out, const bf_config* cfg) {
   c->sm_count = prop.multiProcessorCount;
   c->stats.sm_count = (uint32_t)prop.multiProcessorCount;
   if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMalloc(&c->d_counts, sizeof(bf_counts)) != cudaSuccess) {
+      cudaMalloc(&c->d_counts, sizeof(bf_counts)) != cudaSuccess ||
+      cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), sizeof(bf_counts), cudaHostAllocDefault) != cudaSuccess) {
     delete c;
     return BF_ECUDA;
   }
@@ -651,6 +658,11 @@ void bf_destroy(bf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->pipe_ready) {
+    cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
+    for (uint32_t k = 0; k < bf_ctx::kMaxChunks; ++k) { cudaEventDestroy(c->ev_in[k]); cudaEventDestroy(c->ev_k[k]); }
+  }
+  cudaFreeHost(c->h_counts);
   cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
   cudaFree(c->d_defer); cudaFree(c->d_walk); cudaFree(c->d_walk_count); cudaFree(c->info_dev); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums);
   delete c;
@@ -814,15 +826,68 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
   if (want_exp)
     if (int rc = ensure_dev(c, c->d_exp, c->d_exp_cap, (size_t)b->expansion_cap)) return rc;
   cudaStream_t s = c->stream;
-  if (sbytes) BF_CUDA(c, cudaMemcpyAsync(c->d_state, b->state, sbytes, cudaMemcpyHostToDevice, s));
-  BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
-  bf_batch db = *b;
-  if (!want_exp) db.flags &= ~BF_EVAL_EXPANSION;
-  if (int rc = run_pass(c, db, c->d_state, c->d_result, want_exp ? c->d_exp : nullptr, c->d_counts, s)) return rc;
-  if (rbytes) BF_CUDA(c, cudaMemcpyAsync(b->result, c->d_result, rbytes, cudaMemcpyDeviceToHost, s));
+  // Large batches are cut into chunks of runs (runs are independent) so that the upload of chunk k+1, the
+  // kernel of chunk k and the download of chunk k-1 overlap: PCIe is full duplex and the pass itself is ~5x
+  // faster than either copy, so the call costs about max(H2D, D2H) instead of their sum.  Expansion needs a
+  // batch-wide scan and stays on the single-stream path.
+  uint32_t chunks = 1;
+  if (!want_exp && sbytes + rbytes >= (2u << 20)) {
+    // measured on B200 (tools/e2e_sweep.py, 22.4 MB per call): 1 chunk 0.50 ms, 2: 0.43, 4: 0.42, 8: 0.43, 16: 0.48 —
+    // ~5.5 MB per chunk, at least two
+    chunks = (uint32_t)((sbytes + rbytes + (11u << 18)) / (11u << 19));
+    if (chunks < 2) chunks = 2;
+    if (const char* e = getenv("BF_E2E_CHUNKS")) chunks = (uint32_t)atoi(e);
+    if (chunks > bf_ctx::kMaxChunks) chunks = bf_ctx::kMaxChunks;
+    if (chunks < 1) chunks = 1;
+  }
+  if (chunks > 1 && !c->pipe_ready) {
+    BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (uint32_t k = 0; k < bf_ctx::kMaxChunks; ++k) {
+      BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+      BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[k], cudaEventDisableTiming));
+    }
+    c->pipe_ready = true;
+  }
   bf_counts hc{};
-  BF_CUDA(c, cudaMemcpyAsync(&hc, c->d_counts, sizeof hc, cudaMemcpyDeviceToHost, s));
-  BF_CUDA(c, cudaStreamSynchronize(s));
+  auto body = [&]() -> int {
+    BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
+    bf_batch db = *b;
+    if (!want_exp) db.flags &= ~BF_EVAL_EXPANSION;
+    const uint8_t* hs = static_cast<const uint8_t*>(b->state);
+    uint8_t* hr = static_cast<uint8_t*>(b->result);
+    for (uint32_t k = 0; k < chunks; ++k) {
+      const size_t lo = (size_t)b->n_runs * k / chunks, hi = (size_t)b->n_runs * (k + 1) / chunks;
+      const size_t so = lo * L.state_stride, ro = lo * L.result_stride;
+      const size_t sb = (hi - lo) * L.state_stride, rb = (hi - lo) * L.result_stride;
+      const bool piped = chunks > 1;
+      if (sb) BF_CUDA(c, cudaMemcpyAsync(c->d_state + so, hs + so, sb, cudaMemcpyHostToDevice, piped ? c->s_in : s));
+      if (piped) {
+        BF_CUDA(c, cudaEventRecord(c->ev_in[k], c->s_in));
+        BF_CUDA(c, cudaStreamWaitEvent(s, c->ev_in[k], 0));
+      }
+      db.n_runs = (uint32_t)(hi - lo);
+      if (int rc = run_pass(c, db, c->d_state + so, c->d_result + ro, want_exp ? c->d_exp : nullptr, c->d_counts, s)) return rc;
+      if (piped) {
+        BF_CUDA(c, cudaEventRecord(c->ev_k[k], s));
+        BF_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
+      }
+      if (rb) BF_CUDA(c, cudaMemcpyAsync(hr + ro, c->d_result + ro, rb, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
+    }
+    BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof hc, cudaMemcpyDeviceToHost, s));
+    return BF_OK;
+  };
+  const int body_rc = body();
+  // never return while a copy that touches the caller's buffers is still in flight
+  cudaError_t e_sync = cudaStreamSynchronize(s);
+  if (chunks > 1) {
+    const cudaError_t e1 = cudaStreamSynchronize(c->s_in), e2 = cudaStreamSynchronize(c->s_out);
+    if (e_sync == cudaSuccess) e_sync = e1 != cudaSuccess ? e1 : e2;
+  }
+  if (body_rc != BF_OK) return body_rc;
+  if (e_sync != cudaSuccess) return cuda_fail(c, e_sync, "cudaStreamSynchronize");
+  hc = *c->h_counts;
+  c->stats.last_eval_chunks = chunks;
   if (want_exp) {
     const uint64_t n = hc.expansion < b->expansion_cap ? hc.expansion : b->expansion_cap;
     if (n) BF_CUDA(c, cudaMemcpy(b->expansion, c->d_exp, (size_t)n * sizeof(bf_expansion), cudaMemcpyDeviceToHost));

@@ -314,6 +314,8 @@ typedef struct bf_stats {
   uint32_t last_grid, last_block, last_smem_bytes, last_stages;
   uint32_t last_kernel;        /* 0 = one run per warp (general), 1 = packed lanes, 2 = packed lanes + deferred general */
   uint32_t last_runs_per_trip; /* StoryRuns evaluated per warp trip by the last pass                                   */
+  uint32_t last_eval_chunks;   /* run chunks the last bf_eval pipelined over its copy/compute streams (1 = serial)      */
+  uint32_t reserved0;
 } bf_stats;
 int bf_get_stats(const bf_ctx* ctx, bf_stats* out);
 /* Device address + byte size of a topology record (for traffic accounting).   */

@@ -195,3 +195,22 @@ def test_drop_and_reuse_slot(fr):
     want, _ = PK.evaluate(pt, L, state)
     got, _ = fr.eval(L, state)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("chunks", [0, 1, 5, 32])
+def test_pipelined_host_eval_matches_oracle(fr, monkeypatch, chunks):
+    """bf_eval cuts large batches into run chunks whose H2D / kernel / D2H overlap on three streams; any chunking
+    (default, serial, uneven, maximum) must give the same records and the same global counts."""
+    if chunks:
+        monkeypatch.setenv("BF_E2E_CHUNKS", str(chunks))
+    else:
+        monkeypatch.delenv("BF_E2E_CHUNKS", raising=False)
+    n = 20011
+    ts = synth.topologies(4, 0, n, 256)
+    slots = fr.put_topologies(ts)
+    L = make_layout(256, 0, ALL)
+    state = synth.state(4, 0, n, L, slots, ts)
+    _compare(fr, ts, slots, L, state)
+    total = n * (L.state_stride + L.result_stride)
+    want_chunks = {0: max(2, (total + (11 << 18)) // (11 << 19)), 1: 1, 5: 5, 32: 32}[chunks]
+    assert fr.stats()["last_eval_chunks"] == want_chunks
