@@ -186,7 +186,10 @@ int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_ka
   uint32_t off = sizeof(bf::TopoHeader);
   off += round_up(2 * (S + 1), 16);
   p.off_col = off;
-  off += round_up(2 * E, 16);
+  // + 4 zero entries: the branch-free walk fetches col[e0..e0+3] whatever the row length (e0 = E for trailing
+  // rows without deps), so the last rows read past E; zero padding keeps every fetched index a valid step index
+  // and the walk needs no clamp
+  off += round_up(2 * E + 8, 16);
   p.off_planes = off;
   off += round_up(bf::PL_COUNT * p.W * 4, 16);
   p.off_par = off;
@@ -346,6 +349,8 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
     P.result_tail = tail;
   }
 
+  P.run_blocked = 0;
+  if (const char* e = getenv("BF_ASSIGN")) P.run_blocked = !strcmp(e, "blocked");
   const bool want_exp = (b.flags & BF_EVAL_EXPANSION) && d_exp != nullptr;
   if (want_exp) {
     if (int rc = ensure_dev(c, c->d_exp_counts, c->d_exp_counts_cap, b.n_runs)) return rc;

@@ -6,7 +6,7 @@
 //
 //   +0            TopoHeader (32 B)
 //   +32           row_ptr   u16[S+1]          CSR over allStorySteps (dag.go:3270), pad 16
-//   +off_col      col_idx   u16[E]            dependency step indices, pad 16
+//   +off_col      col_idx   u16[E]            dependency step indices, then >= 4 zero entries, pad 16
 //   +off_planes   planes    u32[8][W]         static step flags, BIT-SLICED (W = ceil(S/32)):
 //                                             t0,t1,t2 (type), AF, TS, HAS_IF, G1 (comp), G2 (finally)
 //                                             = S bytes, same size as the canonical u8 step_flags[S]
@@ -109,6 +109,7 @@ struct KParams {
   uint32_t stage_bytes;         // state_stride + topo_buf_bytes (multiple of 16)
   uint32_t work_bytes;          // per-warp scratch
   uint32_t warps_per_block;
+  uint32_t run_blocked;         // 1: a warp takes a contiguous block of runs, 0: every G-th run
   // packed-lanes kernel (frontier_quad.cu): words per run rounded up to a power of two
   uint32_t wq, wq_log2;
 };

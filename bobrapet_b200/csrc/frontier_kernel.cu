@@ -42,7 +42,6 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
   const uint32_t per_warp = ring_bytes + P.work_bytes + 64;  // + mbarriers (<= 8 stages)
   uint8_t* const wbase = smem_raw + 128 + warp * per_warp;
   const uint32_t bars = smem_u32(wbase + ring_bytes + P.work_bytes);
-  const uint32_t ring = smem_u32(wbase);
 
   if (threadIdx.x < 4) blk_counts[threadIdx.x] = 0ull;
   if (lane == 0) {
@@ -56,64 +55,59 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
   // run-list mode (second tier after the packed-lanes kernel): the runs to take are run_list[0..count)
   const uint32_t* const rlist = LIST ? P.run_list : nullptr;
   const uint32_t N = LIST ? min(*reinterpret_cast<const volatile uint32_t*>(P.run_list_count), P.n_runs) : P.n_runs;
-  const uint32_t my_runs = gw < N ? (N - gw + G - 1) / G : 0;
+  // This warp's n-th run is run (or list position) rbase + n * rstride: a contiguous block of the batch
+  // (run_blocked) or every G-th run.
+  uint32_t rbase, rstride, my_runs;
+  if (P.run_blocked) {
+    const uint32_t lo = (uint32_t)((uint64_t)N * gw / G), hi = (uint32_t)((uint64_t)N * (gw + 1) / G);
+    rbase = lo; rstride = 1; my_runs = hi - lo;
+  } else {
+    rbase = gw; rstride = G; my_runs = gw < N ? (N - gw + G - 1) / G : 0;
+  }
   auto run_of = [&](uint32_t n) -> uint32_t {  // global run index of this warp's n-th run
-    const uint32_t idx = gw + n * G;
+    const uint32_t idx = rbase + n * rstride;
     return LIST ? __ldg(rlist + idx) : idx;
   };
 
-  // ---- producer state (used by lane 0): prefetch chain run id -> slot id -> slot entry -> TMA ----
-  uint32_t ni = 0, is = 0;   // next issue index, its stage
-  uint32_t r_0 = 0, r_1 = 0, r_2 = 0;  // LIST: run ids of issue index ni, ni+1, ni+2
-  const size_t state_step = (size_t)G * P.state_stride;
-  const uint8_t* src_state = P.state + (size_t)gw * P.state_stride;  // !LIST: state record of issue index ni
-  uint64_t ent_addr = 0;     // slot entry for issue index ni
-  uint32_t ent_bytes = 0;
-  uint32_t sid_q = 0xFFFFFFFFu;  // slot id for issue index ni+1
-  uint32_t ok_bits = 0;          // bit s: stage s holds a staged topology record
-
-  auto load_sid = [&](uint32_t r) -> uint32_t {
-    return __ldg(reinterpret_cast<const uint32_t*>(P.state + (size_t)r * P.state_stride));
-  };
-  auto load_ent = [&](uint32_t sid) {
-    ent_addr = 0;
-    ent_bytes = 0;
-    if (sid < P.n_slots) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.slots + sid));
-      ent_addr = (uint64_t)v.x | ((uint64_t)v.y << 32);
-      ent_bytes = v.z;
+  // ---- producer: the warp prefetches slot ids and slot entries 32 runs at a time (lane l holds issue index
+  //      32*b + l), so the chain run -> slot id -> slot entry -> TMA costs two coalesced loads per 32 runs and
+  //      the lane that owns an index issues its copies from its own registers ----
+  uint32_t ni = 0;                          // next issue index (lane-uniform)
+  uint32_t nx_rid = 0, nx_sid = 0xFFFFFFFFu;  // lane l: run / slot id of index (next batch) + l
+  uint32_t pf_rid = 0, pf_lo = 0, pf_hi = 0, pf_bytes = 0;  // lane l: run, record address, record bytes of index (this batch) + l
+  auto load_sids = [&](uint32_t n0) {
+    const uint32_t n = n0 + lane;
+    nx_rid = 0; nx_sid = 0xFFFFFFFFu;
+    if (n < my_runs) {
+      nx_rid = run_of(n);
+      nx_sid = __ldg(reinterpret_cast<const uint32_t*>(P.state + (size_t)nx_rid * P.state_stride));
     }
   };
-  auto issue = [&]() {  // lane 0 only
-    if (ni < my_runs) {
-      const uint32_t buf = ring + is * P.stage_bytes;
-      const uint32_t bar = bars + 8 * is;
-      const bool ok = ent_addr != 0 && ent_bytes <= P.topo_buf_bytes;
-      const uint32_t tb = ok ? ent_bytes : 0u;
-      ok_bits = ok ? (ok_bits | (1u << is)) : (ok_bits & ~(1u << is));
-      mbar_expect_tx(bar, P.state_stride + tb);
-      bulk_g2s(buf, LIST ? P.state + (size_t)r_0 * P.state_stride : src_state, P.state_stride, bar);
-      if (ok) bulk_g2s(buf + P.state_stride, reinterpret_cast<const void*>(ent_addr), tb, bar);
+  auto load_ents = [&]() {
+    pf_rid = nx_rid; pf_lo = 0; pf_hi = 0; pf_bytes = 0;
+    if (nx_sid < P.n_slots) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.slots + nx_sid));
+      pf_lo = v.x; pf_hi = v.y; pf_bytes = v.z;
     }
-    load_ent(sid_q);  // entry for ni+1 (consumed by the next issue)
-    if (LIST) {
-      sid_q = (ni + 2 < my_runs) ? load_sid(r_2) : 0xFFFFFFFFu;
-      r_0 = r_1; r_1 = r_2;
-      r_2 = (ni + 3 < my_runs) ? run_of(ni + 3) : 0u;
-    } else {
-      sid_q = (ni + 2 < my_runs) ? __ldg(reinterpret_cast<const uint32_t*>(src_state + 2 * state_step)) : 0xFFFFFFFFu;
-      src_state += state_step;
+  };
+  // issue the copies of index ni into the stage at shared address `buf` guarded by mbarrier `bar`
+  auto issue = [&](uint32_t buf, uint32_t bar) {
+    if (lane == (ni & 31u) && ni < my_runs) {
+      const bool ok = (pf_lo | pf_hi) != 0 && pf_bytes <= P.topo_buf_bytes;
+      if (!ok) sts_zero16(buf + P.state_stride);  // dead / oversized slot: a zero header (W = 0) marks the stage
+      mbar_expect_tx(bar, P.state_stride + (ok ? pf_bytes : 0u));
+      bulk_g2s(buf, P.state + (size_t)pf_rid * P.state_stride, P.state_stride, bar);
+      if (ok) bulk_g2s(buf + P.state_stride, reinterpret_cast<const void*>((uint64_t)pf_lo | ((uint64_t)pf_hi << 32)), pf_bytes, bar);
     }
     ++ni;
-    is = (is + 1 == ST) ? 0 : is + 1;
+    if ((ni & 31u) == 16u) load_sids((ni & ~31u) + 32u);  // half a batch ahead
+    if ((ni & 31u) == 0u) load_ents();                    // consumed from the next issue on
   };
-  if (lane == 0 && my_runs != 0) {
-    r_0 = run_of(0);
-    r_1 = my_runs > 1 ? run_of(1) : 0u;
-    r_2 = my_runs > 2 ? run_of(2) : 0u;
-    load_ent(load_sid(r_0));
-    sid_q = my_runs > 1 ? load_sid(r_1) : 0xFFFFFFFFu;
-    for (uint32_t s = 0; s < ST; ++s) issue();
+  const uint32_t wb = smem_u32(wbase);
+  if (my_runs != 0) {
+    load_sids(0);
+    load_ents();
+    for (uint32_t s = 0; s < ST; ++s) issue(wb + s * P.stage_bytes, bars + 8 * s);
   }
 
   // scratch (per warp): fix-up fail mask words, then one status byte per step (+16 clamp guard)
@@ -127,31 +121,30 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
 
   uint32_t tot_ready = 0, tot_skip = 0, tot_exp = 0, tot_evals = 0;  // lane-uniform
   uint32_t cs = 0, cpar = 0;                                         // consumer stage / parity
-  uint32_t r_next = (LIST && my_runs != 0) ? run_of(0) : gw;
-  const size_t result_step = (size_t)G * P.result_stride;
-  uint8_t* rr_inc = P.result + (size_t)gw * P.result_stride;
+  uint32_t stage_a = wb, bar_a = bars;                               // shared addresses of the consumer stage / its mbarrier
+  const size_t result_step = (size_t)rstride * P.result_stride;
+  uint8_t* rr_inc = P.result + (size_t)rbase * P.result_stride;
+  uint32_t r_inc = rbase;
 
-  for (uint32_t k = 0; k < my_runs; ++k, rr_inc += result_step) {
-    const uint32_t r = r_next;
-    if (LIST) { if (k + 1 < my_runs) r_next = run_of(k + 1); }  // issued one trip early: its latency hides under this run
-    else r_next = r + G;
+  for (uint32_t k = 0; k < my_runs; ++k, rr_inc += result_step, r_inc += rstride) {
+    const uint32_t r = LIST ? run_of(k) : r_inc;
     uint8_t* const rr = LIST ? P.result + (size_t)r * P.result_stride : rr_inc;
-    mbar_wait(bars + 8 * cs, cpar);
-    const uint8_t* sr = wbase + cs * P.stage_bytes;
+    mbar_wait(bar_a, cpar);
+    const uint32_t cur_stage = stage_a, cur_bar = bar_a;  // the stage index ni = k + ST will be copied into
+    const uint8_t* sr = wbase + (cur_stage - wb);
     const uint8_t* tr = sr + P.state_stride;
-    const bool staged = (__shfl_sync(FULL, ok_bits, 0) >> cs) & 1u;
-    cs = (cs + 1 == ST) ? 0 : cs + 1;
-    cpar ^= (cs == 0);
+    ++cs; stage_a += P.stage_bytes; bar_a += 8;
+    if (cs == ST) { cs = 0; stage_a = wb; bar_a = bars; cpar ^= 1u; }
 
     const uint4 h0 = *reinterpret_cast<const uint4*>(tr);        // TopoHeader, first half
     const uint32_t S = h0.x & 0xFFFFu, Wt = h0.x >> 16;          // S, W
     const uint32_t max_deg = h0.y & 0xFFFFu, nP = h0.y >> 16;    // max_deg, P
     const uint32_t n_main = h0.z & 0xFFFFu, n_comp = h0.z >> 16, n_final = h0.w & 0xFFFFu;
-    if (!staged || Wt > Wmax) {  // dead / out-of-range slot: empty result, summary all-ones
+    if (Wt - 1u >= Wmax) {  // dead slot (zero header) / out-of-range record: empty result, summary all-ones
       for (uint32_t x = lane; x < P.result_stride / 4; x += 32) reinterpret_cast<uint32_t*>(rr)[x] = x == 0 ? 0xFFFFFFFFu : 0u;
       if (P.exp_counts && lane == 0) P.exp_counts[r] = 0;
       __syncwarp();
-      if (lane == 0) issue();
+      issue(cur_stage, cur_bar);
       continue;
     }
     const uint4 h1 = *reinterpret_cast<const uint4*>(tr + 16);   // off_col, off_planes, off_par, rec_bytes
@@ -356,16 +349,20 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
           const uint32_t m = m0 + lane;
           const uint32_t src = (m >> 2) & 31u, sh = (m & 3u) * 8u;
           const uint32_t ub = __shfl_sync(FULL, U, src) >> sh;
-          const uint32_t fb = __shfl_sync(FULL, FD, src) >> sh;
           uint2 v;
-          v.x = bits4_to_bytes(ub & 0xFu) | (bits4_to_bytes(fb & 0xFu) << 1);
-          v.y = bits4_to_bytes((ub >> 4) & 0xFu) | (bits4_to_bytes((fb >> 4) & 0xFu) << 1);
+          v.x = bits4_to_bytes(ub & 0xFu);
+          v.y = bits4_to_bytes((ub >> 4) & 0xFu);
+          if (skip_on_failed) {  // lane-uniform: FD is empty under every other policy
+            const uint32_t fb = __shfl_sync(FULL, FD, src) >> sh;
+            v.x |= bits4_to_bytes(fb & 0xFu) << 1;
+            v.y |= bits4_to_bytes((fb >> 4) & 0xFu) << 1;
+          }
           if (m < 4 * Wt) reinterpret_cast<uint2*>(st)[m] = v;
         }
         __syncwarp();
         // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
         uint32_t met_w, fd_w;
-        walk_rows<false>(lane, CAND, zidx, max_deg, row_ptr, col, st, mFAIL, 0u, met_w, fd_w);
+        walk_rows_s(lane, CAND, max_deg, smem_u32(row_ptr), smem_u32(col), smem_u32(st), met_w, fd_w);
         uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
         if (CD) {
           ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
@@ -418,8 +415,8 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
     }
 
     // ---------------- stage E: result record ----------------
-    const uint32_t n_ready = redux_add((uint32_t)__popc(acc_ready));
-    const uint32_t n_skip = redux_add((uint32_t)__popc(acc_skip));
+    const uint32_t n_rs = redux_add((uint32_t)__popc(acc_ready) | ((uint32_t)__popc(acc_skip) << 16));  // both <= S <= 1024
+    const uint32_t n_ready = n_rs & 0xFFFFu, n_skip = n_rs >> 16;
     uint32_t n_exp = 0;
     if (CH && nP != 0) {
       const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + h1.z);
@@ -458,7 +455,7 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
     tot_ready += n_ready; tot_skip += n_skip; tot_exp += n_exp; tot_evals += S;
 
     __syncwarp();  // every lane is done with this stage's buffers
-    if (lane == 0) issue();
+    issue(cur_stage, cur_bar);
   }
 
   // ---- counters: warp -> block (shared atomics) -> one global atomic per block ----

@@ -40,6 +40,7 @@ DI void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+DI void sts_zero16(uint32_t a) { asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory"); }
 DI void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 template <int IMM>
@@ -162,7 +163,7 @@ DI void walk_rows(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_deg,
 
 // Same walk with explicit 32-bit shared addresses (ld.shared), for kernels whose CSR / status arrays are given
 // as shared-window addresses: keeps every address computation a single 32-bit add.
-DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_deg, uint32_t rp_addr, uint32_t col_addr,
+DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t max_deg, uint32_t rp_addr, uint32_t col_addr,
                     uint32_t st_addr, uint32_t& met_w, uint32_t& fd_w) {
   met_w = 0;
   fd_w = 0;
@@ -180,11 +181,12 @@ DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_de
       n = lds_u16(a + 2u) - e0;
     }
     const uint32_t cpa = col_addr + e0 * 2u;
+    // The four fetches may run past the row (and, for the last rows, past E): every u16 there is another row's
+    // entry or the record's zero padding (device_record.h), i.e. a valid step index; the verdict is masked below.
     uint32_t x0, x1, x2, x3;
     asm volatile("ld.shared.u16 %0, [%4];\n\tld.shared.u16 %1, [%4+2];\n\tld.shared.u16 %2, [%4+4];\n\tld.shared.u16 %3, [%4+6];"
-                 : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(cpa));  // may run past the row: masked below
-    const uint32_t s0 = lds_u8(st_addr + min(x0, zidx)), s1 = lds_u8(st_addr + min(x1, zidx)),
-                   s2 = lds_u8(st_addr + min(x2, zidx)), s3 = lds_u8(st_addr + min(x3, zidx));
+                 : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(cpa));
+    const uint32_t s0 = lds_u8(st_addr + x0), s1 = lds_u8(st_addr + x1), s2 = lds_u8(st_addr + x2), s3 = lds_u8(st_addr + x3);
     uint32_t w = ((s3 * 256u + s2) * 256u + s1) * 256u + s0;
     w &= bmsk_clamp(0u, n * 8u);
     if (max_deg > 4) {  // warp-uniform
