@@ -22,7 +22,7 @@ namespace bf {
 cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, unsigned long long* offsets,
                              bf_expansion* out, unsigned long long cap, cudaStream_t stream, uint32_t* launches);
-int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
+int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes, uint32_t* occ2);
 cudaError_t launch_frontier_quad(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
 int frontier_quad_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
 uint32_t split_entry_bytes(const KParams& P);
@@ -91,7 +91,7 @@ struct bf_ctx {
 
   // cached shared-memory plan (recomputed when the layout or the largest record changes)
   uint32_t plan_key_stride = 0, plan_key_words = 0, plan_key_rec = 0, plan_key_variant = 0xFFFFFFFFu;
-  uint32_t plan_stages = 0, plan_wpb = 0, plan_per_sm = 0, plan_wq = 0, plan_lg = 0;
+  uint32_t plan_stages = 0, plan_wpb = 0, plan_per_sm = 0, plan_wq = 0, plan_lg = 0, plan_occ2 = 0;
 
   bf_stats stats{};
 };
@@ -454,7 +454,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
     // is latency/issue bound before it is HBM bound — then ring depth: >= 2 stages keep the next trip's TMA
     // copies in flight under the current evaluation.
     const uint32_t budget = 227u * 1024u - 128u;
-    uint32_t best_st = 0, best_wpb = 0, best_score = 0, best_wq = 0, best_lg = 0;
+    uint32_t best_st = 0, best_wpb = 0, best_score = 0, best_wq = 0, best_lg = 0, best_occ2 = 0;
     int per_sm_q = 1;
     const char* env_st = getenv("BF_STAGES");
     const char* env_w = getenv("BF_WARPS");
@@ -473,14 +473,15 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
             if (env_w && (uint32_t)atoi(env_w) != wpb) continue;
             const uint32_t smem_try = 128 + wpb * (st * R * P.stage_bytes + P.work_bytes + 64);
             if (smem_try > budget + 128) continue;
-            int ctas = q ? bf::frontier_quad_max_blocks_per_sm(P, wpb * 32, smem_try) : bf::frontier_max_blocks_per_sm(P, wpb * 32, smem_try);
+            uint32_t occ2 = 0;
+            int ctas = q ? bf::frontier_quad_max_blocks_per_sm(P, wpb * 32, smem_try) : bf::frontier_max_blocks_per_sm(P, wpb * 32, smem_try, &occ2);
             if (ctas < 1) continue;
             if (env_b && atoi(env_b) >= 1 && atoi(env_b) < ctas) ctas = atoi(env_b);
             const uint32_t warps_sm = (uint32_t)ctas * wpb;
             const uint32_t depth = st >= 3 ? 2 : st - 1;           // 0, 1, 2, 2
             const uint32_t score = q ? (warps_sm * R > 128 ? 128 : warps_sm * R) * 8 + warps_sm * 2 + depth * 24 + (wpb >= 4 ? 2 : 0)
                                      : warps_sm * 16 + depth * 24 + (wpb >= 8 ? 2 : 0) + (4 - st);
-            if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; per_sm_q = ctas; best_wq = wq; best_lg = lgq; }
+            if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; per_sm_q = ctas; best_wq = wq; best_lg = lgq; best_occ2 = occ2; }
           }
         }
         if (!q) break;
@@ -489,7 +490,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
     }
     if (best_wpb == 0) return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
     c->plan_stages = best_st; c->plan_wpb = best_wpb; c->plan_per_sm = (uint32_t)per_sm_q;
-    c->plan_wq = quad ? best_wq : 0; c->plan_lg = best_lg;
+    c->plan_wq = quad ? best_wq : 0; c->plan_lg = best_lg; c->plan_occ2 = best_occ2;
     c->plan_key_stride = L.state_stride; c->plan_key_words = L.words; c->plan_key_rec = c->max_rec_bytes;
     c->plan_key_variant = variant;
   }
@@ -508,6 +509,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   const int per_sm = (int)c->plan_per_sm;
   P.stages = best_st;
   P.warps_per_block = best_wpb;
+  P.occ2 = c->plan_occ2;
   const uint32_t smem = 128 + best_wpb * (best_st * stage_total + P.work_bytes + 64);
   uint32_t grid = (uint32_t)c->sm_count * (uint32_t)per_sm;
   const uint32_t trips = (b.n_runs + R - 1) / R;

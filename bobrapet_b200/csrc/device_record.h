@@ -109,6 +109,7 @@ struct KParams {
   uint32_t stage_bytes;         // state_stride + topo_buf_bytes (multiple of 16)
   uint32_t work_bytes;          // per-warp scratch
   uint32_t warps_per_block;
+  uint32_t occ2;                // launch the build compiled for two resident CTAs per SM
   uint32_t run_blocked;         // 1: a warp takes a contiguous block of runs, 0: every G-th run
   // packed-lanes kernel (frontier_quad.cu): words per run rounded up to a power of two
   uint32_t wq, wq_log2;

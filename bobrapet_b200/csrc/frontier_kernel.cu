@@ -30,9 +30,11 @@ extern __shared__ __align__(128) uint8_t smem_raw[];
 // CD: cond and/or decision codes present   CH: topologies with `parallel` steps may occur (stage H, expansion count)
 // FX: device-side fixpoint (BF_EVAL_FIXPOINT)   XO: any of fail/needs_cond/skip_dep/phase_out requested
 // LIST: second-tier run over P.run_list (runs deferred by the packed-lanes kernel)
-template <bool CD, bool CH, bool FX, bool XO, bool LIST>
-__global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
-  const uint32_t lane = threadIdx.x & 31u;
+// OCC2: compiled for two resident 512-thread CTAs per SM (<= 64 registers); chosen by the host plan when the
+//       shared-memory ring of two CTAs fits, otherwise the unconstrained build runs one CTA per SM
+template <bool CD, bool CH, bool FX, bool XO, bool LIST, bool OCC2>
+__global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KParams P) {
+  const uint32_t lane = pin(threadIdx.x & 31u);  // pinned: otherwise rematerialised from S2R inside the loop
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t ST = P.stages;
 
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
   const uint32_t ring_bytes = ST * P.stage_bytes;
   const uint32_t per_warp = ring_bytes + P.work_bytes + 64;  // + mbarriers (<= 8 stages)
   uint8_t* const wbase = smem_raw + 128 + warp * per_warp;
-  const uint32_t bars = smem_u32(wbase + ring_bytes + P.work_bytes);
+  const uint32_t bars = pin(smem_u32(wbase + ring_bytes + P.work_bytes));
 
   if (threadIdx.x < 4) blk_counts[threadIdx.x] = 0ull;
   if (lane == 0) {
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
     if ((ni & 31u) == 16u) load_sids((ni & ~31u) + 32u);  // half a batch ahead
     if ((ni & 31u) == 0u) load_ents();                    // consumed from the next issue on
   };
-  const uint32_t wb = smem_u32(wbase);
+  const uint32_t wb = pin(smem_u32(wbase));
   if (my_runs != 0) {
     load_sids(0);
     load_ents();
@@ -111,9 +113,11 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
   }
 
   // scratch (per warp): fix-up fail mask words, then one status byte per step (+16 clamp guard)
+  // (all shared-memory traffic of the loop below goes through 32-bit shared-window addresses: no generic
+  //  pointers, no cvta, no 64-bit address arithmetic)
   const uint32_t Wmax = P.words;
-  uint32_t* const mFAIL = reinterpret_cast<uint32_t*>(wbase + ring_bytes);
-  uint8_t* const st = wbase + ring_bytes + ((4u * Wmax + 15u) & ~15u);
+  const uint32_t mfail_a = wb + ring_bytes;
+  const uint32_t st_a = pin(mfail_a + ((4u * Wmax + 15u) & ~15u));
 
   const bool has_cond = CD && P.off_cond != BF_OFF_NONE;
   const bool has_dec = CD && P.off_decision != BF_OFF_NONE;
@@ -131,12 +135,11 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
     uint8_t* const rr = LIST ? P.result + (size_t)r * P.result_stride : rr_inc;
     mbar_wait(bar_a, cpar);
     const uint32_t cur_stage = stage_a, cur_bar = bar_a;  // the stage index ni = k + ST will be copied into
-    const uint8_t* sr = wbase + (cur_stage - wb);
-    const uint8_t* tr = sr + P.state_stride;
+    const uint32_t sr_a = cur_stage, tr_a = cur_stage + P.state_stride;  // state record / topology record
     ++cs; stage_a += P.stage_bytes; bar_a += 8;
     if (cs == ST) { cs = 0; stage_a = wb; bar_a = bars; cpar ^= 1u; }
 
-    const uint4 h0 = *reinterpret_cast<const uint4*>(tr);        // TopoHeader, first half
+    const uint4 h0 = lds_v4(tr_a);                               // TopoHeader, first half
     const uint32_t S = h0.x & 0xFFFFu, Wt = h0.x >> 16;          // S, W
     const uint32_t max_deg = h0.y & 0xFFFFu, nP = h0.y >> 16;    // max_deg, P
     const uint32_t n_main = h0.z & 0xFFFFu, n_comp = h0.z >> 16, n_final = h0.w & 0xFFFFu;
@@ -147,8 +150,8 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
       issue(cur_stage, cur_bar);
       continue;
     }
-    const uint4 h1 = *reinterpret_cast<const uint4*>(tr + 16);   // off_col, off_planes, off_par, rec_bytes
-    const uint32_t rflags = sr[4];
+    const uint4 h1 = lds_v4(tr_a + 16);                          // off_col, off_planes, off_par, rec_bytes
+    const uint32_t rflags = lds_u8(sr_a + 4);
 
     // ---------------- planes of word `lane`: dynamic codes (state record) + static flags (topology) ----------------
     const bool act = lane < Wt;
@@ -156,21 +159,21 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
     uint32_t c0 = 0, c1 = 0, d0 = 0, d1 = 0;
     uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     if (act) {
-      const uint32_t* sp = reinterpret_cast<const uint32_t*>(tr + h1.y) + lane;
-      if (CD || FX || CH) { t0 = sp[PL_T0 * Wt]; t1 = sp[PL_T1 * Wt]; t2 = sp[PL_T2 * Wt]; }
-      AF = sp[PL_AF * Wt];
-      if (CD) TS = sp[PL_TS * Wt];
-      if (XO) HASIF = sp[PL_HASIF * Wt];
-      G1 = sp[PL_G1 * Wt]; G2 = sp[PL_G2 * Wt];
+      const uint32_t sp = tr_a + h1.y + lane * 4u, ps = Wt * 4u;  // static planes: word `lane`, plane stride
+      if (CD || FX || CH) { t0 = lds_u32(sp + PL_T0 * ps); t1 = lds_u32(sp + PL_T1 * ps); t2 = lds_u32(sp + PL_T2 * ps); }
+      AF = lds_u32(sp + PL_AF * ps);
+      if (CD) TS = lds_u32(sp + PL_TS * ps);
+      if (XO) HASIF = lds_u32(sp + PL_HASIF * ps);
+      G1 = lds_u32(sp + PL_G1 * ps); G2 = lds_u32(sp + PL_G2 * ps);
       const uint32_t rem = S - lane * 32;
       VALID = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
-      const uint32_t* pw = reinterpret_cast<const uint32_t*>(sr + P.off_phase) + lane;
-      p0 = pw[0]; p1 = pw[Wmax]; p2 = pw[2 * Wmax]; p3 = pw[3 * Wmax];
+      const uint32_t pw = sr_a + P.off_phase + lane * 4u, ds = Wmax * 4u;  // dynamic planes: stride of the layout
+      p0 = lds_u32(pw); p1 = lds_u32(pw + ds); p2 = lds_u32(pw + 2u * ds); p3 = lds_u32(pw + 3u * ds);
       const uint32_t keep = VALID & ~(p0 & p1 & p2 & p3);   // steps >= S and the reserved code 15 read as 0
       p0 &= keep; p1 &= keep; p2 &= keep; p3 &= keep;
       if (CD) {
-        if (has_cond) { const uint32_t* cw = reinterpret_cast<const uint32_t*>(sr + P.off_cond) + lane; c0 = cw[0]; c1 = cw[Wmax]; }
-        if (has_dec) { const uint32_t* dw = reinterpret_cast<const uint32_t*>(sr + P.off_decision) + lane; d0 = dw[0]; d1 = dw[Wmax]; }
+        if (has_cond) { const uint32_t cw = sr_a + P.off_cond + lane * 4u; c0 = lds_u32(cw); c1 = lds_u32(cw + ds); }
+        if (has_dec) { const uint32_t dw = sr_a + P.off_decision + lane * 4u; d0 = lds_u32(dw); d1 = lds_u32(dw + ds); }
       }
     }
     const uint32_t q0 = p0, q1 = p1, q2 = p2, q3 = p3;  // input planes (for the "changed" flag)
@@ -189,14 +192,14 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
     uint32_t summary = 0, iters = 0;
     bool marked = false;  // some phase was rewritten (lane-uniform)
     const uint32_t cap = FX ? (P.max_iter ? P.max_iter : S + 1) : 1u;
-    const uint16_t* row_ptr = reinterpret_cast<const uint16_t*>(tr + sizeof(TopoHeader));
-    const uint16_t* col = reinterpret_cast<const uint16_t*>(tr + h1.x);
-    const uint32_t zidx = 32 * Wt;  // clamp target of the branch-free walk (inside the status array's guard)
+    const uint32_t rp_a = tr_a + (uint32_t)sizeof(TopoHeader), col_a = tr_a + h1.x;  // CSR: row_ptr u16[S+1], col_idx u16[E]
 
     for (uint32_t it = 0; it < cap; ++it) {
       ++iters;
       // ---------------- stage H: parallel join (dag.go:1131-1198) ----------------
       if (CH && has_child && nP != 0) {
+        const uint8_t* sr = gptr(sr_a);
+        const uint8_t* tr = gptr(tr_a);
         const uint64_t registered = *reinterpret_cast<const uint64_t*>(sr + 8);
         const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + h1.z);
         const uint8_t* child = sr + P.off_child;
@@ -357,12 +360,12 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
             v.x |= bits4_to_bytes(fb & 0xFu) << 1;
             v.y |= bits4_to_bytes((fb >> 4) & 0xFu) << 1;
           }
-          if (m < 4 * Wt) reinterpret_cast<uint2*>(st)[m] = v;
+          if (m < 4 * Wt) sts_v2(st_a + m * 8u, v.x, v.y);
         }
         __syncwarp();
         // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
         uint32_t met_w, fd_w;
-        walk_rows_s(lane, CAND, max_deg, smem_u32(row_ptr), smem_u32(col), smem_u32(st), met_w, fd_w);
+        walk_rows_s(lane, CAND, max_deg, rp_a, col_a, st_a, met_w, fd_w);
         uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
         if (CD) {
           ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
@@ -375,9 +378,11 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
             const uint32_t fclass = allow_failed ? 0u : (skip_on_failed ? 3u : 1u);
             for (uint32_t round = 0; round <= S; ++round) {
               __syncwarp();
-              if (act) mFAIL[lane] = fail_w;
+              if (act) sts_u32(mfail_a + lane * 4u, fail_w);
               __syncwarp();
-              walk_rows<true>(lane, CAND, zidx, max_deg, row_ptr, col, st, mFAIL, fclass, met_w, fd_w);
+              walk_rows<true>(lane, CAND, 32u * Wt, max_deg, reinterpret_cast<const uint16_t*>(gptr(rp_a)),
+                              reinterpret_cast<const uint16_t*>(gptr(col_a)), gptr(st_a),
+                              reinterpret_cast<const uint32_t*>(gptr(mfail_a)), fclass, met_w, fd_w);
               const uint32_t nf = met_w & c0 & c1;
               const bool same = !__any_sync(FULL, nf != fail_w);
               fail_w = nf;
@@ -419,7 +424,7 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
     const uint32_t n_ready = n_rs & 0xFFFFu, n_skip = n_rs >> 16;
     uint32_t n_exp = 0;
     if (CH && nP != 0) {
-      const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + h1.z);
+      const ParDesc* pd = reinterpret_cast<const ParDesc*>(gptr(tr_a + h1.z));
       uint32_t mine = 0;
       for (uint32_t q0i = 0; q0i < nP; q0i += 32) {  // uniform trip count (shuffles inside)
         const uint32_t q = q0i + lane;
@@ -473,53 +478,63 @@ __global__ void __launch_bounds__(512) frontier_kernel(const KParams P) {
 
 // ------------------------------------------------------------------ host-side dispatch
 typedef void (*KernelFn)(const KParams);
-template <bool LIST>
+template <bool LIST, bool OCC2>
 static KernelFn pick_kernel(bool cd, bool ch, bool fx, bool xo) {
   static const KernelFn table[16] = {
-      frontier_kernel<false, false, false, false, LIST>, frontier_kernel<false, false, false, true, LIST>,
-      frontier_kernel<false, false, true, false, LIST>,  frontier_kernel<false, false, true, true, LIST>,
-      frontier_kernel<false, true, false, false, LIST>,  frontier_kernel<false, true, false, true, LIST>,
-      frontier_kernel<false, true, true, false, LIST>,   frontier_kernel<false, true, true, true, LIST>,
-      frontier_kernel<true, false, false, false, LIST>,  frontier_kernel<true, false, false, true, LIST>,
-      frontier_kernel<true, false, true, false, LIST>,   frontier_kernel<true, false, true, true, LIST>,
-      frontier_kernel<true, true, false, false, LIST>,   frontier_kernel<true, true, false, true, LIST>,
-      frontier_kernel<true, true, true, false, LIST>,    frontier_kernel<true, true, true, true, LIST>,
+      frontier_kernel<false, false, false, false, LIST, OCC2>, frontier_kernel<false, false, false, true, LIST, OCC2>,
+      frontier_kernel<false, false, true, false, LIST, false>, frontier_kernel<false, false, true, true, LIST, false>,
+      frontier_kernel<false, true, false, false, LIST, OCC2>,  frontier_kernel<false, true, false, true, LIST, OCC2>,
+      frontier_kernel<false, true, true, false, LIST, false>,  frontier_kernel<false, true, true, true, LIST, false>,
+      frontier_kernel<true, false, false, false, LIST, OCC2>,  frontier_kernel<true, false, false, true, LIST, OCC2>,
+      frontier_kernel<true, false, true, false, LIST, false>,  frontier_kernel<true, false, true, true, LIST, false>,
+      frontier_kernel<true, true, false, false, LIST, OCC2>,   frontier_kernel<true, true, false, true, LIST, OCC2>,
+      frontier_kernel<true, true, true, false, LIST, false>,   frontier_kernel<true, true, true, true, LIST, false>,
   };
   return table[(cd ? 8 : 0) | (ch ? 4 : 0) | (fx ? 2 : 0) | (xo ? 1 : 0)];
 }
 
-static KernelFn kernel_for(const KParams& P) {
+static KernelFn kernel_for(const KParams& P, bool occ2) {
   const bool cd = P.off_cond != BF_OFF_NONE || P.off_decision != BF_OFF_NONE;
   const bool ch = P.any_parallel != 0;  // join needs the child area; the expansion count needs only the descs
   const bool fx = (P.flags & BF_EVAL_FIXPOINT) != 0;
   const bool xo = P.off_fail != BF_OFF_NONE || P.off_needs_cond != BF_OFF_NONE || P.off_skip_dep != BF_OFF_NONE ||
                   P.off_phase_out != BF_OFF_NONE;
-  return P.run_list ? pick_kernel<true>(cd, ch, fx, xo) : pick_kernel<false>(cd, ch, fx, xo);
+  if (P.run_list) return pick_kernel<true, false>(cd, ch, fx, xo);   // second tier: a handful of runs
+  return occ2 ? pick_kernel<false, true>(cd, ch, fx, xo) : pick_kernel<false, false>(cd, ch, fx, xo);
 }
 
 cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream) {
-  KernelFn fn = kernel_for(P);
-  static KernelFn configured[8][32] = {};
+  KernelFn fn = kernel_for(P, P.occ2 != 0);
+  static KernelFn configured[8][64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   bool known = false;
   if (dev >= 0 && dev < 8)
-    for (int i = 0; i < 32; ++i) known = known || configured[dev][i] == fn;
+    for (int i = 0; i < 64; ++i) known = known || configured[dev][i] == fn;
   if (!known) {
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 8)
-      for (int i = 0; i < 32; ++i)
+      for (int i = 0; i < 64; ++i)
         if (configured[dev][i] == nullptr) { configured[dev][i] = fn; break; }
   }
   fn<<<grid, P.warps_per_block * 32, smem_bytes, stream>>>(P);
   return cudaGetLastError();
 }
 
-int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes) {
+// Resident CTAs per SM for this launch shape; *occ2 says which build to launch (the 64-register one when two
+// CTAs fit in shared memory, else the unconstrained one).
+int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes, uint32_t* occ2) {
   int n = 0;
-  KernelFn fn = kernel_for(P);
+  *occ2 = 0;
+  KernelFn fn2 = kernel_for(P, true);
+  cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn2, (int)threads, smem_bytes) == cudaSuccess && n >= 2) {
+    *occ2 = 1;
+    return n;
+  }
+  KernelFn fn = kernel_for(P, false);
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, (int)threads, smem_bytes) != cudaSuccess) return 1;
   return n;
