@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BF_LIB") or os.path.join(_HERE, "lib", "libbobrafrontier.so")  # BF_LIB: A/B builds
 
-BF_ABI_VERSION = 1
+BF_ABI_VERSION = 2
 BF_OK, BF_EINVAL, BF_ENOMEM, BF_ECUDA, BF_ENCCL, BF_ETOPO, BF_ENODEV = 0, -1, -2, -3, -4, -5, -6
 
 # phase codes (pkg/enums/enums.go:44-97 order; 14 = Pending + "Queued due to ..." message)
@@ -94,6 +94,21 @@ class Stats(C.Structure):
                 ("last_eval_chunks", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
+class SchedTables(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_stories", C.c_uint32), ("n_queues", C.c_uint32), ("global_limit", C.c_int32),
+                ("global_running_base", C.c_uint32), ("story_limit", C.c_void_p), ("story_running_base", C.c_void_p),
+                ("queue_limit", C.c_void_p), ("queue_aging_s", C.c_void_p), ("queue_running_base", C.c_void_p)]
+
+
+class SchedOut(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("records", C.c_void_p), ("story_running", C.c_void_p),
+                ("queue_running", C.c_void_p), ("queue_max_priority", C.c_void_p), ("global_running", C.c_void_p)]
+
+
+def sched_stride(words: int) -> int:
+    return (16 + 12 * words + 15) & ~15
+
+
 # every symbol include/bobrafrontier.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("bf_abi_version", C.c_uint32, []),
@@ -110,6 +125,8 @@ SYMBOLS = [
     ("bf_layout_init", C.c_int, [C.POINTER(Layout), C.c_uint32, C.c_uint32, C.c_uint32]),
     ("bf_eval", C.c_int, [C.c_void_p, C.POINTER(Batch)]),
     ("bf_eval_device", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
+    ("bf_schedule", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(SchedTables), C.POINTER(SchedOut)]),
+    ("bf_schedule_device", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(SchedTables), C.POINTER(SchedOut), C.c_void_p]),
     ("bf_alloc_pinned", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     ("bf_free_pinned", C.c_int, [C.c_void_p, C.c_void_p]),
     ("bf_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
@@ -142,11 +159,17 @@ def load() -> C.CDLL:
             "bobrapet_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback for the frontier path)" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
+    ab_build = bool(os.environ.get("BF_LIB"))  # an older build loaded for a same-box A/B timing: newer entry points may be absent
     for name, res, args in SYMBOLS:
-        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        try:
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        except AttributeError:
+            if ab_build:
+                continue
+            raise
         fn.restype = res
         fn.argtypes = args
-    if lib.bf_abi_version() != BF_ABI_VERSION:
+    if lib.bf_abi_version() != BF_ABI_VERSION and not ab_build:
         raise RuntimeError("bobrapet_b200: ABI version mismatch")
     _lib = lib
     return lib

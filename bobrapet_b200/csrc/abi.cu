@@ -29,6 +29,7 @@ uint32_t split_entry_bytes(const KParams& P);
 int walk_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
 cudaError_t launch_classify(const KParams& P, uint32_t sm_count, cudaStream_t stream);
 cudaError_t launch_walk(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_schedule(const SchedParams& P, uint32_t sm_count, cudaStream_t stream);
 cudaError_t launch_validate(const Slot* slots, const uint32_t* slot_ids, uint32_t n, uint32_t n_slots, uint32_t* status,
                             cudaStream_t stream);
 }  // namespace bf
@@ -88,6 +89,12 @@ struct bf_ctx {
   uint8_t* d_walk = nullptr; size_t d_walk_cap = 0;      // phase-1 -> phase-2 entries
   uint32_t* d_walk_count = nullptr;
   uint32_t max_csr_bytes = 0;
+
+  // limiters (bf_schedule): what the last bf_eval left on the device + scratch
+  bool last_eval_valid = false;
+  uint32_t last_eval_runs = 0;
+  bf_layout last_eval_layout{};
+  uint8_t* d_sched = nullptr; size_t d_sched_cap = 0;   // runs | records | tables, one allocation
 
   // cached shared-memory plan (recomputed when the layout or the largest record changes)
   uint32_t plan_key_stride = 0, plan_key_words = 0, plan_key_rec = 0, plan_key_variant = 0xFFFFFFFFu;
@@ -445,7 +452,9 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
 
   // ---- shared-memory plan ----
   P.topo_buf_bytes = round_up(c->max_rec_bytes, 16);
-  P.stage_bytes = L.state_stride + P.topo_buf_bytes;
+  uint32_t stage_pad = 0;
+  if (const char* e = getenv("BF_X_STAGE_PAD")) stage_pad = (uint32_t)atoi(e) & ~15u;  // experiment: shifts the alignment of the second stage
+  P.stage_bytes = L.state_stride + P.topo_buf_bytes + stage_pad;
   const uint32_t work_general = round_up(4 * L.words, 16) + 32 * L.words + 16;  // fix-up mask words + status bytes (+ clamp guard)
   const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | ((uint32_t)quad << 9) | (L.fields << 16);
   if (c->plan_wpb == 0 || c->plan_key_stride != L.state_stride || c->plan_key_words != L.words ||
@@ -671,7 +680,7 @@ void bf_destroy(bf_ctx* c) {
   }
   cudaFreeHost(c->h_counts);
   cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
-  cudaFree(c->d_defer); cudaFree(c->d_walk); cudaFree(c->d_walk_count); cudaFree(c->info_dev); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums);
+  cudaFree(c->d_defer); cudaFree(c->d_walk); cudaFree(c->d_walk_count); cudaFree(c->info_dev); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums); cudaFree(c->d_sched);
   delete c;
 }
 
@@ -808,6 +817,7 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
   if (!b || b->struct_size != sizeof(bf_batch)) return fail(c, BF_EINVAL, "bad bf_batch.struct_size");
   if (int rc = check_layout(c, b->layout)) return rc;
   if (b->n_runs && (!b->state || !b->result)) return fail(c, BF_EINVAL, "null state/result");
+  c->last_eval_valid = false;
   const bf_layout& L = b->layout;
   const size_t sbytes = (size_t)b->n_runs * L.state_stride, rbytes = (size_t)b->n_runs * L.result_stride;
   if (b->flags & BF_EVAL_VALIDATE) {
@@ -895,11 +905,105 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
   if (e_sync != cudaSuccess) return cuda_fail(c, e_sync, "cudaStreamSynchronize");
   hc = *c->h_counts;
   c->stats.last_eval_chunks = chunks;
+  c->last_eval_valid = true; c->last_eval_runs = b->n_runs; c->last_eval_layout = L;
   if (want_exp) {
     const uint64_t n = hc.expansion < b->expansion_cap ? hc.expansion : b->expansion_cap;
     if (n) BF_CUDA(c, cudaMemcpy(b->expansion, c->d_exp, (size_t)n * sizeof(bf_expansion), cudaMemcpyDeviceToHost));
   }
   if (b->counts) *b->counts = hc;
+  return BF_OK;
+}
+
+// ---- limiters (rows a9 / f4) ----------------------------------------------------------------------------
+static int fill_sched_params(bf_ctx* c, const bf_batch* b, const bf_sched_tables* t, bf::SchedParams& P) {
+  if (!b || b->struct_size != sizeof(bf_batch)) return fail(c, BF_EINVAL, "bad bf_batch.struct_size");
+  if (!t || t->struct_size != sizeof(bf_sched_tables)) return fail(c, BF_EINVAL, "bad bf_sched_tables.struct_size");
+  if (int rc = check_layout(c, b->layout)) return rc;
+  if ((t->n_stories && !t->story_limit) || (t->n_queues && (!t->queue_limit || !t->queue_aging_s)))
+    return fail(c, BF_EINVAL, "null limit table");
+  const bf_layout& L = b->layout;
+  P.n_stories = t->n_stories; P.n_queues = t->n_queues; P.global_limit = t->global_limit; P.global_base = t->global_running_base;
+  P.n_slots = (uint32_t)c->slots_host.size(); P.n_runs = b->n_runs;
+  P.words = L.words; P.state_stride = L.state_stride; P.off_phase = L.off_phase; P.off_child = L.off_child;
+  P.result_stride = L.result_stride; P.off_ready = L.off_ready; P.stride = BF_SCHED_STRIDE(L.words);
+  P.slots = c->slots_dev;
+  return BF_OK;
+}
+
+int bf_schedule_device(bf_ctx* c, const bf_batch* b, const bf_sched_run* runs, const bf_sched_tables* t, bf_sched_out* out,
+                       void* stream) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  bf::SchedParams P{};
+  if (int rc = fill_sched_params(c, b, t, P)) return rc;
+  if (!out || out->struct_size != sizeof(bf_sched_out)) return fail(c, BF_EINVAL, "bad bf_sched_out.struct_size");
+  if (b->n_runs && (!b->state || !b->result || !runs || !out->records)) return fail(c, BF_EINVAL, "null state/result/runs/records");
+  if (!out->story_running || !out->queue_running || !out->queue_max_priority || !out->global_running)
+    return fail(c, BF_EINVAL, "device path: the totals arrays are the reduction scratch and must be given");
+  BF_CUDA(c, cudaSetDevice(c->device));
+  if (int rc = sync_slots(c, static_cast<cudaStream_t>(stream))) return rc;
+  P.slots = c->slots_dev;
+  P.state = static_cast<const uint8_t*>(b->state); P.result = static_cast<const uint8_t*>(b->result);
+  P.runs = runs; P.records = static_cast<uint8_t*>(out->records);
+  P.story_running = out->story_running; P.queue_running = out->queue_running; P.queue_maxprio = out->queue_max_priority;
+  P.global_running = out->global_running;
+  P.story_limit = t->story_limit; P.queue_limit = t->queue_limit; P.queue_aging = t->queue_aging_s;
+  P.story_base = t->story_running_base; P.queue_base = t->queue_running_base;
+  BF_CUDA(c, bf::launch_schedule(P, (uint32_t)c->sm_count, static_cast<cudaStream_t>(stream)));
+  c->stats.kernel_launches += 3;
+  return BF_OK;
+}
+
+int bf_schedule(bf_ctx* c, const bf_batch* b, const bf_sched_run* runs, const bf_sched_tables* t, bf_sched_out* out) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  bf::SchedParams P{};
+  if (int rc = fill_sched_params(c, b, t, P)) return rc;
+  if (!out || out->struct_size != sizeof(bf_sched_out)) return fail(c, BF_EINVAL, "bad bf_sched_out.struct_size");
+  if (b->n_runs && (!runs || !out->records)) return fail(c, BF_EINVAL, "null runs/records");
+  if (!c->last_eval_valid || c->last_eval_runs != b->n_runs || memcmp(&c->last_eval_layout, &b->layout, sizeof(bf_layout)) != 0)
+    return fail(c, BF_EINVAL, "bf_schedule must follow bf_eval of the same batch (n_runs and layout) on this ctx");
+  BF_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  // one device allocation: runs | records | story_running | queue_running | queue_maxprio | global | limits | bases
+  const size_t n = b->n_runs, ns = t->n_stories, nq = t->n_queues;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off = round_up_sz(off + bytes, 16); return o; };
+  const size_t o_runs = take(n * sizeof(bf_sched_run)), o_rec = take(n * (size_t)P.stride), o_sr = take(ns * 4), o_qr = take(nq * 4),
+               o_mp = take(nq * 4), o_gl = take(4), o_sl = take(ns * 4), o_ql = take(nq * 4), o_qa = take(nq * 4), o_sb = take(ns * 4),
+               o_qb = take(nq * 4);
+  if (int rc = ensure_dev(c, c->d_sched, c->d_sched_cap, off ? off : 16)) return rc;
+  uint8_t* d = c->d_sched;
+  auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+    return (src && bytes) ? cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+  };
+  BF_CUDA(c, up(o_runs, runs, n * sizeof(bf_sched_run)));
+  BF_CUDA(c, up(o_sl, t->story_limit, ns * 4));
+  BF_CUDA(c, up(o_ql, t->queue_limit, nq * 4));
+  BF_CUDA(c, up(o_qa, t->queue_aging_s, nq * 4));
+  BF_CUDA(c, up(o_sb, t->story_running_base, ns * 4));
+  BF_CUDA(c, up(o_qb, t->queue_running_base, nq * 4));
+  P.state = c->d_state; P.result = c->d_result;
+  P.runs = reinterpret_cast<const bf_sched_run*>(d + o_runs); P.records = d + o_rec;
+  P.story_running = reinterpret_cast<uint32_t*>(d + o_sr); P.queue_running = reinterpret_cast<uint32_t*>(d + o_qr);
+  P.queue_maxprio = reinterpret_cast<int32_t*>(d + o_mp); P.global_running = reinterpret_cast<uint32_t*>(d + o_gl);
+  P.story_limit = reinterpret_cast<const int32_t*>(d + o_sl); P.queue_limit = reinterpret_cast<const int32_t*>(d + o_ql);
+  P.queue_aging = reinterpret_cast<const int32_t*>(d + o_qa);
+  P.story_base = t->story_running_base ? reinterpret_cast<const uint32_t*>(d + o_sb) : nullptr;
+  P.queue_base = t->queue_running_base ? reinterpret_cast<const uint32_t*>(d + o_qb) : nullptr;
+  cudaError_t e = bf::launch_schedule(P, (uint32_t)c->sm_count, s);
+  c->stats.kernel_launches += 3;
+  auto down = [&](void* dst, size_t o, size_t bytes) -> cudaError_t {
+    return (dst && bytes) ? cudaMemcpyAsync(dst, d + o, bytes, cudaMemcpyDeviceToHost, s) : cudaSuccess;
+  };
+  if (e == cudaSuccess) e = down(out->records, o_rec, n * (size_t)P.stride);
+  if (e == cudaSuccess) e = down(out->story_running, o_sr, ns * 4);
+  if (e == cudaSuccess) e = down(out->queue_running, o_qr, nq * 4);
+  if (e == cudaSuccess) e = down(out->queue_max_priority, o_mp, nq * 4);
+  if (e == cudaSuccess) e = down(out->global_running, o_gl, 4);
+  const cudaError_t es = cudaStreamSynchronize(s);  // never return with copies into the caller's buffers in flight
+  if (e != cudaSuccess) return cuda_fail(c, e, "bf_schedule");
+  if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
   return BF_OK;
 }
 

@@ -115,4 +115,26 @@ struct KParams {
   uint32_t wq, wq_log2;
 };
 
+// limiters.cu (rows a9 / f4)
+struct SchedParams {
+  const uint8_t* state;
+  const uint8_t* result;
+  const Slot* slots;
+  const bf_sched_run* runs;
+  uint8_t* records;            // [n_runs][stride]
+  uint32_t* story_running;     // totals (pre-loaded with the base counts)
+  uint32_t* queue_running;
+  int32_t* queue_maxprio;      // pre-loaded with INT32_MIN
+  uint32_t* global_running;
+  const int32_t* story_limit;
+  const int32_t* queue_limit;
+  const int32_t* queue_aging;
+  const uint32_t* story_base;  // StepRuns the batch does not hold, or nullptr
+  const uint32_t* queue_base;
+  uint32_t global_base;
+  int32_t global_limit;
+  uint32_t n_stories, n_queues, n_slots, n_runs;
+  uint32_t words, state_stride, off_phase, off_child, result_stride, off_ready, stride;
+};
+
 }  // namespace bf

@@ -40,14 +40,24 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
 
   // ---- shared memory carve-up: [block counters 128 B][warp regions] ----
   unsigned long long* blk_counts = reinterpret_cast<unsigned long long*>(smem_raw);
+#ifndef BF_X_BAR
+#define BF_X_BAR 2
+#endif
+#ifndef BF_X_FD
+#define BF_X_FD 1
+#endif
+  // per warp: ST stages of [state record | topology record], then scratch.  The stages' mbarriers live AWAY from
+  // the TMA destinations (a barrier next to the record tail costs ~9%: measured): BF_X_BAR 2 = one block for the
+  // whole CTA in front of the warp regions, 0 = behind each warp's scratch.
   const uint32_t ring_bytes = ST * P.stage_bytes;
-  const uint32_t per_warp = ring_bytes + P.work_bytes + 64;  // + mbarriers (<= 8 stages)
-  uint8_t* const wbase = smem_raw + 128 + warp * per_warp;
-  const uint32_t bars = pin(smem_u32(wbase + ring_bytes + P.work_bytes));
+  const uint32_t per_warp = ring_bytes + P.work_bytes + (BF_X_BAR == 2 ? 0u : 64u);
+  uint8_t* const wbase = smem_raw + 128 + (BF_X_BAR == 2 ? P.warps_per_block * 64u : 0u) + warp * per_warp;
+  const uint32_t wb = pin(smem_u32(wbase));  // pinned: otherwise rematerialised from S2R inside the loop
+  const uint32_t bar_base = pin(BF_X_BAR == 2 ? smem_u32(smem_raw) + 128u + warp * 64u : wb + ring_bytes + P.work_bytes);
 
   if (threadIdx.x < 4) blk_counts[threadIdx.x] = 0ull;
   if (lane == 0) {
-    for (uint32_t s = 0; s < ST; ++s) mbar_init(bars + 8 * s, 1);
+    for (uint32_t s = 0; s < ST; ++s) mbar_init(bar_base + 8 * s, 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -105,11 +115,10 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
     if ((ni & 31u) == 16u) load_sids((ni & ~31u) + 32u);  // half a batch ahead
     if ((ni & 31u) == 0u) load_ents();                    // consumed from the next issue on
   };
-  const uint32_t wb = pin(smem_u32(wbase));
   if (my_runs != 0) {
     load_sids(0);
     load_ents();
-    for (uint32_t s = 0; s < ST; ++s) issue(wb + s * P.stage_bytes, bars + 8 * s);
+    for (uint32_t s = 0; s < ST; ++s) issue(wb + s * P.stage_bytes, bar_base + 8 * s);
   }
 
   // scratch (per warp): fix-up fail mask words, then one status byte per step (+16 clamp guard)
@@ -117,15 +126,15 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
   //  pointers, no cvta, no 64-bit address arithmetic)
   const uint32_t Wmax = P.words;
   const uint32_t mfail_a = wb + ring_bytes;
-  const uint32_t st_a = pin(mfail_a + ((4u * Wmax + 15u) & ~15u));
+  const uint32_t st_a = mfail_a + ((4u * Wmax + 15u) & ~15u);
 
   const bool has_cond = CD && P.off_cond != BF_OFF_NONE;
   const bool has_dec = CD && P.off_decision != BF_OFF_NONE;
   const bool has_child = CH && P.off_child != BF_OFF_NONE;
 
   uint32_t tot_ready = 0, tot_skip = 0, tot_exp = 0, tot_evals = 0;  // lane-uniform
-  uint32_t cs = 0, cpar = 0;                                         // consumer stage / parity
-  uint32_t stage_a = wb, bar_a = bars;                               // shared addresses of the consumer stage / its mbarrier
+  uint32_t cs = 0, cpar = 0;                                         // consumer stage index / parity
+  uint32_t stage_a = wb;                                             // shared address of the consumer stage
   const size_t result_step = (size_t)rstride * P.result_stride;
   uint8_t* rr_inc = P.result + (size_t)rbase * P.result_stride;
   uint32_t r_inc = rbase;
@@ -133,11 +142,11 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
   for (uint32_t k = 0; k < my_runs; ++k, rr_inc += result_step, r_inc += rstride) {
     const uint32_t r = LIST ? run_of(k) : r_inc;
     uint8_t* const rr = LIST ? P.result + (size_t)r * P.result_stride : rr_inc;
-    mbar_wait(bar_a, cpar);
-    const uint32_t cur_stage = stage_a, cur_bar = bar_a;  // the stage index ni = k + ST will be copied into
+    const uint32_t cur_stage = stage_a, cur_bar = bar_base + 8u * cs;
+    mbar_wait(cur_bar, cpar);  // the stage index ni = k + ST will be copied into
     const uint32_t sr_a = cur_stage, tr_a = cur_stage + P.state_stride;  // state record / topology record
-    ++cs; stage_a += P.stage_bytes; bar_a += 8;
-    if (cs == ST) { cs = 0; stage_a = wb; bar_a = bars; cpar ^= 1u; }
+    stage_a += P.stage_bytes; ++cs;
+    if (cs == ST) { cs = 0; stage_a = wb; cpar ^= 1u; }
 
     const uint4 h0 = lds_v4(tr_a);                               // TopoHeader, first half
     const uint32_t S = h0.x & 0xFFFFu, Wt = h0.x >> 16;          // S, W
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
     const uint32_t n_main = h0.z & 0xFFFFu, n_comp = h0.z >> 16, n_final = h0.w & 0xFFFFu;
     if (Wt - 1u >= Wmax) {  // dead slot (zero header) / out-of-range record: empty result, summary all-ones
       for (uint32_t x = lane; x < P.result_stride / 4; x += 32) reinterpret_cast<uint32_t*>(rr)[x] = x == 0 ? 0xFFFFFFFFu : 0u;
-      if (P.exp_counts && lane == 0) P.exp_counts[r] = 0;
+      if (CH && P.exp_counts && lane == 0) P.exp_counts[r] = 0;
       __syncwarp();
       issue(cur_stage, cur_bar);
       continue;
@@ -348,7 +357,9 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         const uint32_t CAND = GSEL & ~COMPL & ~RUNQ & ~TERM;
         // ------------- stage C: masks -> one status byte per step (bit0 unmet, bit1 failed-dep) -------------
         __syncwarp();
-        for (uint32_t m0 = 0; m0 < 4 * Wt; m0 += 32) {  // uniform trip count: every lane takes part in the shuffles
+        uint32_t m0 = 0;
+#pragma unroll 1
+        do {  // uniform trip count (one trip per 256 steps): every lane takes part in the shuffles
           const uint32_t m = m0 + lane;
           const uint32_t src = (m >> 2) & 31u, sh = (m & 3u) * 8u;
           const uint32_t ub = __shfl_sync(FULL, U, src) >> sh;
@@ -361,11 +372,13 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
             v.y |= bits4_to_bytes((fb >> 4) & 0xFu) << 1;
           }
           if (m < 4 * Wt) sts_v2(st_a + m * 8u, v.x, v.y);
-        }
+          m0 += 32;
+        } while (m0 < 4 * Wt);
         __syncwarp();
         // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
         uint32_t met_w, fd_w;
-        walk_rows_s(lane, CAND, max_deg, rp_a, col_a, st_a, met_w, fd_w);
+        if (!BF_X_FD || skip_on_failed) walk_rows_s<true>(lane, CAND, max_deg, rp_a, col_a, st_a, met_w, fd_w);
+        else walk_rows_s<false>(lane, CAND, max_deg, rp_a, col_a, st_a, met_w, fd_w);
         uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
         if (CD) {
           ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
@@ -440,7 +453,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
     summary |= (changed ? BF_SUM_PHASE_CHANGED : 0u) | (iters << BF_SUM_ITER_SHIFT);
     if (lane == 0) {
       *reinterpret_cast<uint4*>(rr) = make_uint4(summary, n_ready, n_skip, n_exp);
-      if (P.exp_counts) P.exp_counts[r] = n_exp;
+      if (CH && P.exp_counts) P.exp_counts[r] = n_exp;
     }
     if (lane < Wmax) {
       reinterpret_cast<uint32_t*>(rr + P.off_ready)[lane] = acc_ready;

@@ -172,6 +172,8 @@ DI void walk_rows(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_deg,
 
 // Same walk with explicit 32-bit shared addresses (ld.shared), for kernels whose CSR / status arrays are given
 // as shared-window addresses: keeps every address computation a single 32-bit add.
+// NEED_FD = false: the policy has no failed-dependency class (status bit 1 is never set), fd_w stays 0.
+template <bool NEED_FD>
 DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t max_deg, uint32_t rp_addr, uint32_t col_addr,
                     uint32_t st_addr, uint32_t& met_w, uint32_t& fd_w) {
   met_w = 0;
@@ -201,12 +203,12 @@ DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t max_deg, uint32_t rp_
     if (max_deg > 4) {  // warp-uniform
       for (uint32_t e = 4; e < n; ++e) w |= lds_u8(st_addr + lds_u16(cpa + e * 2u));
     }
-    const uint32_t fdb = __ballot_sync(FULL, (w & 0x02020202u) != 0);
     const uint32_t metb = __ballot_sync(FULL, cand && (w & 0x01010101u) == 0);
-    if (lane == j) {
-      fd_w = fdb;
-      met_w = metb;
+    if (NEED_FD) {
+      const uint32_t fdb = __ballot_sync(FULL, (w & 0x02020202u) != 0);
+      if (lane == j) fd_w = fdb;
     }
+    if (lane == j) met_w = metb;
   }
 }
 

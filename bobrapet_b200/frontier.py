@@ -149,6 +149,37 @@ class Frontier:
             return result, cdict, exp[:min(int(counts.expansion), expansion_cap)]
         return result, cdict
 
+
+    # -- limiters over the ready sets of the batch just evaluated (rows a9 / f4; dag.go:1780-1961)
+    def schedule(self, L: A.Layout, n_runs: int, sched_runs: np.ndarray, story_limit, queue_limit, queue_aging_s,
+                 global_limit: int = 0, story_running_base=None, queue_running_base=None, global_running_base: int = 0):
+        """bf_schedule: must follow eval() of the same batch.  sched_runs: [n_runs] records of 32 bytes (bf_sched_run).
+        Returns dict(records [n, stride] uint8, story_running, queue_running, queue_max_priority, global_running)."""
+        assert sched_runs.nbytes == 32 * n_runs and sched_runs.flags["C_CONTIGUOUS"]
+        sl = np.ascontiguousarray(story_limit, dtype=np.int32)
+        ql = np.ascontiguousarray(queue_limit, dtype=np.int32)
+        qa = np.ascontiguousarray(queue_aging_s, dtype=np.int32)
+        sb = None if story_running_base is None else np.ascontiguousarray(story_running_base, dtype=np.uint32)
+        qb = None if queue_running_base is None else np.ascontiguousarray(queue_running_base, dtype=np.uint32)
+        assert ql.shape == qa.shape
+        t = A.SchedTables(struct_size=C.sizeof(A.SchedTables), n_stories=sl.size, n_queues=ql.size, global_limit=global_limit,
+                          global_running_base=global_running_base, story_limit=sl.ctypes.data,
+                          story_running_base=(sb.ctypes.data if sb is not None else None), queue_limit=ql.ctypes.data,
+                          queue_aging_s=qa.ctypes.data, queue_running_base=(qb.ctypes.data if qb is not None else None))
+        stride = A.sched_stride(L.words)
+        rec = np.zeros((n_runs, stride), dtype=np.uint8)
+        sr = np.zeros(max(sl.size, 1), dtype=np.uint32)
+        qr = np.zeros(max(ql.size, 1), dtype=np.uint32)
+        mp = np.zeros(max(ql.size, 1), dtype=np.int32)
+        gr = np.zeros(1, dtype=np.uint32)
+        out = A.SchedOut(struct_size=C.sizeof(A.SchedOut), records=rec.ctypes.data, story_running=sr.ctypes.data,
+                         queue_running=qr.ctypes.data, queue_max_priority=mp.ctypes.data, global_running=gr.ctypes.data)
+        b = A.Batch(struct_size=C.sizeof(A.Batch), n_runs=n_runs, layout=L)
+        self._check(self._lib.bf_schedule(self._ctx, C.byref(b), C.c_void_p(sched_runs.ctypes.data), C.byref(t), C.byref(out)),
+                    "bf_schedule")
+        return {"records": rec, "story_running": sr[:sl.size], "queue_running": qr[:ql.size], "queue_max_priority": mp[:ql.size],
+                "global_running": int(gr[0])}
+
     # -- evaluation over DEVICE buffers (async on `stream`)
     def eval_device(self, L: A.Layout, n_runs: int, state_ptr: int, result_ptr: int, counts_ptr: int = 0,
                     stream: int = 0, flags: int = 0, max_iterations: int = 0, expansion_ptr: int = 0,

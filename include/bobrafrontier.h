@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define BF_ABI_VERSION 1u
+#define BF_ABI_VERSION 2u
 
 /* ------------------------------------------------------------------ status */
 typedef enum bf_status {
@@ -299,6 +299,86 @@ int bf_eval(bf_ctx* ctx, const bf_batch* batch);
  * counts must be zeroed by the caller unless BF_EVAL_NO_COUNTS (the library
  * only adds).                                                                 */
 int bf_eval_device(bf_ctx* ctx, const bf_batch* batch, void* stream);
+
+/* ------------------------------------------------------------------ limiters
+ * The consumer of the ready sets: findAndLaunchReadySteps applies enforceStoryConcurrency (dag.go:1780-1799)
+ * and enforceSchedulingLimits (:1801-1861, with enforcePriorityOrdering :1910-1946 and effectivePriority
+ * :1948-1961) to each run's ready LIST and keeps a prefix (readySteps[:slots]); the rest is marked
+ * "Queued due to ...".  Ready masks are LSB-first = list order, so the prefix is "the first k set bits".
+ *
+ * Batch contract (one consistent snapshot per tick): first the counts the reference obtains from cluster LISTs
+ * are REDUCED over the batch on the device —
+ *   running StepRuns of a run = engram steps in phase Running + Running children of registered parallel steps
+ *                               (StepState mirrors StepRun.Status.Phase after syncStateFromStepRuns, :965-1009),
+ *   per story key / per queue key / global totals = host-supplied base (StepRuns the batch does not hold) + sum,
+ *   per queue the highest effective priority among non-terminal runs with demand (storyRunHasDemand :1981-1999:
+ *   run phase Running/Pending, or a step Running or queued) —
+ * then every run is limited independently against them (StepRuns created in the same tick have no phase yet
+ * and do not count, exactly as in the reference).  Host work that stays on the host: label -> key mapping,
+ * time (queued_elapsed_s = int32((now - storyRunQueuedSince).Seconds()), BF_SCHED_NONE when nothing is queued
+ * with a StartedAt), formatting "(%d running, limit %d)" from the totals returned here.
+ * A run's own label priority is the priority its Story resolves to (ensureSchedulingLabels, scheduling.go:48-70).
+ */
+#define BF_SCHED_NONE 0xFFFFFFFFu
+enum {                       /* why the steps in queued_sched were queued                               */
+  BF_QUEUED_NONE = 0,
+  BF_QUEUED_PRIORITY = 1,    /* "Queued due to higher-priority work"      dag.go:1807-1811               */
+  BF_QUEUED_GLOBAL = 2,      /* "Queued due to global concurrency limit"  dag.go:1849-1850               */
+  BF_QUEUED_QUEUE = 3,       /* "Queued due to queue concurrency limit"   dag.go:1851-1852               */
+  BF_QUEUED_OTHER = 4        /* "Queued due to scheduling limits"         dag.go:1853-1855               */
+};
+
+typedef struct bf_sched_run { /* 32 B per run                                                           */
+  uint32_t story_key;         /* index into the story tables (namespace + Story name)                    */
+  uint32_t queue_key;         /* index into the queue tables (queueLabelValue of the scheduling decision)*/
+  int32_t priority;           /* schedulingDecision.Priority == the run's priority label                 */
+  uint32_t queued_elapsed_s;  /* seconds queued, BF_SCHED_NONE if no queued step has a StartedAt         */
+  uint32_t run_phase;         /* BF_PHASE_* of StoryRun.Status.Phase                                     */
+  uint32_t reserved[3];
+} bf_sched_run;
+
+typedef struct bf_sched_tables {
+  uint32_t struct_size;
+  uint32_t n_stories, n_queues;
+  int32_t global_limit;                /* scheduling.globalConcurrency, <= 0: none                       */
+  uint32_t global_running_base;
+  const int32_t* story_limit;          /* [n_stories] Story.spec.policy.concurrency, <= 0: none          */
+  const uint32_t* story_running_base;  /* [n_stories] or NULL (zeros)                                     */
+  const int32_t* queue_limit;          /* [n_queues]  queues[q].concurrency, <= 0: none                  */
+  const int32_t* queue_aging_s;        /* [n_queues]  queues[q].priorityAgingSeconds, <= 0: no aging      */
+  const uint32_t* queue_running_base;  /* [n_queues] or NULL (zeros)                                      */
+} bf_sched_tables;
+
+typedef struct bf_sched_header { /* first 16 B of a schedule record                                     */
+  uint32_t n_launch;             /* popcount(launch): steps to hand to StepExecutor.Execute              */
+  uint32_t n_queued_story;       /* queued by the Story's own concurrency limit                          */
+  uint32_t n_queued_sched;       /* queued by priority ordering / queue / global limits                  */
+  uint32_t sched_reason;         /* BF_QUEUED_*                                                          */
+} bf_sched_header;
+
+/* schedule record of a run: bf_sched_header, then launch[words], queued_story[words], queued_sched[words]
+ * (u32 bit masks, same bit order as ready); stride = BF_SCHED_STRIDE(words), a multiple of 16.           */
+#define BF_SCHED_STRIDE(words) ((16u + 12u * (uint32_t)(words) + 15u) & ~15u)
+
+typedef struct bf_sched_out {
+  uint32_t struct_size;
+  uint32_t reserved;
+  void* records;                 /* [n_runs][BF_SCHED_STRIDE(layout.words)]                               */
+  uint32_t* story_running;       /* [n_stories] totals used (base + batch), or NULL                       */
+  uint32_t* queue_running;       /* [n_queues] or NULL                                                    */
+  int32_t* queue_max_priority;   /* [n_queues] INT32_MIN when no run of the queue has demand, or NULL     */
+  uint32_t* global_running;      /* [1] or NULL                                                           */
+} bf_sched_out;
+
+/* Host buffers.  Limits the ready sets of the batch evaluated by the IMMEDIATELY PRECEDING bf_eval on this
+ * ctx (same n_runs and layout; its state and result records are still on the device).  Synchronous.      */
+int bf_schedule(bf_ctx* ctx, const bf_batch* batch, const bf_sched_run* runs, const bf_sched_tables* tables,
+                bf_sched_out* out);
+/* Device buffers: batch->state / batch->result as for bf_eval_device, runs / table arrays / out arrays are
+ * device pointers (totals arrays are required here: they are the reduction scratch).  Asynchronous on `stream`. */
+int bf_schedule_device(bf_ctx* ctx, const bf_batch* batch, const bf_sched_run* runs, const bf_sched_tables* tables,
+                       bf_sched_out* out, void* stream);
+
 
 /* Pinned host memory for batches (cgo: memory with no Go pointers).           */
 int bf_alloc_pinned(bf_ctx* ctx, size_t bytes, void** out);
