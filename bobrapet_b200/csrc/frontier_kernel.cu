@@ -43,9 +43,6 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
 #ifndef BF_X_BAR
 #define BF_X_BAR 2
 #endif
-#ifndef BF_X_FD
-#define BF_X_FD 1
-#endif
   // per warp: ST stages of [state record | topology record], then scratch.  The stages' mbarriers live AWAY from
   // the TMA destinations (a barrier next to the record tail costs ~9%: measured): BF_X_BAR 2 = one block for the
   // whole CTA in front of the warp regions, 0 = behind each warp's scratch.
@@ -174,8 +171,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
       if (CD) TS = lds_u32(sp + PL_TS * ps);
       if (XO) HASIF = lds_u32(sp + PL_HASIF * ps);
       G1 = lds_u32(sp + PL_G1 * ps); G2 = lds_u32(sp + PL_G2 * ps);
-      const uint32_t rem = S - lane * 32;
-      VALID = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
+      VALID = bmsk_clamp(0u, S - lane * 32u);  // the word's steps below S (width clamps at 32)
       const uint32_t pw = sr_a + P.off_phase + lane * 4u, ds = Wmax * 4u;  // dynamic planes: stride of the layout
       p0 = lds_u32(pw); p1 = lds_u32(pw + ds); p2 = lds_u32(pw + 2u * ds); p3 = lds_u32(pw + 3u * ds);
       const uint32_t keep = VALID & ~(p0 & p1 & p2 & p3);   // steps >= S and the reserved code 15 read as 0
@@ -377,8 +373,13 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         __syncwarp();
         // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
         uint32_t met_w, fd_w;
-        if (!BF_X_FD || skip_on_failed) walk_rows_s<true>(lane, CAND, max_deg, rp_a, col_a, st_a, met_w, fd_w);
-        else walk_rows_s<false>(lane, CAND, max_deg, rp_a, col_a, st_a, met_w, fd_w);
+        if (max_deg > 4) {  // warp-uniform: rows longer than the straight-line four exist in this topology
+          if (skip_on_failed) walk_rows_s<true, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
+          else walk_rows_s<false, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
+        } else {
+          if (skip_on_failed) walk_rows_s<true, false>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
+          else walk_rows_s<false, false>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
+        }
         uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
         if (CD) {
           ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS

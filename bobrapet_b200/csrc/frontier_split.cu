@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(512) walk_kernel(const KParams P) {
     // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
     const uint32_t zidx = 32 * Wt;
     uint32_t met_w, fd_w;
-    walk_rows_s<true>(lane, CAND, max_deg, smem_u32(row_ptr), smem_u32(col), st_addr, met_w, fd_w);
+    walk_rows_s<true, true>(lane, CAND, smem_u32(row_ptr), smem_u32(col), st_addr, met_w, fd_w);
     uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
     if (CD) {
       ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS

@@ -173,8 +173,10 @@ DI void walk_rows(uint32_t lane, uint32_t CAND, uint32_t zidx, uint32_t max_deg,
 // Same walk with explicit 32-bit shared addresses (ld.shared), for kernels whose CSR / status arrays are given
 // as shared-window addresses: keeps every address computation a single 32-bit add.
 // NEED_FD = false: the policy has no failed-dependency class (status bit 1 is never set), fd_w stays 0.
-template <bool NEED_FD>
-DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t max_deg, uint32_t rp_addr, uint32_t col_addr,
+// LONG_ROWS = false: no row of this topology has more than 4 dependencies (TopoHeader.max_deg), the tail loop is
+// compiled out instead of being tested per lane.
+template <bool NEED_FD, bool LONG_ROWS>
+DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t rp_addr, uint32_t col_addr,
                     uint32_t st_addr, uint32_t& met_w, uint32_t& fd_w) {
   met_w = 0;
   fd_w = 0;
@@ -200,7 +202,7 @@ DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t max_deg, uint32_t rp_
     const uint32_t s0 = lds_u8(st_addr + x0), s1 = lds_u8(st_addr + x1), s2 = lds_u8(st_addr + x2), s3 = lds_u8(st_addr + x3);
     uint32_t w = ((s3 * 256u + s2) * 256u + s1) * 256u + s0;
     w &= bmsk_clamp(0u, n * 8u);
-    if (max_deg > 4) {  // warp-uniform
+    if (LONG_ROWS) {
       for (uint32_t e = 4; e < n; ++e) w |= lds_u8(st_addr + lds_u16(cpa + e * 2u));
     }
     const uint32_t metb = __ballot_sync(FULL, cand && (w & 0x01010101u) == 0);
