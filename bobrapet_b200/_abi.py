@@ -120,6 +120,7 @@ SYMBOLS = [
     ("bf_topology_put_many", C.c_int, [C.c_void_p, C.POINTER(Topology), C.c_uint32, C.POINTER(C.c_uint32)]),
     ("bf_topology_put_many_checked_on_device", C.c_int, [C.c_void_p, C.POINTER(Topology), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("bf_topology_check", C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("bf_topology_closure", C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("bf_topology_drop", C.c_int, [C.c_void_p, C.c_uint32]),
     ("bf_topology_child_first", C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]),
     ("bf_layout_init", C.c_int, [C.POINTER(Layout), C.c_uint32, C.c_uint32, C.c_uint32]),

@@ -30,6 +30,8 @@ int walk_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_byt
 cudaError_t launch_classify(const KParams& P, uint32_t sm_count, cudaStream_t stream);
 cudaError_t launch_walk(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_schedule(const SchedParams& P, uint32_t sm_count, cudaStream_t stream);
+cudaError_t launch_closure(const Slot* slots, const uint32_t* slot_ids, const uint32_t* starts, uint32_t n, uint32_t n_slots,
+                           uint32_t words_out, uint32_t* masks, cudaStream_t stream);
 cudaError_t launch_validate(const Slot* slots, const uint32_t* slot_ids, uint32_t n, uint32_t n_slots, uint32_t* status,
                             cudaStream_t stream);
 }  // namespace bf
@@ -717,6 +719,35 @@ int bf_topology_check(bf_ctx* c, const uint32_t* slots, uint32_t count, uint32_t
   std::lock_guard<std::mutex> g(c->mu);
   BF_CUDA(c, cudaSetDevice(c->device));
   return check_locked(c, slots, count, status_out);
+}
+
+int bf_topology_closure(bf_ctx* c, const uint32_t* slots, const uint32_t* steps, uint32_t count, uint32_t words, uint32_t* masks_out) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (count && (!slots || !steps || !masks_out)) return fail(c, BF_EINVAL, "null argument");
+  if (words == 0 || words > BF_MAX_STEPS / 32) return fail(c, BF_EINVAL, "words out of range (1..32)");
+  for (uint32_t i = 0; i < count; ++i) {
+    if (slots[i] >= c->meta.size() || !c->meta[slots[i]].alive) return fail(c, BF_ETOPO, "query " + std::to_string(i) + ": unknown topology slot");
+    const TopoMeta& m = c->meta[slots[i]];
+    if (steps[i] >= m.S) return fail(c, BF_EINVAL, "query " + std::to_string(i) + ": step index out of range");  // "step %q not found", :541
+    if ((m.S + 31) / 32 > words) return fail(c, BF_EINVAL, "query " + std::to_string(i) + ": mask too narrow for the topology");
+  }
+  if (count == 0) return BF_OK;
+  BF_CUDA(c, cudaSetDevice(c->device));
+  if (int rc = sync_slots(c, c->stream)) return rc;
+  uint32_t* d = nullptr;
+  const size_t q_bytes = (size_t)count * 4, m_bytes = (size_t)count * words * 4;
+  BF_CUDA(c, cudaMalloc(&d, 2 * q_bytes + m_bytes));
+  cudaError_t e = cudaMemcpyAsync(d, slots, q_bytes, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + count, steps, q_bytes, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = bf::launch_closure(c->slots_dev, d, d + count, count, (uint32_t)c->slots_host.size(), words, d + 2 * (size_t)count, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(masks_out, d + 2 * (size_t)count, m_bytes, cudaMemcpyDeviceToHost, c->stream);
+  const cudaError_t es = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  c->stats.kernel_launches += 1;
+  if (e != cudaSuccess) return cuda_fail(c, e, "bf_topology_closure");
+  if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
+  return BF_OK;
 }
 
 static int drop_locked(bf_ctx* c, uint32_t slot);

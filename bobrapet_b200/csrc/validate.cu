@@ -62,6 +62,64 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const Slot* sl
   if (lane == 0) status[t] = (n_done != S ? 1u : 0u) | (levels << 8);
 }
 
+// Redrive closure (resolveRedriveFromStepSet, internal/controller/runs/storyrun_controller.go:535-558): the steps to
+// reset when a run is re-driven from `start` = start plus everything downstream of it through the dependents
+// edges of buildDependencyGraphs over the start step's OWN group (findStepGroup :560-577).  One warp per query;
+// monotone fixed point over the CSR rows instead of the reference's queue (same closure, order-free).
+__global__ void __launch_bounds__(VAL_WARPS * 32) closure_kernel(const Slot* slots, const uint32_t* slot_ids, const uint32_t* starts,
+                                                                 uint32_t n, uint32_t n_slots, uint32_t words_out, uint32_t* masks) {
+  __shared__ uint32_t sel_s[VAL_WARPS][BF_MAX_STEPS / 32];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t t = blockIdx.x * VAL_WARPS + warp;
+  if (t >= n) return;
+  uint32_t* out = masks + (size_t)t * words_out;
+  for (uint32_t w = lane; w < words_out; w += 32) out[w] = 0u;
+  const uint32_t sid = slot_ids[t];
+  if (sid >= n_slots || slots[sid].addr == 0) return;
+  const uint8_t* rec = reinterpret_cast<const uint8_t*>(slots[sid].addr);
+  const TopoHeader* th = reinterpret_cast<const TopoHeader*>(rec);
+  const uint32_t S = th->S, W = th->W, start = starts[t];
+  if (start >= S || W > words_out) return;
+  const uint16_t* row_ptr = reinterpret_cast<const uint16_t*>(rec + sizeof(TopoHeader));
+  const uint16_t* col = reinterpret_cast<const uint16_t*>(rec + th->off_col);
+  const uint32_t* planes = reinterpret_cast<const uint32_t*>(rec + th->off_planes);
+  auto group_of = [&](uint32_t i) -> uint32_t {
+    const uint32_t w = i >> 5, b = i & 31u;
+    return ((planes[PL_G1 * W + w] >> b) & 1u) | (((planes[PL_G2 * W + w] >> b) & 1u) << 1);
+  };
+  const uint32_t g0 = group_of(start);
+  uint32_t* sel = sel_s[warp];
+  for (uint32_t w = lane; w < W; w += 32) sel[w] = 0;
+  __syncwarp();
+  if (lane == 0) sel[start >> 5] = 1u << (start & 31u);
+  __syncwarp();
+  for (;;) {
+    bool changed = false;
+    for (uint32_t i = lane; i < S; i += 32) {
+      if ((sel[i >> 5] >> (i & 31u)) & 1u) continue;
+      if (group_of(i) != g0) continue;
+      for (uint32_t e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+        const uint32_t d = col[e];
+        if ((sel[d >> 5] >> (d & 31u)) & 1u) {
+          atomicOr(&sel[i >> 5], 1u << (i & 31u));
+          changed = true;
+          break;
+        }
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(FULL, changed)) break;
+  }
+  for (uint32_t w = lane; w < W; w += 32) out[w] = sel[w];
+}
+
+cudaError_t launch_closure(const Slot* slots, const uint32_t* slot_ids, const uint32_t* starts, uint32_t n, uint32_t n_slots,
+                           uint32_t words_out, uint32_t* masks, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  closure_kernel<<<(n + VAL_WARPS - 1) / VAL_WARPS, VAL_WARPS * 32, 0, stream>>>(slots, slot_ids, starts, n, n_slots, words_out, masks);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_validate(const Slot* slots, const uint32_t* slot_ids, uint32_t n, uint32_t n_slots, uint32_t* status,
                             cudaStream_t stream) {
   if (n == 0) return cudaSuccess;

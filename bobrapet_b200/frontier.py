@@ -150,6 +150,19 @@ class Frontier:
         return result, cdict
 
 
+
+    # -- redrive closure (row f3; storyrun_controller.go:535-558)
+    def closure(self, slots, steps, words: int) -> np.ndarray:
+        """bf_topology_closure: [count, words] uint32 masks of the steps a redrive from (slot, step) resets."""
+        sl = np.ascontiguousarray(slots, dtype=np.uint32)
+        st = np.ascontiguousarray(steps, dtype=np.uint32)
+        assert sl.shape == st.shape
+        out = np.zeros((sl.size, words), dtype=np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        self._check(self._lib.bf_topology_closure(self._ctx, sl.ctypes.data_as(u32p), st.ctypes.data_as(u32p), sl.size, words,
+                                                  out.ctypes.data_as(u32p)), "bf_topology_closure")
+        return out
+
     # -- limiters over the ready sets of the batch just evaluated (rows a9 / f4; dag.go:1780-1961)
     def schedule(self, L: A.Layout, n_runs: int, sched_runs: np.ndarray, story_limit, queue_limit, queue_aging_s,
                  global_limit: int = 0, story_running_base=None, queue_running_base=None, global_running_base: int = 0):

@@ -126,3 +126,85 @@ func (c *Ctx) Eval(b *Batch, flags uint32) (C.bf_counts, error) {
 	}
 	return counts, c.err(C.bf_eval(c.p, &cb))
 }
+
+// SchedTables are the limits and the running-StepRun counts the batch does not hold (dag.go:1780-1961).
+type SchedTables struct {
+	StoryLimit       []int32  // Story.spec.policy.concurrency per story key
+	StoryRunningBase []uint32 // nil = zeros
+	QueueLimit       []int32  // scheduling.queues[q].concurrency per queue key
+	QueueAgingS      []int32  // scheduling.queues[q].priorityAgingSeconds
+	QueueRunningBase []uint32 // nil = zeros
+	GlobalLimit      int32    // scheduling.globalConcurrency
+	GlobalBase       uint32
+}
+
+// SchedResult holds the schedule records (BF_SCHED_STRIDE(words) bytes per run: bf_sched_header, launch,
+// queued_story, queued_sched masks) and the totals the "(%d running, limit %d)" messages are formatted from.
+type SchedResult struct {
+	Records       []byte
+	StoryRunning  []uint32
+	QueueRunning  []uint32
+	QueueMaxPrio  []int32
+	GlobalRunning uint32
+}
+
+// Schedule applies enforceStoryConcurrency / enforceSchedulingLimits to the ready sets of the batch Eval just
+// evaluated: it replaces the three cluster-wide LISTs per reconcile (dag.go:1863-1920) by one reduction per tick.
+func (c *Ctx) Schedule(b *Batch, runs []C.bf_sched_run, t *SchedTables) (*SchedResult, error) {
+	words := uint32(b.Layout.words)
+	stride := (16 + 12*words + 15) &^ 15
+	res := &SchedResult{
+		Records:      make([]byte, int(b.N)*int(stride)),
+		StoryRunning: make([]uint32, len(t.StoryLimit)),
+		QueueRunning: make([]uint32, len(t.QueueLimit)),
+		QueueMaxPrio: make([]int32, len(t.QueueLimit)),
+	}
+	ct := C.bf_sched_tables{
+		struct_size:         C.uint32_t(unsafe.Sizeof(C.bf_sched_tables{})),
+		n_stories:           C.uint32_t(len(t.StoryLimit)),
+		n_queues:            C.uint32_t(len(t.QueueLimit)),
+		global_limit:        C.int32_t(t.GlobalLimit),
+		global_running_base: C.uint32_t(t.GlobalBase),
+	}
+	if len(t.StoryLimit) > 0 {
+		ct.story_limit = (*C.int32_t)(unsafe.Pointer(&t.StoryLimit[0]))
+	}
+	if len(t.StoryRunningBase) > 0 {
+		ct.story_running_base = (*C.uint32_t)(unsafe.Pointer(&t.StoryRunningBase[0]))
+	}
+	if len(t.QueueLimit) > 0 {
+		ct.queue_limit = (*C.int32_t)(unsafe.Pointer(&t.QueueLimit[0]))
+		ct.queue_aging_s = (*C.int32_t)(unsafe.Pointer(&t.QueueAgingS[0]))
+	}
+	if len(t.QueueRunningBase) > 0 {
+		ct.queue_running_base = (*C.uint32_t)(unsafe.Pointer(&t.QueueRunningBase[0]))
+	}
+	out := C.bf_sched_out{struct_size: C.uint32_t(unsafe.Sizeof(C.bf_sched_out{})), global_running: (*C.uint32_t)(unsafe.Pointer(&res.GlobalRunning))}
+	if len(res.Records) > 0 {
+		out.records = unsafe.Pointer(&res.Records[0])
+	}
+	if len(res.StoryRunning) > 0 {
+		out.story_running = (*C.uint32_t)(unsafe.Pointer(&res.StoryRunning[0]))
+	}
+	if len(res.QueueRunning) > 0 {
+		out.queue_running = (*C.uint32_t)(unsafe.Pointer(&res.QueueRunning[0]))
+		out.queue_max_priority = (*C.int32_t)(unsafe.Pointer(&res.QueueMaxPrio[0]))
+	}
+	cb := C.bf_batch{struct_size: C.uint32_t(unsafe.Sizeof(C.bf_batch{})), n_runs: C.uint32_t(b.N), layout: b.Layout}
+	var rp *C.bf_sched_run
+	if len(runs) > 0 {
+		rp = &runs[0]
+	}
+	return res, c.err(C.bf_schedule(c.p, &cb, rp, &ct, &out))
+}
+
+// RedriveClosure returns, for each (slot, step), the bit mask of the steps a redrive from that step resets
+// (resolveRedriveFromStepSet, storyrun_controller.go:535-558).
+func (c *Ctx) RedriveClosure(slots, steps []uint32, words uint32) ([]uint32, error) {
+	masks := make([]uint32, len(slots)*int(words))
+	if len(slots) == 0 {
+		return masks, nil
+	}
+	return masks, c.err(C.bf_topology_closure(c.p, (*C.uint32_t)(unsafe.Pointer(&slots[0])), (*C.uint32_t)(unsafe.Pointer(&steps[0])),
+		C.uint32_t(len(slots)), C.uint32_t(words), (*C.uint32_t)(unsafe.Pointer(&masks[0]))))
+}

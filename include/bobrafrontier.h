@@ -284,6 +284,14 @@ int bf_topology_put_many_checked_on_device(bf_ctx* ctx, const bf_topology* topos
                                            uint32_t* status_out);
 /* Re-validate already uploaded topologies on the device (status words as above; 0xFFFFFFFF = unknown slot). */
 int bf_topology_check(bf_ctx* ctx, const uint32_t* slots, uint32_t count, uint32_t* status_out);
+
+/* Redrive closure (row f3): for each query (topology slot, step index) the set of steps a redrive from that step
+ * resets — the step plus everything downstream of it inside its own group (resolveRedriveFromStepSet,
+ * internal/controller/runs/storyrun_controller.go:535-558; findStepGroup :560-577).  masks_out[q][words], same bit
+ * order as the ready masks.  BF_EINVAL for a step index >= S ("step %q not found", :541).  Host buffers, synchronous. */
+int bf_topology_closure(bf_ctx* ctx, const uint32_t* slots, const uint32_t* steps, uint32_t count, uint32_t words,
+                        uint32_t* masks_out);
+
 int bf_topology_drop(bf_ctx* ctx, uint32_t slot);
 /* Nibble offset of parallel desc p's children inside the child area.          */
 int bf_topology_child_first(const bf_ctx* ctx, uint32_t slot, uint32_t* child_first_out, uint32_t cap);

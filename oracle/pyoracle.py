@@ -1071,3 +1071,32 @@ def run_dag_iterations(srun: StoryRun, story: Story, step_runs: Optional[List[St
         if device_contract and any(by_name[n].type == "stop" and not by_name[n].ref for n in last.ready.ready):
             break
     return iters, launched, skipped, expansion, last
+
+
+# --------------------------------------------------------------------------
+# internal/controller/runs/storyrun_controller.go:535-577 — redrive closure
+# --------------------------------------------------------------------------
+def find_step_group(story: Story, step_name: str) -> Optional[List[Step]]:
+    """findStepGroup, storyrun_controller.go:560-577."""
+    for group in (story.steps, story.compensations, story.finally_):
+        if any(s.name == step_name for s in group):
+            return group
+    return None
+
+
+def resolve_redrive_from_step_set(story: Story, step_name: str) -> Dict[str, bool]:
+    """resolveRedriveFromStepSet, storyrun_controller.go:535-558: BFS over the dependents map of the step's own group."""
+    steps = find_step_group(story, step_name)
+    if steps is None:
+        raise KeyError("step %r not found in story" % step_name)
+    _, dependents = build_dependency_graphs(steps)
+    selected = {step_name: True}
+    queue = [step_name]
+    while queue:
+        current = queue.pop(0)
+        for dep in dependents.get(current, {}):
+            if selected.get(dep):
+                continue
+            selected[dep] = True
+            queue.append(dep)
+    return selected
