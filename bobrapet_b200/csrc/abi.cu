@@ -477,7 +477,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
         if (q && env_q && (uint32_t)atoi(env_q) != wq) continue;
         const uint32_t R = q ? 32u / wq : 1u;
         P.wq = wq; P.wq_log2 = lgq;
-        P.work_bytes = q ? 1168u : work_general;
+        P.work_bytes = q ? 1424u : work_general;
         for (uint32_t st = 1; st <= 4; ++st) {
           if (env_st && (uint32_t)atoi(env_st) != st) continue;
           for (uint32_t wpb = 16; wpb >= 1; wpb = (wpb > 4 ? wpb - 4 : wpb - 1)) {
@@ -507,7 +507,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   }
   quad = c->plan_wq != 0;
   P.wq = quad ? c->plan_wq : 32u; P.wq_log2 = quad ? c->plan_lg : 5u;
-  P.work_bytes = quad ? 1168u : work_general;
+  P.work_bytes = quad ? 1424u : work_general;
   const uint32_t R = quad ? 32u / P.wq : 1u;
   const uint32_t stage_total = R * P.stage_bytes;
   const bool two_tier = quad && c->n_with_parallel != 0;

@@ -12,6 +12,10 @@
 // per lane over a CSR row) is inherently per run and visits the candidate words of all R
 // runs one after another.
 //
+// Shared memory is addressed through 32-bit shared-window addresses throughout (ld.shared / st.shared, no generic
+// pointers); the walk reads a 16-byte per-group entry {col_idx base, row_ptr base, status base, max_deg} written by
+// the group's first lane, so an item (run, word) costs one extra ld.shared over the one-run-per-warp walk.
+//
 // Used for single-pass evaluation of batches whose topologies have no `parallel` steps;
 // the general kernel (frontier_kernel.cu) covers fixpoint mode and parallel joins.
 // Semantics are identical (same stages, same citations); parity tests run both.
@@ -80,14 +84,54 @@ DI void walk_quad(uint32_t lane, uint32_t CAND, uint32_t wq_log2, uint32_t col_o
   }
 }
 
+// Lean walk over the (run, word) items of a trip: one step per lane, first four deps branch-free and clamp-free
+// (col_idx carries zero padding, device_record.h).  tab_a: per-group entries {col_a, rp_a, st_a, max_deg}.
+template <bool NEED_FD, bool LONG_ROWS>
+DI void walk_items(uint32_t lane, uint32_t CAND, uint32_t lg, uint32_t tab_a, uint32_t& met_w, uint32_t& fd_w) {
+  met_w = 0;
+  fd_w = 0;
+  const uint32_t wmask = (1u << lg) - 1u;
+  const uint32_t lane2 = lane * 2u;
+  uint32_t todo = __ballot_sync(FULL, CAND != 0);  // (run, word) pairs with at least one candidate step
+  while (todo) {
+    const uint32_t L = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t candw = __shfl_sync(FULL, CAND, L);
+    const uint4 t = lds_v4(tab_a + (L >> lg) * 16u);  // col_a, rp_a, st_a, max_deg of the item's run
+    const bool cand = (candw >> lane) & 1u;
+    uint32_t e0 = 0, n = 0;
+    if (cand) {
+      const uint32_t a = t.y + (L & wmask) * 64u + lane2;
+      e0 = lds_u16(a);
+      n = lds_u16(a + 2u) - e0;
+    }
+    const uint32_t cpa = t.x + e0 * 2u;
+    uint32_t x0, x1, x2, x3;
+    asm volatile("ld.shared.u16 %0, [%4];\n\tld.shared.u16 %1, [%4+2];\n\tld.shared.u16 %2, [%4+4];\n\tld.shared.u16 %3, [%4+6];"
+                 : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(cpa));  // may run past the row: valid indices, masked below
+    const uint32_t s0 = lds_u8(t.z + x0), s1 = lds_u8(t.z + x1), s2 = lds_u8(t.z + x2), s3 = lds_u8(t.z + x3);
+    uint32_t w = ((s3 * 256u + s2) * 256u + s1) * 256u + s0;
+    w &= bmsk_clamp(0u, n * 8u);
+    if (LONG_ROWS) {
+      for (uint32_t e = 4; e < n; ++e) w |= lds_u8(t.z + lds_u16(cpa + e * 2u));
+    }
+    const uint32_t metb = __ballot_sync(FULL, cand && (w & 0x01010101u) == 0);
+    if (NEED_FD) {
+      const uint32_t fdb = __ballot_sync(FULL, (w & 0x02020202u) != 0);
+      if (lane == L) fd_w = fdb;
+    }
+    if (lane == L) met_w = metb;
+  }
+}
+
 // CD: cond and/or decision codes present   XO: any of fail/needs_cond/skip_dep/phase_out requested
 template <bool CD, bool XO>
 __global__ void __launch_bounds__(512) frontier_quad_kernel(const KParams P) {
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lane = pin(threadIdx.x & 31u);  // pinned: otherwise rematerialised from S2R inside the loop
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t ST = P.stages;
   const uint32_t Wq = P.wq, lg = P.wq_log2, R = 32u >> lg;
-  const uint32_t g = lane >> lg, w = lane & (Wq - 1u);
+  const uint32_t g = pin(lane >> lg), w = pin(lane & (Wq - 1u));
   const uint32_t gmask = (Wq == 32u ? FULL : ((1u << Wq) - 1u)) << (g << lg);
 
   // ---- shared memory carve-up: [block counters 128 B][warp regions] ----
@@ -96,13 +140,16 @@ __global__ void __launch_bounds__(512) frontier_quad_kernel(const KParams P) {
   const uint32_t stage_bytes = R * run_bytes;
   const uint32_t ring_bytes = ST * stage_bytes;
   const uint32_t per_warp = ring_bytes + P.work_bytes + 64;
-  const uint32_t wbase_off = pin(128 + warp * per_warp);
+  const uint32_t wbase_off = 128 + warp * per_warp;
   uint8_t* const wbase = smem_q + wbase_off;
-  const uint32_t bars = smem_u32(wbase + ring_bytes + P.work_bytes);
-  const uint32_t ring = smem_u32(wbase);
-  const uint32_t smem_base = pin(smem_u32(smem_q));
-  uint32_t* const mFAIL = reinterpret_cast<uint32_t*>(wbase + ring_bytes);  // [32]
-  const uint32_t st0_off = wbase_off + ring_bytes + 128;                   // status bytes [1024 + 16]
+  const uint32_t smem_base = smem_u32(smem_q);
+  const uint32_t ring = pin(smem_base + wbase_off);                         // shared-window address of the warp's ring
+  const uint32_t bars = ring + ring_bytes + P.work_bytes;                   // mbarriers: behind the scratch, away from the TMA destinations
+  // scratch: [fix-up fail words 128 B][status bytes 1024 + 16][per-group walk entries 16 x 16 B]
+  uint32_t* const mFAIL = reinterpret_cast<uint32_t*>(wbase + ring_bytes);  // [32] (fix-up path only)
+  const uint32_t st0_off = wbase_off + ring_bytes + 128;
+  const uint32_t st0_a = ring + ring_bytes + 128u;
+  const uint32_t tab_a = st0_a + 1040u;
 
   if (threadIdx.x < 4) blk_counts[threadIdx.x] = 0ull;
   if (lane == 0) {
@@ -186,23 +233,24 @@ __global__ void __launch_bounds__(512) frontier_quad_kernel(const KParams P) {
   for (uint32_t k = 0; k < my_trips; ++k, r += G * R, rr += trip_result_step) {
     mbar_wait(bars + 8 * cs, cpar);
     const uint32_t stage_off = wbase_off + cs * stage_bytes;
-    const uint8_t* sr = smem_q + stage_off + g * P.state_stride;
     const uint32_t tr0_off = stage_off + R * P.state_stride;
-    const uint8_t* tr = smem_q + tr0_off + g * P.topo_buf_bytes;
+    const uint32_t stage_a = ring + cs * stage_bytes;
+    const uint32_t sr_a = stage_a + g * P.state_stride;                                 // my run's state record
+    const uint32_t tr_a = stage_a + R * P.state_stride + g * P.topo_buf_bytes;          // my run's topology record
     const bool staged = (__shfl_sync(FULL, ok_bits, g) >> cs) & 1u;
     const bool deferred = (__shfl_sync(FULL, defer_bits, g) >> cs) & 1u;
     cs = (cs + 1 == ST) ? 0 : cs + 1;
     cpar ^= (cs == 0);
 
     const bool in_batch = r < N;
-    const uint4 h0 = *reinterpret_cast<const uint4*>(tr);
-    const uint4 h1 = *reinterpret_cast<const uint4*>(tr + 16);
+    const uint4 h0 = lds_v4(tr_a);
+    const uint4 h1 = lds_v4(tr_a + 16);
     uint32_t S = h0.x & 0xFFFFu, Wt = h0.x >> 16;
     const uint32_t max_deg = h0.y & 0xFFFFu;
     uint32_t n_main = h0.z & 0xFFFFu, n_comp = h0.z >> 16, n_final = h0.w & 0xFFFFu;
     const bool live = in_batch && staged && Wt <= Wmax;  // group-uniform
     if (!live) { S = 0; Wt = 0; n_main = n_comp = n_final = 0; }
-    const uint32_t rflags = live ? sr[4] : (uint32_t)BF_RF_HOST_GROUP | (BF_GROUP_DONE << BF_RF_HOST_GROUP_SHIFT);
+    const uint32_t rflags = live ? lds_u8(sr_a + 4) : (uint32_t)BF_RF_HOST_GROUP | (BF_GROUP_DONE << BF_RF_HOST_GROUP_SHIFT);
 
     // ---------------- planes of my word ----------------
     const bool act = w < Wt;
@@ -210,22 +258,21 @@ __global__ void __launch_bounds__(512) frontier_quad_kernel(const KParams P) {
     uint32_t c0 = 0, c1 = 0, d0 = 0, d1 = 0;
     uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     if (act) {
-      const uint32_t* sp = reinterpret_cast<const uint32_t*>(tr + h1.y) + w;
-      AF = sp[PL_AF * Wt];
-      G1 = sp[PL_G1 * Wt]; G2 = sp[PL_G2 * Wt];
-      if (XO) HASIF = sp[PL_HASIF * Wt];
-      const uint32_t rem = S - w * 32;
-      VALID = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
-      const uint32_t* pw = reinterpret_cast<const uint32_t*>(sr + P.off_phase) + w;
-      p0 = pw[0]; p1 = pw[Wmax]; p2 = pw[2 * Wmax]; p3 = pw[3 * Wmax];
+      const uint32_t sp = tr_a + h1.y + w * 4u, ps = Wt * 4u;   // static planes: my word, plane stride
+      AF = lds_u32(sp + PL_AF * ps);
+      G1 = lds_u32(sp + PL_G1 * ps); G2 = lds_u32(sp + PL_G2 * ps);
+      if (XO) HASIF = lds_u32(sp + PL_HASIF * ps);
+      VALID = bmsk_clamp(0u, S - w * 32u);
+      const uint32_t pw = sr_a + P.off_phase + w * 4u, ds = Wmax * 4u;  // dynamic planes: stride of the layout
+      p0 = lds_u32(pw); p1 = lds_u32(pw + ds); p2 = lds_u32(pw + 2u * ds); p3 = lds_u32(pw + 3u * ds);
       const uint32_t keep = VALID & ~(p0 & p1 & p2 & p3);  // steps >= S and the reserved code 15 read as 0
       p0 &= keep; p1 &= keep; p2 &= keep; p3 &= keep;
       if (CD) {
-        if (has_cond) { const uint32_t* cw = reinterpret_cast<const uint32_t*>(sr + P.off_cond) + w; c0 = cw[0]; c1 = cw[Wmax]; }
+        if (has_cond) { const uint32_t cw = sr_a + P.off_cond + w * 4u; c0 = lds_u32(cw); c1 = lds_u32(cw + ds); }
         if (has_dec) {
-          const uint32_t* dw = reinterpret_cast<const uint32_t*>(sr + P.off_decision) + w; d0 = dw[0]; d1 = dw[Wmax];
-          const uint32_t t0 = sp[PL_T0 * Wt], t1 = sp[PL_T1 * Wt], t2 = sp[PL_T2 * Wt];
-          TS = sp[PL_TS * Wt];
+          const uint32_t dw = sr_a + P.off_decision + w * 4u; d0 = lds_u32(dw); d1 = lds_u32(dw + ds);
+          const uint32_t t0 = lds_u32(sp + PL_T0 * ps), t1 = lds_u32(sp + PL_T1 * ps), t2 = lds_u32(sp + PL_T2 * ps);
+          TS = lds_u32(sp + PL_TS * ps);
           SYNC_T = t0 & (t1 | t2);  // sleep(3) | wait(5) | gate(7)
         }
       }
@@ -329,25 +376,37 @@ __global__ void __launch_bounds__(512) frontier_quad_kernel(const KParams P) {
     const uint32_t FD = skip_on_failed ? (TERM & ~SAT) : 0u;
     const uint32_t CAND = evaluate ? (GSEL & ~COMPL & ~RUNQ & ~TERM) : 0u;
     // ------------- stage C: one status byte per step (bit0 unmet, bit1 failed-dep), all R runs -------------
+    const bool any_fd = __any_sync(FULL, skip_on_failed);              // some run of the trip has a failed-dependency class
+    const bool any_long = __any_sync(FULL, live && max_deg > 4);       // some run has rows longer than the straight-line four
     __syncwarp();
 #pragma unroll
     for (uint32_t t = 0; t < 4; ++t) {
       const uint32_t item = t * 32 + lane;  // 8 steps: byte (item & 3) of the word held by lane item >> 2
       const uint32_t sh = (item & 3u) * 8u;
       const uint32_t ub = __shfl_sync(FULL, U, item >> 2) >> sh;
-      const uint32_t fb = __shfl_sync(FULL, FD, item >> 2) >> sh;
-      uint2 v;
-      v.x = bits4_to_bytes(ub & 0xFu) | (bits4_to_bytes(fb & 0xFu) << 1);
-      v.y = bits4_to_bytes((ub >> 4) & 0xFu) | (bits4_to_bytes((fb >> 4) & 0xFu) << 1);
-      reinterpret_cast<uint2*>(smem_q + st0_off)[item] = v;
+      uint32_t vx = bits4_to_bytes(ub & 0xFu), vy = bits4_to_bytes((ub >> 4) & 0xFu);
+      if (any_fd) {  // warp-uniform
+        const uint32_t fb = __shfl_sync(FULL, FD, item >> 2) >> sh;
+        vx |= bits4_to_bytes(fb & 0xFu) << 1;
+        vy |= bits4_to_bytes((fb >> 4) & 0xFu) << 1;
+      }
+      sts_v2(st0_a + item * 8u, vx, vy);
     }
+    // per-group walk entry: CSR bases, status base, longest row
+    const uint32_t col_a = tr_a + h1.x;
+    if (w == 0) sts_v4(tab_a + g * 16u, col_a, tr_a + (uint32_t)sizeof(TopoHeader), st0_a + (g << (5u + lg)), max_deg);
     __syncwarp();
     // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
-    const uint32_t col_off = tr0_off + g * P.topo_buf_bytes + h1.x;
+    const uint32_t col_off = col_a - smem_base;             // fix-up path (generic pointers)
     const uint32_t meta = (32u * Wt) | (max_deg << 16);
     uint32_t met_w, fd_w;
-    walk_deps2(lane, CAND, lg, smem_base + col_off, meta, smem_base + tr0_off + (uint32_t)sizeof(TopoHeader), P.topo_buf_bytes,
-               smem_base + st0_off, met_w, fd_w);
+    if (any_long) {
+      if (any_fd) walk_items<true, true>(lane, CAND, lg, tab_a, met_w, fd_w);
+      else walk_items<false, true>(lane, CAND, lg, tab_a, met_w, fd_w);
+    } else {
+      if (any_fd) walk_items<true, false>(lane, CAND, lg, tab_a, met_w, fd_w);
+      else walk_items<false, false>(lane, CAND, lg, tab_a, met_w, fd_w);
+    }
     uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
     if (CD) {
       ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
