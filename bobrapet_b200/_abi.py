@@ -21,6 +21,8 @@ PHASE_SCHEDULING, PHASE_TIMEOUT, PHASE_ABORTED, PHASE_SKIPPED, PHASE_PENDING_QUE
 PHASE_NAMES = ["", "Pending", "Running", "Succeeded", "Failed", "Finished", "Canceled", "Compensated",
                "Paused", "Blocked", "Scheduling", "Timeout", "Aborted", "Skipped", "Pending"]
 
+QUEUED_NONE, QUEUED_PRIORITY, QUEUED_GLOBAL, QUEUED_QUEUE, QUEUED_OTHER = range(5)  # BF_QUEUED_*
+SCHED_NONE = 0xFFFFFFFF
 STEP_ENGRAM, STEP_CONDITION, STEP_PARALLEL, STEP_SLEEP, STEP_STOP, STEP_WAIT, STEP_EXECUTE_STORY, STEP_GATE = range(8)
 STEP_TYPE_CODE = {"": STEP_ENGRAM, "condition": STEP_CONDITION, "parallel": STEP_PARALLEL, "sleep": STEP_SLEEP,
                   "stop": STEP_STOP, "wait": STEP_WAIT, "executeStory": STEP_EXECUTE_STORY, "gate": STEP_GATE}

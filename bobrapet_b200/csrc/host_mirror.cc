@@ -521,3 +521,199 @@ int bfh_run_skip_reason(const bfh_batch* b, uint32_t run, uint32_t step, char* o
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ limiters (rows a9 / f4)
+namespace {
+std::string normalize_queue(const char* name) {  // scheduling.go:21-27: TrimSpace + ToLower
+  std::string q = name ? name : "";
+  size_t a = 0, b = q.size();
+  while (a < b && is_space(q[a])) ++a;
+  while (b > a && is_space(q[b - 1])) --b;
+  q = q.substr(a, b - a);
+  for (char& c : q) if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+  return q;
+}
+int phase_code_plain(const char* phase) { return phase_code_of(phase ? phase : "", ""); }
+}  // namespace
+
+struct bfh_sched {
+  bfh_batch* batch = nullptr;
+  std::string err;
+  int32_t global_limit = 0;
+  uint32_t global_base = 0;
+  std::vector<std::string> queue_names;
+  std::unordered_map<std::string, uint32_t> queue_key;
+  std::vector<int32_t> queue_limit, queue_default_prio, queue_aging;
+  std::vector<uint32_t> queue_base;
+  std::unordered_map<std::string, uint32_t> story_key;   // "namespace/name"
+  std::vector<int32_t> story_limit;
+  std::vector<uint32_t> story_base;
+  std::vector<bf_sched_run> runs;
+  // results
+  std::vector<uint8_t> records;
+  std::vector<uint32_t> story_running, queue_running;
+  std::vector<int32_t> queue_maxprio;
+  uint32_t global_running = 0;
+  bool applied = false;
+
+  uint32_t queue_of(const std::string& normalized) {  // "" -> default (queueLabelValue, scheduling.go:29-35)
+    const std::string n = normalized.empty() ? "default" : normalized;
+    auto it = queue_key.find(n);
+    if (it != queue_key.end()) return it->second;
+    const uint32_t k = (uint32_t)queue_names.size();
+    queue_key[n] = k;
+    queue_names.push_back(n);
+    queue_limit.push_back(0); queue_default_prio.push_back(0); queue_aging.push_back(0); queue_base.push_back(0);
+    return k;
+  }
+  uint32_t story_of(const char* ns, const char* name) {
+    const std::string k = std::string(ns ? ns : "") + "/" + (name ? name : "");
+    auto it = story_key.find(k);
+    if (it != story_key.end()) return it->second;
+    const uint32_t id = (uint32_t)story_limit.size();
+    story_key[k] = id;
+    story_limit.push_back(0); story_base.push_back(0);
+    return id;
+  }
+};
+
+extern "C" {
+
+bfh_sched* bfh_sched_new(bfh_batch* batch) {
+  if (!batch) return nullptr;
+  bfh_sched* s = new (std::nothrow) bfh_sched();
+  if (!s) return nullptr;
+  s->batch = batch;
+  // the default scheduling config: queue "default" ages every 60 s (internal/config/controller_config.go:731-739)
+  const uint32_t k = s->queue_of("default");
+  s->queue_aging[k] = 60;
+  return s;
+}
+void bfh_sched_free(bfh_sched* s) { delete s; }
+const char* bfh_sched_error(const bfh_sched* s) { return s ? s->err.c_str() : "null sched"; }
+
+int bfh_sched_set_global(bfh_sched* s, int32_t limit, uint32_t base) {
+  if (!s) return BF_EINVAL;
+  s->global_limit = limit; s->global_base = base;
+  return BF_OK;
+}
+int bfh_sched_set_queue(bfh_sched* s, const char* name, int32_t concurrency, int32_t default_priority, int32_t aging, uint32_t base) {
+  if (!s) return BF_EINVAL;
+  const uint32_t k = s->queue_of(normalize_queue(name));
+  s->queue_limit[k] = concurrency; s->queue_default_prio[k] = default_priority; s->queue_aging[k] = aging; s->queue_base[k] = base;
+  return (int)k;
+}
+int bfh_sched_set_story_base(bfh_sched* s, const char* ns, const char* name, uint32_t base) {
+  if (!s) return BF_EINVAL;
+  const uint32_t k = s->story_of(ns, name);
+  s->story_base[k] = base;
+  return (int)k;
+}
+int bfh_sched_set_run(bfh_sched* s, uint32_t run, const char* ns, const char* name, int32_t story_concurrency, const char* policy_queue,
+                      int has_priority, int32_t policy_priority, const char* run_phase, int64_t queued_since_ns, int64_t now_ns) {
+  if (!s || run >= s->batch->n) { if (s) s->err = "run index out of range"; return BF_EINVAL; }
+  if (s->runs.size() < s->batch->n) s->runs.resize(s->batch->n);
+  // resolveSchedulingDecision, scheduling.go:130-163 (no fallback decision on this path: dag.go:1805 passes nil)
+  const std::string sq = normalize_queue(policy_queue);
+  const uint32_t qk = s->queue_of(sq);
+  int32_t prio;
+  if (has_priority) prio = policy_priority;
+  else prio = s->queue_default_prio[qk];  // both remaining cases read queueDefaultPriority of the decided queue
+  const uint32_t sk = s->story_of(ns, name);
+  s->story_limit[sk] = story_concurrency > 0 ? story_concurrency : 0;  // storyConcurrencyLimit, dag.go:1863-1868
+  bf_sched_run& r = s->runs[run];
+  memset(&r, 0, sizeof r);
+  r.story_key = sk; r.queue_key = qk; r.priority = prio;
+  r.run_phase = (uint32_t)phase_code_plain(run_phase);
+  if (queued_since_ns < 0) r.queued_elapsed_s = BF_SCHED_NONE;
+  else {
+    const int64_t el_ns = now_ns - queued_since_ns;  // elapsed <= 0 -> base priority (dag.go:1952-1955)
+    const int64_t el = el_ns <= 0 ? 0 : el_ns / 1000000000ll;  // int32(elapsed.Seconds())
+    r.queued_elapsed_s = el > 0x7FFFFFFF ? 0x7FFFFFFFu : (uint32_t)el;
+  }
+  s->applied = false;
+  return BF_OK;
+}
+const bf_sched_run* bfh_sched_runs(const bfh_sched* s) { return s && !s->runs.empty() ? s->runs.data() : nullptr; }
+int bfh_sched_tables(const bfh_sched* s, bf_sched_tables* t) {
+  if (!s || !t) return BF_EINVAL;
+  memset(t, 0, sizeof *t);
+  t->struct_size = sizeof *t;
+  t->n_stories = (uint32_t)s->story_limit.size(); t->n_queues = (uint32_t)s->queue_limit.size();
+  t->global_limit = s->global_limit; t->global_running_base = s->global_base;
+  t->story_limit = s->story_limit.data(); t->story_running_base = s->story_base.data();
+  t->queue_limit = s->queue_limit.data(); t->queue_aging_s = s->queue_aging.data(); t->queue_running_base = s->queue_base.data();
+  return BF_OK;
+}
+const char* bfh_sched_queue_name(const bfh_sched* s, uint32_t k) { return s && k < s->queue_names.size() ? s->queue_names[k].c_str() : ""; }
+
+int bfh_sched_apply(bfh_sched* s) {
+  if (!s) return BF_EINVAL;
+  bfh_batch* b = s->batch;
+  if (!b->ctx) { s->err = "batch was created without a device context"; return BF_ENODEV; }
+  if (s->runs.size() != b->n) { s->err = "bfh_sched_set_run was not called for every run of the batch"; return BF_EINVAL; }
+  bf_sched_tables t;
+  bfh_sched_tables(s, &t);
+  const uint32_t stride = BF_SCHED_STRIDE(b->L.words);
+  s->records.assign((size_t)b->n * stride, 0);
+  s->story_running.assign(t.n_stories, 0); s->queue_running.assign(t.n_queues, 0); s->queue_maxprio.assign(t.n_queues, 0);
+  bf_sched_out out{};
+  out.struct_size = sizeof out;
+  out.records = s->records.data();
+  out.story_running = s->story_running.data(); out.queue_running = s->queue_running.data();
+  out.queue_max_priority = s->queue_maxprio.data(); out.global_running = &s->global_running;
+  bf_batch bb{};
+  bb.struct_size = sizeof(bf_batch);
+  bb.n_runs = b->n; bb.layout = b->L;
+  const int rc = bf_schedule(b->ctx, &bb, s->runs.data(), &t, &out);
+  if (rc != BF_OK) { s->err = bf_last_error(b->ctx); return rc; }
+  s->applied = true;
+  return BF_OK;
+}
+
+int bfh_sched_steps(const bfh_sched* s, uint32_t run, int which, uint32_t* out, uint32_t cap) {
+  if (!s || !s->applied || run >= s->batch->n || which < 0 || which > 2) return BF_EINVAL;
+  const uint32_t W = s->batch->L.words, stride = BF_SCHED_STRIDE(W);
+  const uint32_t* m = reinterpret_cast<const uint32_t*>(s->records.data() + (size_t)run * stride + 16) + (size_t)which * W;
+  const uint32_t S = (uint32_t)s->batch->story_of_run[run]->flags.size();
+  int n = 0;
+  for (uint32_t i = 0; i < S; ++i)
+    if ((m[i >> 5] >> (i & 31u)) & 1u) {
+      if (out && (uint32_t)n < cap) out[n] = i;
+      ++n;
+    }
+  return n;
+}
+
+int bfh_sched_format_message(int reason, uint32_t running, int32_t limit, char* out, size_t cap) {
+  if (!out || !cap) return BF_EINVAL;
+  const char* prefix;
+  switch (reason) {
+    case 0: prefix = "Queued due to story concurrency limit"; break;        // dag.go:104, 1797
+    case BF_QUEUED_GLOBAL: prefix = "Queued due to global concurrency limit"; break;  // :106, 1850
+    case BF_QUEUED_QUEUE: prefix = "Queued due to queue concurrency limit"; break;    // :105, 1852
+    case BF_QUEUED_PRIORITY: snprintf(out, cap, "Queued due to higher-priority work"); return BF_OK;  // :107, 1944
+    case BF_QUEUED_OTHER: snprintf(out, cap, "Queued due to scheduling limits"); return BF_OK;        // :1854
+    default: out[0] = 0; return BF_OK;
+  }
+  snprintf(out, cap, "%s (%u running, limit %d)", prefix, running, limit);
+  return BF_OK;
+}
+
+int bfh_sched_message(const bfh_sched* s, uint32_t run, int which, char* out, size_t cap) {
+  if (!s || !s->applied || run >= s->batch->n || !out || !cap || (which != 1 && which != 2)) return BF_EINVAL;
+  const uint32_t stride = BF_SCHED_STRIDE(s->batch->L.words);
+  const bf_sched_header* h = reinterpret_cast<const bf_sched_header*>(s->records.data() + (size_t)run * stride);
+  const bf_sched_run& r = s->runs[run];
+  out[0] = 0;
+  if (which == 1) {
+    if (h->n_queued_story) return bfh_sched_format_message(0, s->story_running[r.story_key], s->story_limit[r.story_key], out, cap);
+    return BF_OK;
+  }
+  if (!h->n_queued_sched) return BF_OK;
+  if (h->sched_reason == BF_QUEUED_GLOBAL) return bfh_sched_format_message(BF_QUEUED_GLOBAL, s->global_running, s->global_limit, out, cap);
+  if (h->sched_reason == BF_QUEUED_QUEUE) return bfh_sched_format_message(BF_QUEUED_QUEUE, s->queue_running[r.queue_key], s->queue_limit[r.queue_key], out, cap);
+  return bfh_sched_format_message((int)h->sched_reason, 0, 0, out, cap);
+}
+
+}  // extern "C"

@@ -49,6 +49,21 @@ _SYMS = [
     ("bfh_run_needs_cond", C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]),
     ("bfh_run_phase_out", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     ("bfh_run_skip_reason", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]),
+    ("bfh_sched_new", C.c_void_p, [C.c_void_p]),
+    ("bfh_sched_free", None, [C.c_void_p]),
+    ("bfh_sched_error", C.c_char_p, [C.c_void_p]),
+    ("bfh_sched_set_global", C.c_int, [C.c_void_p, C.c_int32, C.c_uint32]),
+    ("bfh_sched_set_queue", C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32]),
+    ("bfh_sched_set_story_base", C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32]),
+    ("bfh_sched_set_run", C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int, C.c_int32,
+                                    C.c_char_p, C.c_int64, C.c_int64]),
+    ("bfh_sched_runs", C.c_void_p, [C.c_void_p]),
+    ("bfh_sched_tables", C.c_int, [C.c_void_p, C.POINTER(A.SchedTables)]),
+    ("bfh_sched_queue_name", C.c_char_p, [C.c_void_p, C.c_uint32]),
+    ("bfh_sched_apply", C.c_int, [C.c_void_p]),
+    ("bfh_sched_steps", C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32]),
+    ("bfh_sched_message", C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]),
+    ("bfh_sched_format_message", C.c_int, [C.c_int, C.c_uint32, C.c_int32, C.c_char_p, C.c_size_t]),
 ]
 HOST_SYMBOLS = [n for n, _, _ in _SYMS]
 _bound = False
@@ -179,6 +194,9 @@ class HostBatch:
     def set_phase(self, run, step, phase, message=""):
         self._chk(self._l.bfh_run_set_phase(self._p, run, step, _b(phase), _b(message)), "bfh_run_set_phase")
 
+    def set_phase_code(self, run, step, code):
+        self._chk(self._l.bfh_run_set_phase_code(self._p, run, step, code), "bfh_run_set_phase_code")
+
     def set_cond(self, run, step, code):
         self._chk(self._l.bfh_run_set_cond(self._p, run, step, code), "bfh_run_set_cond")
 
@@ -244,3 +262,89 @@ class HostBatch:
         buf = C.create_string_buffer(512)
         self._chk(self._l.bfh_run_skip_reason(self._p, run, step, buf, len(buf)), "bfh_run_skip_reason")
         return buf.value.decode()
+
+
+class HostSched:
+    """bfh_sched: host side of the limiters (rows a9 / f4) for one HostBatch — scheduling decisions, keys, elapsed
+    seconds in; launch / queued step lists and the reference's queue messages out."""
+
+    def __init__(self, batch: "HostBatch"):
+        self._l = lib()
+        self._batch = batch
+        self._p = C.c_void_p(self._l.bfh_sched_new(batch._p))
+        if not self._p:
+            raise RuntimeError("bfh_sched_new failed")
+
+    def close(self):
+        if self._p:
+            self._l.bfh_sched_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc < 0:
+            raise A.FrontierError(rc, "%s: %s" % (what, self._l.bfh_sched_error(self._p).decode()))
+        return rc
+
+    def set_global(self, limit: int, running_base: int = 0):
+        self._chk(self._l.bfh_sched_set_global(self._p, limit, running_base), "bfh_sched_set_global")
+
+    def set_queue(self, name, concurrency=0, default_priority=0, aging_s=0, running_base=0) -> int:
+        return self._chk(self._l.bfh_sched_set_queue(self._p, _b(name), concurrency, default_priority, aging_s, running_base),
+                         "bfh_sched_set_queue")
+
+    def set_story_base(self, namespace, name, running_base) -> int:
+        return self._chk(self._l.bfh_sched_set_story_base(self._p, _b(namespace), _b(name), running_base), "bfh_sched_set_story_base")
+
+    def set_run(self, run, namespace, story, story_concurrency=0, queue=None, priority=None, run_phase="", queued_since=None, now=0.0):
+        """queued_since / now: Unix seconds (float); passed to the library in nanoseconds"""
+        self._chk(self._l.bfh_sched_set_run(self._p, run, _b(namespace), _b(story), story_concurrency, _b(queue),
+                                            int(priority is not None), int(priority or 0), _b(run_phase),
+                                            -1 if queued_since is None else int(round(queued_since * 1e9)), int(round(now * 1e9))), "bfh_sched_set_run")
+
+    def packed(self):
+        """(runs [n] structured array copy, SchedTables with pointers into the C++ object, table arrays as numpy copies)"""
+        n = self._l.bfh_batch_size(self._batch._p)
+        dt = np.dtype([("story_key", "<u4"), ("queue_key", "<u4"), ("priority", "<i4"), ("queued_elapsed_s", "<u4"),
+                       ("run_phase", "<u4"), ("reserved", "<u4", (3,))])
+        ptr = self._l.bfh_sched_runs(self._p)
+        runs = np.frombuffer((C.c_uint8 * (32 * n)).from_address(ptr), dtype=dt).copy() if ptr and n else np.zeros(0, dt)
+        t = A.SchedTables()
+        self._chk(self._l.bfh_sched_tables(self._p, C.byref(t)), "bfh_sched_tables")
+
+        def arr(p, cnt, ctype, npdt):
+            return np.frombuffer((ctype * cnt).from_address(p), dtype=npdt).copy() if p and cnt else np.zeros(0, npdt)
+        tabs = {"story_limit": arr(t.story_limit, t.n_stories, C.c_int32, np.int32),
+                "story_base": arr(t.story_running_base, t.n_stories, C.c_uint32, np.uint32),
+                "queue_limit": arr(t.queue_limit, t.n_queues, C.c_int32, np.int32),
+                "queue_aging": arr(t.queue_aging_s, t.n_queues, C.c_int32, np.int32),
+                "queue_base": arr(t.queue_running_base, t.n_queues, C.c_uint32, np.uint32),
+                "global_limit": t.global_limit, "global_base": t.global_running_base}
+        return runs, tabs
+
+    def queue_name(self, key: int) -> str:
+        return self._l.bfh_sched_queue_name(self._p, key).decode()
+
+    def apply(self):
+        self._chk(self._l.bfh_sched_apply(self._p), "bfh_sched_apply")
+
+    def steps(self, run: int, which: int) -> List[int]:
+        buf = np.zeros(1024, np.uint32)
+        n = self._chk(self._l.bfh_sched_steps(self._p, run, which, buf.ctypes.data, 1024), "bfh_sched_steps")
+        return buf[:n].tolist()
+
+    def message(self, run: int, which: int) -> str:
+        buf = C.create_string_buffer(256)
+        self._chk(self._l.bfh_sched_message(self._p, run, which, buf, len(buf)), "bfh_sched_message")
+        return buf.value.decode()
+
+
+def format_queue_message(reason: int, running: int, limit: int) -> str:
+    buf = C.create_string_buffer(256)
+    lib().bfh_sched_format_message(reason, running, limit, buf, len(buf))
+    return buf.value.decode()

@@ -100,6 +100,46 @@ int bfh_run_phase_out(const bfh_batch* b, uint32_t run, uint32_t step); /* phase
 /* "Skipped due to failed dependency: <name>" names the first dep in CSR order that is failed. */
 int bfh_run_skip_reason(const bfh_batch* b, uint32_t run, uint32_t step, char* out, size_t cap);
 
+/* ------------------------------------------------------------------ limiters (rows a9 / f4)
+ * Host side of bf_schedule: what stays on the host in the batch contract of bobrafrontier.h —
+ *   resolveSchedulingDecision / queueLabelValue / normalizeQueueName   scheduling.go:21-35, 130-163
+ *   queueConfigForName (a queue without an entry = zero config)        scheduling.go:101-112
+ *   storyConcurrencyLimit                                              dag.go:1863-1868
+ *   storyRunQueuedSince -> elapsed seconds for effectivePriority       dag.go:1948-1979
+ *   the "Queued due to ... (%d running, limit %d)" messages            dag.go:103-108, 1797, 1849-1855
+ * Keys: a story key per (namespace, Story name) — countRunningStepRuns lists by namespace + story label,
+ * dag.go:1874-1877 — and a queue key per queue label.  One bf_sched_run per run of the batch.              */
+typedef struct bfh_sched bfh_sched;
+
+bfh_sched* bfh_sched_new(bfh_batch* batch);
+void bfh_sched_free(bfh_sched* s);
+const char* bfh_sched_error(const bfh_sched* s);
+/* scheduling.globalConcurrency + Running StepRuns the batch does not hold */
+int bfh_sched_set_global(bfh_sched* s, int32_t global_concurrency, uint32_t running_base);
+/* scheduling.queues[name]; returns the queue key.  Queues named by a Story but never configured read as zeros. */
+int bfh_sched_set_queue(bfh_sched* s, const char* name, int32_t concurrency, int32_t default_priority,
+                        int32_t priority_aging_seconds, uint32_t running_base);
+/* Running StepRuns of (namespace, story) held by StoryRuns outside the batch; returns the story key. */
+int bfh_sched_set_story_base(bfh_sched* s, const char* story_namespace, const char* story_name, uint32_t running_base);
+/* One run: its Story's policy (policy_queue NULL/"" = unset, has_priority 0 = unset, story_concurrency <= 0 = none),
+ * StoryRun.Status.Phase, and the earliest StartedAt among its queued steps (Unix nanoseconds; queued_since_ns < 0:
+ * none) against now_ns: the elapsed seconds are int32((now - since).Seconds()) as in effectivePriority, dag.go:1952-1956. */
+int bfh_sched_set_run(bfh_sched* s, uint32_t run, const char* story_namespace, const char* story_name, int32_t story_concurrency,
+                      const char* policy_queue, int has_priority, int32_t policy_priority, const char* run_phase,
+                      int64_t queued_since_ns, int64_t now_ns);
+/* the packed inputs (for inspection / CPU-side checks): bf_sched_run[size], tables valid until the next set_* call */
+const bf_sched_run* bfh_sched_runs(const bfh_sched* s);
+int bfh_sched_tables(const bfh_sched* s, bf_sched_tables* out);
+const char* bfh_sched_queue_name(const bfh_sched* s, uint32_t queue_key);
+/* bf_schedule over the batch's last bfh_batch_eval */
+int bfh_sched_apply(bfh_sched* s);
+/* results of the last apply: step lists in list order; which = 0 launch, 1 queued by the Story limit, 2 queued by scheduling */
+int bfh_sched_steps(const bfh_sched* s, uint32_t run, int which, uint32_t* steps_out, uint32_t cap);
+/* the reference's message text for which = 1 / 2 ("" when nothing was queued that way) */
+int bfh_sched_message(const bfh_sched* s, uint32_t run, int which, char* out, size_t cap);
+/* message text from a reason code and the totals (exposed for CPU-side tests) */
+int bfh_sched_format_message(int reason /* 0 = story limit, else BF_QUEUED_* */, uint32_t running, int32_t limit, char* out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,21 @@ def queue_config_for(cfg: SchedulingConfig, queue: str) -> QueueConfig:
     return cfg.queues.get(name, QueueConfig())
 
 
+def resolve_scheduling_decision(policy_queue: Optional[str], policy_priority: Optional[int], cfg: SchedulingConfig) -> Tuple[str, int]:
+    """resolveSchedulingDecision with a nil fallback (the call of dag.go:1805), scheduling.go:130-163."""
+    queue, priority = DEFAULT_QUEUE, 0
+    story_queue = normalize_queue_name(policy_queue) if policy_queue is not None else ""
+    if story_queue != "":
+        queue = story_queue
+    if policy_priority is not None:
+        priority = policy_priority
+    else:   # `storyQueue != ""` and the default case both read the decided queue's default priority
+        priority = queue_config_for(cfg, queue).default_priority
+    if queue.strip() == "":
+        queue = DEFAULT_QUEUE
+    return queue, priority
+
+
 def priority_from_labels(label: Optional[str]) -> int:
     """scheduling.go:165-178."""
     if label is None:
