@@ -344,6 +344,38 @@ def main():
         e2e = {"value": evals_per_pass * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": int(n_runs * Lk.state_stride),
                "d2h_bytes_per_step": int(n_runs * Lk.result_stride + 32), "steps": k_e2e,
                "api": "bf_eval (host buffers, synchronous): H2D state + frontier kernel + D2H results/counts per step"}
+        # informational: the incremental path of row f2 — state resident on the device, a tick sends only deltas
+        # (here 1 % of all (run, step) phase codes change per tick) and reads every result record back
+        try:
+            rng = np.random.default_rng(1234 + rank)
+            hres = fr.resident_create(Lk, n_runs)
+            fr.resident_upload(hres, 0, sets[0][4])
+            k_delta = max(1, (n_runs * S) // 100)
+            dsets = []
+            for _ in range(3):
+                flat = rng.choice(n_runs * S, size=k_delta, replace=False)
+                d = np.zeros(k_delta, dtype=fr.DELTA_DTYPE)
+                d["run"], d["index"], d["field"] = flat // S, flat % S, A.DELTA_PHASE
+                d["code"] = rng.choice([0, 2, 3, 3, 3, 4, 13], size=k_delta)
+                dsets.append(d)
+            for i in range(3):
+                fr.resident_apply(hres, dsets[i])
+                fr.resident_eval(hres, Lk, n_runs, hr)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(k_e2e):
+                fr.resident_apply(hres, dsets[i % 3])
+                fr.resident_eval(hres, Lk, n_runs, hr)
+            dti = time.perf_counter() - t0
+            tti = torch.tensor([dti], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tti, op=dist.ReduceOp.MAX)
+            e2e["incremental"] = {"value": evals_per_pass * k_e2e / float(tti.item()), "unit": UNIT, "change_rate": 0.01,
+                                  "h2d_bytes_per_step": int(k_delta * 8), "d2h_bytes_per_step": int(n_runs * Lk.result_stride + 32),
+                                  "api": "bf_resident_apply (deltas) + bf_resident_eval: state stays on the device (row f2)"}
+            fr.resident_destroy(hres)
+        except Exception as ex:  # never lose the contract line over the informational leg
+            e2e["incremental"] = {"error": str(ex)[:200]}
         fr.free_pinned(hs.reshape(-1))
         fr.free_pinned(hr.reshape(-1))
 

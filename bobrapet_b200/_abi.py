@@ -23,6 +23,7 @@ PHASE_NAMES = ["", "Pending", "Running", "Succeeded", "Failed", "Finished", "Can
 
 QUEUED_NONE, QUEUED_PRIORITY, QUEUED_GLOBAL, QUEUED_QUEUE, QUEUED_OTHER = range(5)  # BF_QUEUED_*
 SCHED_NONE = 0xFFFFFFFF
+DELTA_PHASE, DELTA_COND, DELTA_DECISION, DELTA_CHILD, DELTA_RUN_FLAGS, DELTA_REGISTERED, DELTA_TOPO_SLOT = range(7)  # BF_DELTA_*
 STEP_ENGRAM, STEP_CONDITION, STEP_PARALLEL, STEP_SLEEP, STEP_STOP, STEP_WAIT, STEP_EXECUTE_STORY, STEP_GATE = range(8)
 STEP_TYPE_CODE = {"": STEP_ENGRAM, "condition": STEP_CONDITION, "parallel": STEP_PARALLEL, "sleep": STEP_SLEEP,
                   "stop": STEP_STOP, "wait": STEP_WAIT, "executeStory": STEP_EXECUTE_STORY, "gate": STEP_GATE}
@@ -130,6 +131,12 @@ SYMBOLS = [
     ("bf_eval_device", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     ("bf_schedule", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(SchedTables), C.POINTER(SchedOut)]),
     ("bf_schedule_device", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(SchedTables), C.POINTER(SchedOut), C.c_void_p]),
+    ("bf_resident_create", C.c_int, [C.c_void_p, C.POINTER(Layout), C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("bf_resident_destroy", C.c_int, [C.c_void_p, C.c_uint32]),
+    ("bf_resident_upload", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    ("bf_resident_apply", C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]),
+    ("bf_resident_eval", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(Counts)]),
+    ("bf_resident_download", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     ("bf_alloc_pinned", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     ("bf_free_pinned", C.c_int, [C.c_void_p, C.c_void_p]),
     ("bf_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),

@@ -29,6 +29,7 @@ uint32_t split_entry_bytes(const KParams& P);
 int walk_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
 cudaError_t launch_classify(const KParams& P, uint32_t sm_count, cudaStream_t stream);
 cudaError_t launch_walk(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_apply_deltas(const DeltaParams& P, cudaStream_t stream);
 cudaError_t launch_schedule(const SchedParams& P, uint32_t sm_count, cudaStream_t stream);
 cudaError_t launch_closure(const Slot* slots, const uint32_t* slot_ids, const uint32_t* starts, uint32_t n, uint32_t n_slots,
                            uint32_t words_out, uint32_t* masks, cudaStream_t stream);
@@ -40,6 +41,14 @@ namespace {
 
 inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 inline size_t round_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Resident {  // a device-resident batch (row f2)
+  bool alive = false;
+  bf_layout L{};
+  uint32_t cap = 0;
+  uint8_t* d_state = nullptr;
+  uint8_t* d_result = nullptr;
+};
 
 struct TopoMeta {
   bool alive = false;
@@ -97,6 +106,12 @@ struct bf_ctx {
   uint32_t last_eval_runs = 0;
   bf_layout last_eval_layout{};
   uint8_t* d_sched = nullptr; size_t d_sched_cap = 0;   // runs | records | tables, one allocation
+  const uint8_t* last_state = nullptr;                  // device records of the last evaluated batch (bf_eval or resident)
+  const uint8_t* last_result = nullptr;
+  // resident batches (row f2)
+  std::vector<Resident> resident;
+  bf_delta* d_deltas = nullptr; size_t d_deltas_cap = 0;
+  uint32_t* d_rejected = nullptr;
 
   // cached shared-memory plan (recomputed when the layout or the largest record changes)
   uint32_t plan_key_stride = 0, plan_key_words = 0, plan_key_rec = 0, plan_key_variant = 0xFFFFFFFFu;
@@ -682,7 +697,8 @@ void bf_destroy(bf_ctx* c) {
   }
   cudaFreeHost(c->h_counts);
   cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
-  cudaFree(c->d_defer); cudaFree(c->d_walk); cudaFree(c->d_walk_count); cudaFree(c->info_dev); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums); cudaFree(c->d_sched);
+  cudaFree(c->d_defer); cudaFree(c->d_walk); cudaFree(c->d_walk_count); cudaFree(c->info_dev); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums); cudaFree(c->d_sched); cudaFree(c->d_deltas); cudaFree(c->d_rejected);
+  for (Resident& r : c->resident) { cudaFree(r.d_state); cudaFree(r.d_result); }
   delete c;
 }
 
@@ -937,6 +953,7 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
   hc = *c->h_counts;
   c->stats.last_eval_chunks = chunks;
   c->last_eval_valid = true; c->last_eval_runs = b->n_runs; c->last_eval_layout = L;
+  c->last_state = c->d_state; c->last_result = c->d_result;
   if (want_exp) {
     const uint64_t n = hc.expansion < b->expansion_cap ? hc.expansion : b->expansion_cap;
     if (n) BF_CUDA(c, cudaMemcpy(b->expansion, c->d_exp, (size_t)n * sizeof(bf_expansion), cudaMemcpyDeviceToHost));
@@ -993,7 +1010,7 @@ int bf_schedule(bf_ctx* c, const bf_batch* b, const bf_sched_run* runs, const bf
   if (!out || out->struct_size != sizeof(bf_sched_out)) return fail(c, BF_EINVAL, "bad bf_sched_out.struct_size");
   if (b->n_runs && (!runs || !out->records)) return fail(c, BF_EINVAL, "null runs/records");
   if (!c->last_eval_valid || c->last_eval_runs != b->n_runs || memcmp(&c->last_eval_layout, &b->layout, sizeof(bf_layout)) != 0)
-    return fail(c, BF_EINVAL, "bf_schedule must follow bf_eval of the same batch (n_runs and layout) on this ctx");
+    return fail(c, BF_EINVAL, "bf_schedule must follow bf_eval / bf_resident_eval of the same batch (n_runs and layout) on this ctx");
   BF_CUDA(c, cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   // one device allocation: runs | records | story_running | queue_running | queue_maxprio | global | limits | bases
@@ -1014,7 +1031,7 @@ int bf_schedule(bf_ctx* c, const bf_batch* b, const bf_sched_run* runs, const bf
   BF_CUDA(c, up(o_qa, t->queue_aging_s, nq * 4));
   BF_CUDA(c, up(o_sb, t->story_running_base, ns * 4));
   BF_CUDA(c, up(o_qb, t->queue_running_base, nq * 4));
-  P.state = c->d_state; P.result = c->d_result;
+  P.state = c->last_state; P.result = c->last_result;
   P.runs = reinterpret_cast<const bf_sched_run*>(d + o_runs); P.records = d + o_rec;
   P.story_running = reinterpret_cast<uint32_t*>(d + o_sr); P.queue_running = reinterpret_cast<uint32_t*>(d + o_qr);
   P.queue_maxprio = reinterpret_cast<int32_t*>(d + o_mp); P.global_running = reinterpret_cast<uint32_t*>(d + o_gl);
@@ -1035,6 +1052,124 @@ int bf_schedule(bf_ctx* c, const bf_batch* b, const bf_sched_run* runs, const bf
   const cudaError_t es = cudaStreamSynchronize(s);  // never return with copies into the caller's buffers in flight
   if (e != cudaSuccess) return cuda_fail(c, e, "bf_schedule");
   if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
+  return BF_OK;
+}
+
+// ---- resident batches (row f2: incremental state upload) --------------------------------------------------
+static Resident* resident_of(bf_ctx* c, uint32_t h) { return h < c->resident.size() && c->resident[h].alive ? &c->resident[h] : nullptr; }
+
+int bf_resident_create(bf_ctx* c, const bf_layout* L, uint32_t capacity, uint32_t* handle_out) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!L || !handle_out || capacity == 0) return fail(c, BF_EINVAL, "null layout / handle or zero capacity");
+  if (int rc = check_layout(c, *L)) return rc;
+  BF_CUDA(c, cudaSetDevice(c->device));
+  Resident r;
+  r.L = *L; r.cap = capacity;
+  cudaError_t e = cudaMalloc(&r.d_state, (size_t)capacity * L->state_stride);
+  if (e == cudaSuccess) e = cudaMalloc(&r.d_result, (size_t)capacity * L->result_stride);
+  if (e == cudaSuccess) e = cudaMemsetAsync(r.d_state, 0, (size_t)capacity * L->state_stride, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { cudaFree(r.d_state); cudaFree(r.d_result); return fail(c, BF_ENOMEM, std::string("resident batch: ") + cudaGetErrorString(e)); }
+  r.alive = true;
+  uint32_t h = 0;
+  while (h < c->resident.size() && c->resident[h].alive) ++h;
+  if (h == c->resident.size()) c->resident.push_back(r); else c->resident[h] = r;
+  *handle_out = h;
+  return BF_OK;
+}
+
+int bf_resident_destroy(bf_ctx* c, uint32_t h) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  Resident* r = resident_of(c, h);
+  if (!r) return fail(c, BF_EINVAL, "unknown resident batch");
+  BF_CUDA(c, cudaSetDevice(c->device));
+  cudaStreamSynchronize(c->stream);
+  if (c->last_state == r->d_state) c->last_eval_valid = false;
+  cudaFree(r->d_state); cudaFree(r->d_result);
+  *r = Resident();
+  return BF_OK;
+}
+
+int bf_resident_upload(bf_ctx* c, uint32_t h, uint32_t first, uint32_t n, const void* records) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  Resident* r = resident_of(c, h);
+  if (!r) return fail(c, BF_EINVAL, "unknown resident batch");
+  if ((uint64_t)first + n > r->cap || (n && !records)) return fail(c, BF_EINVAL, "run range outside the resident batch");
+  if (n == 0) return BF_OK;
+  BF_CUDA(c, cudaSetDevice(c->device));
+  BF_CUDA(c, cudaMemcpyAsync(r->d_state + (size_t)first * r->L.state_stride, records, (size_t)n * r->L.state_stride, cudaMemcpyHostToDevice, c->stream));
+  BF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return BF_OK;
+}
+
+int bf_resident_download(bf_ctx* c, uint32_t h, uint32_t first, uint32_t n, void* records) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  Resident* r = resident_of(c, h);
+  if (!r) return fail(c, BF_EINVAL, "unknown resident batch");
+  if ((uint64_t)first + n > r->cap || (n && !records)) return fail(c, BF_EINVAL, "run range outside the resident batch");
+  if (n == 0) return BF_OK;
+  BF_CUDA(c, cudaSetDevice(c->device));
+  BF_CUDA(c, cudaMemcpyAsync(records, r->d_state + (size_t)first * r->L.state_stride, (size_t)n * r->L.state_stride, cudaMemcpyDeviceToHost, c->stream));
+  BF_CUDA(c, cudaStreamSynchronize(c->stream));
+  return BF_OK;
+}
+
+int bf_resident_apply(bf_ctx* c, uint32_t h, const bf_delta* deltas, uint32_t n) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  Resident* r = resident_of(c, h);
+  if (!r) return fail(c, BF_EINVAL, "unknown resident batch");
+  if (n && !deltas) return fail(c, BF_EINVAL, "null deltas");
+  if (n == 0) return BF_OK;
+  BF_CUDA(c, cudaSetDevice(c->device));
+  if (int rc = ensure_dev(c, c->d_deltas, c->d_deltas_cap, n)) return rc;
+  if (!c->d_rejected) BF_CUDA(c, cudaMalloc(&c->d_rejected, 16));
+  cudaStream_t s = c->stream;
+  BF_CUDA(c, cudaMemcpyAsync(c->d_deltas, deltas, (size_t)n * sizeof(bf_delta), cudaMemcpyHostToDevice, s));
+  BF_CUDA(c, cudaMemsetAsync(c->d_rejected, 0, 4, s));
+  bf::DeltaParams P{};
+  P.state = r->d_state; P.deltas = c->d_deltas; P.n = n; P.n_runs = r->cap;
+  P.words = r->L.words; P.state_stride = r->L.state_stride; P.off_phase = r->L.off_phase; P.off_cond = r->L.off_cond;
+  P.off_decision = r->L.off_decision; P.off_child = r->L.off_child; P.child_nibbles = r->L.child_nibbles;
+  P.rejected = c->d_rejected;
+  BF_CUDA(c, bf::launch_apply_deltas(P, s));
+  c->stats.kernel_launches += 1;
+  BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_rejected, 4, cudaMemcpyDeviceToHost, s));
+  BF_CUDA(c, cudaStreamSynchronize(s));
+  const uint32_t rejected = *reinterpret_cast<const uint32_t*>(c->h_counts);
+  if (rejected) return fail(c, BF_EINVAL, std::to_string(rejected) + " delta(s) outside the record (run, index, code or absent field); the others were applied");
+  return BF_OK;
+}
+
+int bf_resident_eval(bf_ctx* c, uint32_t h, uint32_t n_runs, uint32_t flags, uint32_t max_iterations, void* result, bf_counts* counts) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  c->last_eval_valid = false;
+  Resident* r = resident_of(c, h);
+  if (!r) return fail(c, BF_EINVAL, "unknown resident batch");
+  if (n_runs > r->cap || (n_runs && !result)) return fail(c, BF_EINVAL, "n_runs exceeds the resident batch / null result");
+  if (flags & BF_EVAL_EXPANSION) return fail(c, BF_EINVAL, "expansion is not offered on the resident path");
+  BF_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  bf_batch db{};
+  db.struct_size = sizeof(bf_batch);
+  db.n_runs = n_runs; db.flags = flags & ~BF_EVAL_VALIDATE; db.max_iterations = max_iterations; db.layout = r->L;
+  BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
+  const int rc = run_pass(c, db, r->d_state, r->d_result, nullptr, c->d_counts, s);
+  cudaError_t e = cudaSuccess;
+  if (rc == BF_OK && n_runs) e = cudaMemcpyAsync(result, r->d_result, (size_t)n_runs * r->L.result_stride, cudaMemcpyDeviceToHost, s);
+  if (rc == BF_OK && e == cudaSuccess) e = cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(bf_counts), cudaMemcpyDeviceToHost, s);
+  const cudaError_t es = cudaStreamSynchronize(s);
+  if (rc != BF_OK) return rc;
+  if (e != cudaSuccess) return cuda_fail(c, e, "bf_resident_eval");
+  if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
+  if (counts) *counts = *c->h_counts;
+  c->last_eval_valid = true; c->last_eval_runs = n_runs; c->last_eval_layout = r->L;
+  c->last_state = r->d_state; c->last_result = r->d_result;
   return BF_OK;
 }
 

@@ -115,6 +115,15 @@ struct KParams {
   uint32_t wq, wq_log2;
 };
 
+// resident.cu (row f2)
+struct DeltaParams {
+  uint8_t* state;
+  const bf_delta* deltas;
+  uint32_t n, n_runs;
+  uint32_t words, state_stride, off_phase, off_cond, off_decision, off_child, child_nibbles;
+  uint32_t* rejected;  // count of deltas outside the record (bad run / index / absent field)
+};
+
 // limiters.cu (rows a9 / f4)
 struct SchedParams {
   const uint8_t* state;

@@ -158,6 +158,24 @@ struct bfh_batch {
   bool pinned = false;
   std::vector<const bfh_story*> story_of_run;
   std::string err;
+  // resident mode (row f2): the device holds the records, setters log coalesced deltas, eval sends only those
+  bool resident = false;
+  uint32_t handle = 0;
+  uint32_t uploaded = 0;                             // runs [0, uploaded) exist on the device
+  std::unordered_map<uint64_t, uint32_t> delta_at;   // (run, field, index) -> position in `deltas`
+  std::vector<bf_delta> deltas;
+  uint64_t delta_bytes_sent = 0, full_bytes_sent = 0;
+
+  void log_delta(uint32_t run, uint32_t field, uint32_t index, uint32_t code) {
+    if (!resident || run >= uploaded) return;        // a run not yet on the device travels as a full record
+    const uint64_t key = ((uint64_t)run << 32) | ((uint64_t)field << 16) | index;
+    auto it = delta_at.find(key);
+    if (it != delta_at.end()) { deltas[it->second].code = (uint8_t)code; return; }   // the last value of a tick wins
+    delta_at[key] = (uint32_t)deltas.size();
+    bf_delta d;
+    d.run = run; d.index = (uint16_t)index; d.field = (uint8_t)field; d.code = (uint8_t)code;
+    deltas.push_back(d);
+  }
 };
 
 extern "C" {
@@ -361,6 +379,7 @@ bfh_batch* bfh_batch_new(bf_ctx* ctx, uint32_t steps_max, uint32_t child_nibbles
 }
 void bfh_batch_free(bfh_batch* b) {
   if (!b) return;
+  if (b->resident) bf_resident_destroy(b->ctx, b->handle);
   if (b->pinned) { bf_free_pinned(b->ctx, b->state); bf_free_pinned(b->ctx, b->result); }
   else { free(b->state); free(b->result); }
   delete b;
@@ -388,6 +407,7 @@ int bfh_batch_remove_last_run(bfh_batch* b) {
   if (!b || b->n == 0) return BF_EINVAL;
   b->story_of_run.pop_back();
   --b->n;
+  if (b->uploaded > b->n) b->uploaded = b->n;  // the slot's next occupant is uploaded as a full record
   return BF_OK;
 }
 
@@ -401,6 +421,7 @@ int bfh_run_set_phase_code(bfh_batch* b, uint32_t run, uint32_t step, int code) 
   RUN_CHECK(b, run, step)
   if (code < 0 || code > 14) return BF_EINVAL;
   set_code(rec + b->L.off_phase, b->L.words, 4, step, code);
+  b->log_delta(run, BF_DELTA_PHASE, step, (uint32_t)code);
   return BF_OK;
 }
 int bfh_run_set_phase(bfh_batch* b, uint32_t run, uint32_t step, const char* phase, const char* message) {
@@ -412,12 +433,14 @@ int bfh_run_set_cond(bfh_batch* b, uint32_t run, uint32_t step, int code) {
   RUN_CHECK(b, run, step)
   if (b->L.off_cond == BF_OFF_NONE || code < 0 || code > 3) return BF_EINVAL;
   set_code(rec + b->L.off_cond, b->L.words, 2, step, code);
+  b->log_delta(run, BF_DELTA_COND, step, (uint32_t)code);
   return BF_OK;
 }
 int bfh_run_set_decision(bfh_batch* b, uint32_t run, uint32_t step, int code) {
   RUN_CHECK(b, run, step)
   if (b->L.off_decision == BF_OFF_NONE || code < 0 || code > 3) return BF_EINVAL;
   set_code(rec + b->L.off_decision, b->L.words, 2, step, code);
+  b->log_delta(run, BF_DELTA_DECISION, step, (uint32_t)code);
   return BF_OK;
 }
 int bfh_run_set_gate(bfh_batch* b, uint32_t run, uint32_t step, const char* gate_state, int timed_out) {
@@ -434,12 +457,14 @@ int bfh_run_set_run_flags(bfh_batch* b, uint32_t run, int topology_terminated, i
   if (topology_terminated) f |= BF_RF_TOPOLOGY_TERMINATED;
   if (host_group >= 0) f |= (uint8_t)(BF_RF_HOST_GROUP | ((host_group & 3) << BF_RF_HOST_GROUP_SHIFT));
   h->run_flags = f;
+  b->log_delta(run, BF_DELTA_RUN_FLAGS, 0, f);
   return BF_OK;
 }
 int bfh_run_register_children(bfh_batch* b, uint32_t run, uint32_t q, int on) {
   if (!b || run >= b->n || q >= b->story_of_run[run]->par.size()) return BF_EINVAL;
   bf_run_header* h = reinterpret_cast<bf_run_header*>(b->state + (size_t)run * b->L.state_stride);
   if (on) h->children_registered |= 1ull << q; else h->children_registered &= ~(1ull << q);
+  b->log_delta(run, BF_DELTA_REGISTERED, q, on ? 1u : 0u);
   return BF_OK;
 }
 int bfh_run_set_child_phase(bfh_batch* b, uint32_t run, uint32_t q, uint32_t branch, const char* phase) {
@@ -452,12 +477,30 @@ int bfh_run_set_child_phase(bfh_batch* b, uint32_t run, uint32_t q, uint32_t bra
   const uint32_t i = st->child_first[q] + branch;
   const uint8_t sh = (uint8_t)((i & 1u) * 4u);
   ch[i >> 1] = (uint8_t)((ch[i >> 1] & ~(0xFu << sh)) | ((unsigned)c << sh));
+  b->log_delta(run, BF_DELTA_CHILD, i, (uint32_t)c);
   return BF_OK;
 }
 
 int bfh_batch_eval(bfh_batch* b, uint32_t eval_flags, bf_counts* counts) {
   if (!b) return BF_EINVAL;
   if (!b->ctx) { b->err = "batch was created without a device context"; return BF_ENODEV; }
+  if (b->resident) {
+    // new runs as full records, everything else as the tick's coalesced deltas, then one pass over the device copy
+    int rc = BF_OK;
+    if (b->uploaded < b->n) {
+      rc = bf_resident_upload(b->ctx, b->handle, b->uploaded, b->n - b->uploaded, b->state + (size_t)b->uploaded * b->L.state_stride);
+      if (rc == BF_OK) { b->full_bytes_sent += (uint64_t)(b->n - b->uploaded) * b->L.state_stride; b->uploaded = b->n; }
+    }
+    if (rc == BF_OK && !b->deltas.empty()) {
+      rc = bf_resident_apply(b->ctx, b->handle, b->deltas.data(), (uint32_t)b->deltas.size());
+      b->delta_bytes_sent += b->deltas.size() * sizeof(bf_delta);
+    }
+    b->deltas.clear();
+    b->delta_at.clear();
+    if (rc == BF_OK) rc = bf_resident_eval(b->ctx, b->handle, b->n, eval_flags & ~(uint32_t)BF_EVAL_EXPANSION, 0, b->result, counts);
+    if (rc != BF_OK) b->err = bf_last_error(b->ctx);
+    return rc;
+  }
   bf_batch bb{};
   bb.struct_size = sizeof(bf_batch);
   bb.n_runs = b->n; bb.flags = eval_flags; bb.layout = b->L;
@@ -465,6 +508,29 @@ int bfh_batch_eval(bfh_batch* b, uint32_t eval_flags, bf_counts* counts) {
   const int rc = bf_eval(b->ctx, &bb);
   if (rc != BF_OK) b->err = bf_last_error(b->ctx);
   return rc;
+}
+
+int bfh_batch_set_resident(bfh_batch* b, int on) {
+  if (!b) return BF_EINVAL;
+  if (!b->ctx) { b->err = "batch was created without a device context"; return BF_ENODEV; }
+  if ((on != 0) == b->resident) return BF_OK;
+  if (on) {
+    const int rc = bf_resident_create(b->ctx, &b->L, b->cap, &b->handle);
+    if (rc != BF_OK) { b->err = bf_last_error(b->ctx); return rc; }
+    b->resident = true; b->uploaded = 0;
+  } else {
+    bf_resident_destroy(b->ctx, b->handle);
+    b->resident = false; b->uploaded = 0;
+    b->deltas.clear(); b->delta_at.clear();
+  }
+  return BF_OK;
+}
+int bfh_batch_traffic(const bfh_batch* b, uint64_t* full_record_bytes, uint64_t* delta_bytes, uint32_t* pending_deltas) {
+  if (!b) return BF_EINVAL;
+  if (full_record_bytes) *full_record_bytes = b->full_bytes_sent;
+  if (delta_bytes) *delta_bytes = b->delta_bytes_sent;
+  if (pending_deltas) *pending_deltas = (uint32_t)b->deltas.size();
+  return BF_OK;
 }
 
 uint32_t bfh_run_summary(const bfh_batch* b, uint32_t run) {

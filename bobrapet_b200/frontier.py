@@ -151,6 +151,41 @@ class Frontier:
 
 
 
+
+    # -- resident batches: device-side state, delta uploads (row f2)
+    DELTA_DTYPE = np.dtype([("run", "<u4"), ("index", "<u2"), ("field", "u1"), ("code", "u1")])
+
+    def resident_create(self, L: A.Layout, capacity: int) -> int:
+        h = C.c_uint32()
+        self._check(self._lib.bf_resident_create(self._ctx, C.byref(L), capacity, C.byref(h)), "bf_resident_create")
+        return h.value
+
+    def resident_destroy(self, handle: int):
+        self._check(self._lib.bf_resident_destroy(self._ctx, handle), "bf_resident_destroy")
+
+    def resident_upload(self, handle: int, first_run: int, state: np.ndarray):
+        assert state.dtype == np.uint8 and state.flags["C_CONTIGUOUS"]
+        self._check(self._lib.bf_resident_upload(self._ctx, handle, first_run, state.shape[0], state.ctypes.data), "bf_resident_upload")
+
+    def resident_download(self, handle: int, first_run: int, n_runs: int, state_stride: int) -> np.ndarray:
+        out = np.zeros((n_runs, state_stride), dtype=np.uint8)
+        self._check(self._lib.bf_resident_download(self._ctx, handle, first_run, n_runs, out.ctypes.data), "bf_resident_download")
+        return out
+
+    def resident_apply(self, handle: int, deltas: np.ndarray):
+        """deltas: structured array of DELTA_DTYPE (8 bytes each), at most one per (run, field, index)"""
+        d = np.ascontiguousarray(deltas, dtype=self.DELTA_DTYPE)
+        self._check(self._lib.bf_resident_apply(self._ctx, handle, d.ctypes.data, d.shape[0]), "bf_resident_apply")
+
+    def resident_eval(self, handle: int, L: A.Layout, n_runs: int, result: Optional[np.ndarray] = None, flags: int = 0,
+                      max_iterations: int = 0):
+        if result is None:
+            result = np.zeros((n_runs, L.result_stride), dtype=np.uint8)
+        counts = A.Counts()
+        self._check(self._lib.bf_resident_eval(self._ctx, handle, n_runs, flags, max_iterations, result.ctypes.data, C.byref(counts)),
+                    "bf_resident_eval")
+        return result, {"ready": counts.ready, "skip": counts.skip, "expansion": counts.expansion, "evals": counts.evals}
+
     # -- redrive closure (row f3; storyrun_controller.go:535-558)
     def closure(self, slots, steps, words: int) -> np.ndarray:
         """bf_topology_closure: [count, words] uint32 masks of the steps a redrive from (slot, step) resets."""

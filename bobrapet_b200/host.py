@@ -42,6 +42,8 @@ _SYMS = [
     ("bfh_run_register_children", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
     ("bfh_run_set_child_phase", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p]),
     ("bfh_batch_eval", C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(A.Counts)]),
+    ("bfh_batch_set_resident", C.c_int, [C.c_void_p, C.c_int]),
+    ("bfh_batch_traffic", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("bfh_run_summary", C.c_uint32, [C.c_void_p, C.c_uint32]),
     ("bfh_run_ready", C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]),
     ("bfh_run_skipped", C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]),
@@ -193,6 +195,15 @@ class HostBatch:
 
     def set_phase(self, run, step, phase, message=""):
         self._chk(self._l.bfh_run_set_phase(self._p, run, step, _b(phase), _b(message)), "bfh_run_set_phase")
+
+    def set_resident(self, on=True):
+        self._chk(self._l.bfh_batch_set_resident(self._p, int(bool(on))), "bfh_batch_set_resident")
+
+    def traffic(self):
+        """(bytes sent as full records, bytes sent as deltas, deltas pending)"""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        self._chk(self._l.bfh_batch_traffic(self._p, C.byref(a), C.byref(b), C.byref(c)), "bfh_batch_traffic")
+        return a.value, b.value, c.value
 
     def set_phase_code(self, run, step, code):
         self._chk(self._l.bfh_run_set_phase_code(self._p, run, step, code), "bfh_run_set_phase_code")

@@ -208,3 +208,36 @@ func (c *Ctx) RedriveClosure(slots, steps []uint32, words uint32) ([]uint32, err
 	return masks, c.err(C.bf_topology_closure(c.p, (*C.uint32_t)(unsafe.Pointer(&slots[0])), (*C.uint32_t)(unsafe.Pointer(&steps[0])),
 		C.uint32_t(len(slots)), C.uint32_t(words), (*C.uint32_t)(unsafe.Pointer(&masks[0]))))
 }
+
+// Resident is a device-resident batch (row f2): full records travel once, afterwards only deltas.
+type Resident struct {
+	c      *Ctx
+	handle C.uint32_t
+	layout C.bf_layout
+}
+
+func (c *Ctx) NewResident(layout C.bf_layout, capacity uint32) (*Resident, error) {
+	r := &Resident{c: c, layout: layout}
+	return r, c.err(C.bf_resident_create(c.p, &layout, C.uint32_t(capacity), &r.handle))
+}
+
+func (r *Resident) Close() error { return r.c.err(C.bf_resident_destroy(r.c.p, r.handle)) }
+
+// Upload sends full state records for runs [first, first+n) (new StoryRuns, or a resync).
+func (r *Resident) Upload(first, n uint32, records unsafe.Pointer) error {
+	return r.c.err(C.bf_resident_upload(r.c.p, r.handle, C.uint32_t(first), C.uint32_t(n), records))
+}
+
+// Apply sends the tick's coalesced deltas: what syncStateFromStepRuns (dag.go:965-1009) changed.
+func (r *Resident) Apply(deltas []C.bf_delta) error {
+	if len(deltas) == 0 {
+		return nil
+	}
+	return r.c.err(C.bf_resident_apply(r.c.p, r.handle, &deltas[0], C.uint32_t(len(deltas))))
+}
+
+// Eval runs one pass over runs [0, n) of the resident state and reads the result records back.
+func (r *Resident) Eval(n, flags uint32, result unsafe.Pointer) (C.bf_counts, error) {
+	var counts C.bf_counts
+	return counts, r.c.err(C.bf_resident_eval(r.c.p, r.handle, C.uint32_t(n), C.uint32_t(flags), 0, result, &counts))
+}

@@ -388,6 +388,43 @@ int bf_schedule_device(bf_ctx* ctx, const bf_batch* batch, const bf_sched_run* r
                        bf_sched_out* out, void* stream);
 
 
+/* ------------------------------------------------------------------ resident batches
+ * Incremental state upload: the state records of a batch stay on the device and the host sends DELTAS — what
+ * syncStateFromStepRuns (dag.go:965-1009) and the StepRun watch events (storyrun_controller.go:2116-2129) amount
+ * to per tick: a handful of (run, step) phase changes — so the H2D traffic of a tick is O(changes), not O(N*S).
+ * A delta rewrites one code of one record in place (bit-sliced fields: one bit per plane, by integer atomics).
+ * Contract: within ONE bf_resident_apply call at most one delta per (run, field, index) — the host mirror
+ * coalesces (the last value of a tick wins); deltas of different steps that share a word are fine.              */
+enum {
+  BF_DELTA_PHASE = 0,       /* index = step, code = BF_PHASE_* (0..14)                                           */
+  BF_DELTA_COND = 1,        /* index = step, code = BF_COND_*                                                    */
+  BF_DELTA_DECISION = 2,    /* index = step, code = BF_DEC_*                                                     */
+  BF_DELTA_CHILD = 3,       /* index = child nibble (child_first[p] + branch), code = BF_PHASE_*                 */
+  BF_DELTA_RUN_FLAGS = 4,   /* index ignored, code = BF_RF_* byte                                                */
+  BF_DELTA_REGISTERED = 5,  /* index = parallel desc p, code = 0 / 1 (children_registered bit)                   */
+  BF_DELTA_TOPO_SLOT = 6    /* index = low 16 bits, code = bits 16-23 of the new topology slot (slot < 2^24)     */
+};
+typedef struct bf_delta { /* 8 B */
+  uint32_t run;
+  uint16_t index;
+  uint8_t field; /* BF_DELTA_* */
+  uint8_t code;
+} bf_delta;
+
+/* A resident batch of up to `capacity` runs with the given layout; *handle_out identifies it on this ctx.       */
+int bf_resident_create(bf_ctx* ctx, const bf_layout* layout, uint32_t capacity, uint32_t* handle_out);
+int bf_resident_destroy(bf_ctx* ctx, uint32_t handle);
+/* Full records for runs [first_run, first_run + n_runs) (new StoryRuns, or a resync): host buffer, synchronous.  */
+int bf_resident_upload(bf_ctx* ctx, uint32_t handle, uint32_t first_run, uint32_t n_runs, const void* state_records);
+/* Apply n deltas (host buffer; copied and scattered on the ctx stream, synchronous).                            */
+int bf_resident_apply(bf_ctx* ctx, uint32_t handle, const bf_delta* deltas, uint32_t n);
+/* One pass over runs [0, n_runs) of the resident state: kernels + D2H of the result records (host buffer) and
+ * counts.  flags = BF_EVAL_* (expansion is not offered on this path).  Also the batch bf_schedule refers to.     */
+int bf_resident_eval(bf_ctx* ctx, uint32_t handle, uint32_t n_runs, uint32_t flags, uint32_t max_iterations, void* result,
+                     bf_counts* counts);
+/* Read the device copy back (tests / resync checks).                                                            */
+int bf_resident_download(bf_ctx* ctx, uint32_t handle, uint32_t first_run, uint32_t n_runs, void* state_records);
+
 /* Pinned host memory for batches (cgo: memory with no Go pointers).           */
 int bf_alloc_pinned(bf_ctx* ctx, size_t bytes, void** out);
 int bf_free_pinned(bf_ctx* ctx, void* p);

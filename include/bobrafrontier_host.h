@@ -86,7 +86,15 @@ int bfh_run_set_run_flags(bfh_batch* b, uint32_t run, int topology_terminated, i
 int bfh_run_register_children(bfh_batch* b, uint32_t run, uint32_t parallel_index, int registered);
 int bfh_run_set_child_phase(bfh_batch* b, uint32_t run, uint32_t parallel_index, uint32_t branch, const char* phase);
 
-/* One frontier pass over the batch through bf_eval (eval_flags: BF_EVAL_*). */
+/* Resident mode (row f2, incremental state upload): the device keeps the state records; from then on every
+ * bfh_run_set_* also logs a delta (coalesced per (run, field, index): the last value of a tick wins) and
+ * bfh_batch_eval sends the records of NEW runs plus the tick's deltas instead of the whole batch — H2D is
+ * O(changes), what syncStateFromStepRuns (dag.go:965-1009) produces per reconcile.  Needs a device ctx.        */
+int bfh_batch_set_resident(bfh_batch* b, int on);
+/* bytes sent so far as full records / as deltas, and the deltas logged since the last eval */
+int bfh_batch_traffic(const bfh_batch* b, uint64_t* full_record_bytes, uint64_t* delta_bytes, uint32_t* pending_deltas);
+
+/* One frontier pass over the batch through bf_eval (or, in resident mode, bf_resident_*) (eval_flags: BF_EVAL_*). */
 int bfh_batch_eval(bfh_batch* b, uint32_t eval_flags, bf_counts* counts);
 
 /* Results of the last pass.  Step lists come back in list order (ascending index), the order the
