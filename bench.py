@@ -354,26 +354,26 @@ def main():
             dsets = []
             for _ in range(3):
                 flat = rng.choice(n_runs * S, size=k_delta, replace=False)
-                d = np.zeros(k_delta, dtype=fr.DELTA_DTYPE)
+                d = fr.alloc_pinned(k_delta * 8).view(fr.DELTA_DTYPE)       # pinned: the delta upload is asynchronous
                 d["run"], d["index"], d["field"] = flat // S, flat % S, A.DELTA_PHASE
                 d["code"] = rng.choice([0, 2, 3, 3, 3, 4, 13], size=k_delta)
                 dsets.append(d)
             for i in range(3):
-                fr.resident_apply(hres, dsets[i])
-                fr.resident_eval(hres, Lk, n_runs, hr)
+                fr.resident_tick(hres, Lk, n_runs, dsets[i], hr)
             barrier()
             t0 = time.perf_counter()
             for i in range(k_e2e):
-                fr.resident_apply(hres, dsets[i % 3])
-                fr.resident_eval(hres, Lk, n_runs, hr)
+                fr.resident_tick(hres, Lk, n_runs, dsets[i % 3], hr)
             dti = time.perf_counter() - t0
             tti = torch.tensor([dti], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tti, op=dist.ReduceOp.MAX)
             e2e["incremental"] = {"value": evals_per_pass * k_e2e / float(tti.item()), "unit": UNIT, "change_rate": 0.01,
                                   "h2d_bytes_per_step": int(k_delta * 8), "d2h_bytes_per_step": int(n_runs * Lk.result_stride + 32),
-                                  "api": "bf_resident_apply (deltas) + bf_resident_eval: state stays on the device (row f2)"}
+                                  "api": "bf_resident_tick (deltas + pass + results, one call): state stays on the device (row f2)"}
             fr.resident_destroy(hres)
+            for d in dsets:
+                fr.free_pinned(d.view(np.uint8))
         except Exception as ex:  # never lose the contract line over the informational leg
             e2e["incremental"] = {"error": str(ex)[:200]}
         fr.free_pinned(hs.reshape(-1))

@@ -674,7 +674,7 @@ int bf_create(bf_ctx** out, const bf_config* cfg) {
   c->stats.sm_count = (uint32_t)prop.multiProcessorCount;
   if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&c->d_counts, sizeof(bf_counts)) != cudaSuccess ||
-      cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), sizeof(bf_counts), cudaHostAllocDefault) != cudaSuccess) {
+      cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 2 * sizeof(bf_counts), cudaHostAllocDefault) != cudaSuccess) {
     delete c;
     return BF_ECUDA;
   }
@@ -1118,6 +1118,24 @@ int bf_resident_download(bf_ctx* c, uint32_t h, uint32_t first, uint32_t n, void
   return BF_OK;
 }
 
+// H2D of the deltas + the scatter kernel on the ctx stream, no synchronisation; the rejected counter is read by the caller
+static int resident_apply_async(bf_ctx* c, Resident* r, const bf_delta* deltas, uint32_t n) {
+  if (int rc = ensure_dev(c, c->d_deltas, c->d_deltas_cap, n ? n : 1)) return rc;
+  if (!c->d_rejected) BF_CUDA(c, cudaMalloc(&c->d_rejected, 16));
+  cudaStream_t s = c->stream;
+  BF_CUDA(c, cudaMemsetAsync(c->d_rejected, 0, 4, s));
+  if (n == 0) return BF_OK;
+  BF_CUDA(c, cudaMemcpyAsync(c->d_deltas, deltas, (size_t)n * sizeof(bf_delta), cudaMemcpyHostToDevice, s));
+  bf::DeltaParams P{};
+  P.state = r->d_state; P.deltas = c->d_deltas; P.n = n; P.n_runs = r->cap;
+  P.words = r->L.words; P.state_stride = r->L.state_stride; P.off_phase = r->L.off_phase; P.off_cond = r->L.off_cond;
+  P.off_decision = r->L.off_decision; P.off_child = r->L.off_child; P.child_nibbles = r->L.child_nibbles;
+  P.rejected = c->d_rejected;
+  BF_CUDA(c, bf::launch_apply_deltas(P, s));
+  c->stats.kernel_launches += 1;
+  return BF_OK;
+}
+
 int bf_resident_apply(bf_ctx* c, uint32_t h, const bf_delta* deltas, uint32_t n) {
   if (!c) return BF_EINVAL;
   std::lock_guard<std::mutex> g(c->mu);
@@ -1126,51 +1144,100 @@ int bf_resident_apply(bf_ctx* c, uint32_t h, const bf_delta* deltas, uint32_t n)
   if (n && !deltas) return fail(c, BF_EINVAL, "null deltas");
   if (n == 0) return BF_OK;
   BF_CUDA(c, cudaSetDevice(c->device));
-  if (int rc = ensure_dev(c, c->d_deltas, c->d_deltas_cap, n)) return rc;
-  if (!c->d_rejected) BF_CUDA(c, cudaMalloc(&c->d_rejected, 16));
-  cudaStream_t s = c->stream;
-  BF_CUDA(c, cudaMemcpyAsync(c->d_deltas, deltas, (size_t)n * sizeof(bf_delta), cudaMemcpyHostToDevice, s));
-  BF_CUDA(c, cudaMemsetAsync(c->d_rejected, 0, 4, s));
-  bf::DeltaParams P{};
-  P.state = r->d_state; P.deltas = c->d_deltas; P.n = n; P.n_runs = r->cap;
-  P.words = r->L.words; P.state_stride = r->L.state_stride; P.off_phase = r->L.off_phase; P.off_cond = r->L.off_cond;
-  P.off_decision = r->L.off_decision; P.off_child = r->L.off_child; P.child_nibbles = r->L.child_nibbles;
-  P.rejected = c->d_rejected;
-  BF_CUDA(c, bf::launch_apply_deltas(P, s));
-  c->stats.kernel_launches += 1;
-  BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_rejected, 4, cudaMemcpyDeviceToHost, s));
-  BF_CUDA(c, cudaStreamSynchronize(s));
+  const int rc = resident_apply_async(c, r, deltas, n);
+  cudaError_t e = rc == BF_OK ? cudaMemcpyAsync(c->h_counts, c->d_rejected, 4, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
+  const cudaError_t es = cudaStreamSynchronize(c->stream);  // the caller's delta buffer may be reused after return
+  if (rc != BF_OK) return rc;
+  if (e != cudaSuccess) return cuda_fail(c, e, "bf_resident_apply");
+  if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
   const uint32_t rejected = *reinterpret_cast<const uint32_t*>(c->h_counts);
   if (rejected) return fail(c, BF_EINVAL, std::to_string(rejected) + " delta(s) outside the record (run, index, code or absent field); the others were applied");
+  return BF_OK;
+}
+
+// deltas (optional) + one pass + results, one synchronisation: the pass is cut into run chunks whose kernels overlap
+// the download of the previous chunk's result records (as bf_eval does for both directions)
+static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs, uint32_t flags,
+                                uint32_t max_iterations, void* result, bf_counts* counts) {
+  c->last_eval_valid = false;
+  if (n_runs > r->cap || (n_runs && !result)) return fail(c, BF_EINVAL, "n_runs exceeds the resident batch / null result");
+  if (flags & BF_EVAL_EXPANSION) return fail(c, BF_EINVAL, "expansion is not offered on the resident path");
+  if (n_deltas && !deltas) return fail(c, BF_EINVAL, "null deltas");
+  BF_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const bf_layout& L = r->L;
+  const size_t rbytes = (size_t)n_runs * L.result_stride;
+  uint32_t chunks = 1;
+  if (rbytes >= (2u << 20)) {
+    chunks = (uint32_t)((rbytes + (1u << 20)) / (2u << 20));   // ~2 MB of result records per chunk
+    if (const char* e = getenv("BF_E2E_CHUNKS")) chunks = (uint32_t)atoi(e);
+    if (chunks > bf_ctx::kMaxChunks) chunks = bf_ctx::kMaxChunks;
+    if (chunks < 1) chunks = 1;
+  }
+  if (chunks > 1 && !c->pipe_ready) {
+    BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (uint32_t k = 0; k < bf_ctx::kMaxChunks; ++k) {
+      BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+      BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[k], cudaEventDisableTiming));
+    }
+    c->pipe_ready = true;
+  }
+  uint32_t* h_rej = reinterpret_cast<uint32_t*>(c->h_counts + 1);  // second pinned slot: h_counts is 2 x bf_counts
+  auto body = [&]() -> int {
+    if (int rc = resident_apply_async(c, r, deltas, n_deltas)) return rc;
+    BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
+    bf_batch db{};
+    db.struct_size = sizeof(bf_batch);
+    db.flags = flags & ~(uint32_t)BF_EVAL_VALIDATE; db.max_iterations = max_iterations; db.layout = L;
+    for (uint32_t k = 0; k < chunks; ++k) {
+      const size_t lo = (size_t)n_runs * k / chunks, hi = (size_t)n_runs * (k + 1) / chunks;
+      db.n_runs = (uint32_t)(hi - lo);
+      if (int rc = run_pass(c, db, r->d_state + lo * L.state_stride, r->d_result + lo * L.result_stride, nullptr, c->d_counts, s)) return rc;
+      const bool piped = chunks > 1;
+      if (piped) {
+        BF_CUDA(c, cudaEventRecord(c->ev_k[k], s));
+        BF_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
+      }
+      if (hi > lo)
+        BF_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(result) + lo * L.result_stride, r->d_result + lo * L.result_stride,
+                                   (hi - lo) * L.result_stride, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
+    }
+    BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(bf_counts), cudaMemcpyDeviceToHost, s));
+    BF_CUDA(c, cudaMemcpyAsync(h_rej, c->d_rejected, 4, cudaMemcpyDeviceToHost, s));
+    return BF_OK;
+  };
+  const int rc = body();
+  cudaError_t es = cudaStreamSynchronize(s);
+  if (chunks > 1) {
+    const cudaError_t e2 = cudaStreamSynchronize(c->s_out);
+    if (es == cudaSuccess) es = e2;
+  }
+  if (rc != BF_OK) return rc;
+  if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
+  if (counts) *counts = *c->h_counts;
+  c->stats.last_eval_chunks = chunks;
+  c->last_eval_valid = true; c->last_eval_runs = n_runs; c->last_eval_layout = L;
+  c->last_state = r->d_state; c->last_result = r->d_result;
+  if (n_deltas && *h_rej) return fail(c, BF_EINVAL, std::to_string(*h_rej) + " delta(s) outside the record (run, index, code or absent field); the others were applied and the pass ran");
   return BF_OK;
 }
 
 int bf_resident_eval(bf_ctx* c, uint32_t h, uint32_t n_runs, uint32_t flags, uint32_t max_iterations, void* result, bf_counts* counts) {
   if (!c) return BF_EINVAL;
   std::lock_guard<std::mutex> g(c->mu);
-  c->last_eval_valid = false;
   Resident* r = resident_of(c, h);
   if (!r) return fail(c, BF_EINVAL, "unknown resident batch");
-  if (n_runs > r->cap || (n_runs && !result)) return fail(c, BF_EINVAL, "n_runs exceeds the resident batch / null result");
-  if (flags & BF_EVAL_EXPANSION) return fail(c, BF_EINVAL, "expansion is not offered on the resident path");
-  BF_CUDA(c, cudaSetDevice(c->device));
-  cudaStream_t s = c->stream;
-  bf_batch db{};
-  db.struct_size = sizeof(bf_batch);
-  db.n_runs = n_runs; db.flags = flags & ~BF_EVAL_VALIDATE; db.max_iterations = max_iterations; db.layout = r->L;
-  BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
-  const int rc = run_pass(c, db, r->d_state, r->d_result, nullptr, c->d_counts, s);
-  cudaError_t e = cudaSuccess;
-  if (rc == BF_OK && n_runs) e = cudaMemcpyAsync(result, r->d_result, (size_t)n_runs * r->L.result_stride, cudaMemcpyDeviceToHost, s);
-  if (rc == BF_OK && e == cudaSuccess) e = cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(bf_counts), cudaMemcpyDeviceToHost, s);
-  const cudaError_t es = cudaStreamSynchronize(s);
-  if (rc != BF_OK) return rc;
-  if (e != cudaSuccess) return cuda_fail(c, e, "bf_resident_eval");
-  if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
-  if (counts) *counts = *c->h_counts;
-  c->last_eval_valid = true; c->last_eval_runs = n_runs; c->last_eval_layout = r->L;
-  c->last_state = r->d_state; c->last_result = r->d_result;
-  return BF_OK;
+  return resident_tick_locked(c, r, nullptr, 0, n_runs, flags, max_iterations, result, counts);
+}
+
+int bf_resident_tick(bf_ctx* c, uint32_t h, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs, uint32_t flags,
+                     uint32_t max_iterations, void* result, bf_counts* counts) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  Resident* r = resident_of(c, h);
+  if (!r) return fail(c, BF_EINVAL, "unknown resident batch");
+  return resident_tick_locked(c, r, deltas, n_deltas, n_runs, flags, max_iterations, result, counts);
 }
 
 int bf_alloc_pinned(bf_ctx* c, size_t bytes, void** out) {

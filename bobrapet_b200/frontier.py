@@ -186,6 +186,18 @@ class Frontier:
                     "bf_resident_eval")
         return result, {"ready": counts.ready, "skip": counts.skip, "expansion": counts.expansion, "evals": counts.evals}
 
+    def resident_tick(self, handle: int, L: A.Layout, n_runs: int, deltas: np.ndarray, result: Optional[np.ndarray] = None,
+                      flags: int = 0, max_iterations: int = 0):
+        """bf_resident_tick: deltas + pass + results in one call.  `deltas` must be a C-contiguous DELTA_DTYPE array
+        (pinned memory from alloc_pinned makes its upload asynchronous)."""
+        assert deltas.dtype == self.DELTA_DTYPE and deltas.flags["C_CONTIGUOUS"]
+        if result is None:
+            result = np.zeros((n_runs, L.result_stride), dtype=np.uint8)
+        counts = A.Counts()
+        self._check(self._lib.bf_resident_tick(self._ctx, handle, deltas.ctypes.data, deltas.shape[0], n_runs, flags, max_iterations,
+                                               result.ctypes.data, C.byref(counts)), "bf_resident_tick")
+        return result, {"ready": counts.ready, "skip": counts.skip, "expansion": counts.expansion, "evals": counts.evals}
+
     # -- redrive closure (row f3; storyrun_controller.go:535-558)
     def closure(self, slots, steps, words: int) -> np.ndarray:
         """bf_topology_closure: [count, words] uint32 masks of the steps a redrive from (slot, step) resets."""

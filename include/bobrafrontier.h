@@ -422,6 +422,10 @@ int bf_resident_apply(bf_ctx* ctx, uint32_t handle, const bf_delta* deltas, uint
  * counts.  flags = BF_EVAL_* (expansion is not offered on this path).  Also the batch bf_schedule refers to.     */
 int bf_resident_eval(bf_ctx* ctx, uint32_t handle, uint32_t n_runs, uint32_t flags, uint32_t max_iterations, void* result,
                      bf_counts* counts);
+/* A whole tick in one call and one synchronisation: apply n_deltas deltas (may be 0), run the pass, read the results
+ * (the kernels of later run chunks overlap the download of earlier ones).                                       */
+int bf_resident_tick(bf_ctx* ctx, uint32_t handle, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs, uint32_t flags,
+                     uint32_t max_iterations, void* result, bf_counts* counts);
 /* Read the device copy back (tests / resync checks).                                                            */
 int bf_resident_download(bf_ctx* ctx, uint32_t handle, uint32_t first_run, uint32_t n_runs, void* state_records);
 

@@ -76,11 +76,15 @@ def test_deltas_equal_full_upload(seed):
                 elif f == A.DELTA_CHILD: child[r, idx] = code
                 elif f == A.DELTA_RUN_FLAGS: rflags[r] = code
                 else: reg[r] = (int(reg[r]) & ~(1 << idx)) | (code << idx)
-            fr.resident_apply(h, d[rng.permutation(len(d))])
-            want_state = pack_state(L, slots, rflags, phase, cond, dec, child, reg)
-            assert np.array_equal(fr.resident_download(h, 0, n, L.state_stride), want_state), "tick %d: device copy differs" % tick
             flags = A.EVAL_FIXPOINT if tick % 2 else 0
-            got, gcounts = fr.resident_eval(h, L, n, flags=flags)
+            dp = np.ascontiguousarray(d[rng.permutation(len(d))])
+            want_state = pack_state(L, slots, rflags, phase, cond, dec, child, reg)
+            if tick % 2:   # the fused call: deltas + pass + results, one synchronisation
+                got, gcounts = fr.resident_tick(h, L, n, dp, flags=flags)
+            else:
+                fr.resident_apply(h, dp)
+                got, gcounts = fr.resident_eval(h, L, n, flags=flags)
+            assert np.array_equal(fr.resident_download(h, 0, n, L.state_stride), want_state), "tick %d: device copy differs" % tick
             want, wcounts = PK.evaluate(pt, L, want_state, flags, 0, threads=8)
             assert np.array_equal(got, want), "tick %d" % tick
             assert gcounts == wcounts
