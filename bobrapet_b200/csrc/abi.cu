@@ -135,6 +135,19 @@ int cuda_fail(bf_ctx* c, cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(c, e__, #call); \
   } while (0)
 
+// copy / compute streams and events of the chunked pipelines (bf_eval, bf_resident_tick); created on first use
+int ensure_pipe(bf_ctx* c) {
+  if (c->pipe_ready) return BF_OK;
+  if (!c->s_in) BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  if (!c->s_out) BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  for (uint32_t k = 0; k < bf_ctx::kMaxChunks; ++k) {
+    if (!c->ev_in[k]) BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+    if (!c->ev_k[k]) BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[k], cudaEventDisableTiming));
+  }
+  c->pipe_ready = true;
+  return BF_OK;
+}
+
 template <typename T>
 int ensure_dev(bf_ctx* c, T*& p, size_t& cap, size_t need_elems) {
   if (need_elems <= cap) return BF_OK;
@@ -469,9 +482,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
 
   // ---- shared-memory plan ----
   P.topo_buf_bytes = round_up(c->max_rec_bytes, 16);
-  uint32_t stage_pad = 0;
-  if (const char* e = getenv("BF_X_STAGE_PAD")) stage_pad = (uint32_t)atoi(e) & ~15u;  // experiment: shifts the alignment of the second stage
-  P.stage_bytes = L.state_stride + P.topo_buf_bytes + stage_pad;
+  P.stage_bytes = L.state_stride + P.topo_buf_bytes;
   const uint32_t work_general = round_up(4 * L.words, 16) + 32 * L.words + 16;  // fix-up mask words + status bytes (+ clamp guard)
   const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | ((uint32_t)quad << 9) | (L.fields << 16);
   if (c->plan_wpb == 0 || c->plan_key_stride != L.state_stride || c->plan_key_words != L.words ||
@@ -675,7 +686,8 @@ int bf_create(bf_ctx** out, const bf_config* cfg) {
   if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&c->d_counts, sizeof(bf_counts)) != cudaSuccess ||
       cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 2 * sizeof(bf_counts), cudaHostAllocDefault) != cudaSuccess) {
-    delete c;
+    cudaGetLastError();
+    bf_destroy(c);  // releases whatever was created
     return BF_ECUDA;
   }
   if (cfg && cfg->arena_bytes) {
@@ -691,9 +703,11 @@ void bf_destroy(bf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-  if (c->pipe_ready) {
-    cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
-    for (uint32_t k = 0; k < bf_ctx::kMaxChunks; ++k) { cudaEventDestroy(c->ev_in[k]); cudaEventDestroy(c->ev_k[k]); }
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  for (uint32_t k = 0; k < bf_ctx::kMaxChunks; ++k) {
+    if (c->ev_in[k]) cudaEventDestroy(c->ev_in[k]);
+    if (c->ev_k[k]) cudaEventDestroy(c->ev_k[k]);
   }
   cudaFreeHost(c->h_counts);
   cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
@@ -904,15 +918,8 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
     if (chunks > bf_ctx::kMaxChunks) chunks = bf_ctx::kMaxChunks;
     if (chunks < 1) chunks = 1;
   }
-  if (chunks > 1 && !c->pipe_ready) {
-    BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-    BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-    for (uint32_t k = 0; k < bf_ctx::kMaxChunks; ++k) {
-      BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
-      BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[k], cudaEventDisableTiming));
-    }
-    c->pipe_ready = true;
-  }
+  if (chunks > 1)
+    if (int rc = ensure_pipe(c)) return rc;
   bf_counts hc{};
   auto body = [&]() -> int {
     BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
@@ -1174,15 +1181,8 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
     if (chunks > bf_ctx::kMaxChunks) chunks = bf_ctx::kMaxChunks;
     if (chunks < 1) chunks = 1;
   }
-  if (chunks > 1 && !c->pipe_ready) {
-    BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-    BF_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-    for (uint32_t k = 0; k < bf_ctx::kMaxChunks; ++k) {
-      BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
-      BF_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[k], cudaEventDisableTiming));
-    }
-    c->pipe_ready = true;
-  }
+  if (chunks > 1)
+    if (int rc = ensure_pipe(c)) return rc;
   uint32_t* h_rej = reinterpret_cast<uint32_t*>(c->h_counts + 1);  // second pinned slot: h_counts is 2 x bf_counts
   auto body = [&]() -> int {
     if (int rc = resident_apply_async(c, r, deltas, n_deltas)) return rc;

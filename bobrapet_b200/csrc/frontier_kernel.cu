@@ -38,19 +38,16 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t ST = P.stages;
 
-  // ---- shared memory carve-up: [block counters 128 B][warp regions] ----
+  // ---- shared memory carve-up ----
   unsigned long long* blk_counts = reinterpret_cast<unsigned long long*>(smem_raw);
-#ifndef BF_X_BAR
-#define BF_X_BAR 2
-#endif
-  // per warp: ST stages of [state record | topology record], then scratch.  The stages' mbarriers live AWAY from
-  // the TMA destinations (a barrier next to the record tail costs ~9%: measured): BF_X_BAR 2 = one block for the
-  // whole CTA in front of the warp regions, 0 = behind each warp's scratch.
+  // [128 B counters][mbarriers: 64 B per warp][warp regions: ST stages of (state record | topology record), scratch].
+  // The stages' mbarriers live in one block for the whole CTA, AWAY from the TMA destinations: a barrier placed
+  // right behind a record's tail cost 9 % (measured A/B on the same box).
   const uint32_t ring_bytes = ST * P.stage_bytes;
-  const uint32_t per_warp = ring_bytes + P.work_bytes + (BF_X_BAR == 2 ? 0u : 64u);
-  uint8_t* const wbase = smem_raw + 128 + (BF_X_BAR == 2 ? P.warps_per_block * 64u : 0u) + warp * per_warp;
+  const uint32_t per_warp = ring_bytes + P.work_bytes;
+  uint8_t* const wbase = smem_raw + 128 + P.warps_per_block * 64u + warp * per_warp;
   const uint32_t wb = pin(smem_u32(wbase));  // pinned: otherwise rematerialised from S2R inside the loop
-  const uint32_t bar_base = pin(BF_X_BAR == 2 ? smem_u32(smem_raw) + 128u + warp * 64u : wb + ring_bytes + P.work_bytes);
+  const uint32_t bar_base = pin(smem_u32(smem_raw) + 128u + warp * 64u);
 
   if (threadIdx.x < 4) blk_counts[threadIdx.x] = 0ull;
   if (lane == 0) {
@@ -373,12 +370,15 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         __syncwarp();
         // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
         uint32_t met_w, fd_w;
+        // Two candidate words per loop trip (two independent load chains: +7 % at S = 1024 where one CTA per SM leaves
+        // little else to hide latency, +2 % at cfg3) except in the register-tight CD builds for two CTAs per SM (-1 %).
+        constexpr bool W2 = !(CD && OCC2);
         if (max_deg > 4) {  // warp-uniform: rows longer than the straight-line four exist in this topology
-          if (skip_on_failed) walk_rows_s<true, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
-          else walk_rows_s<false, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
+          if (skip_on_failed) walk_dispatch<W2, true, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
+          else walk_dispatch<W2, false, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
         } else {
-          if (skip_on_failed) walk_rows_s<true, false>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
-          else walk_rows_s<false, false>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
+          if (skip_on_failed) walk_dispatch<W2, true, false>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
+          else walk_dispatch<W2, false, false>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
         }
         uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
         if (CD) {
