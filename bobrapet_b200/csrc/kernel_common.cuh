@@ -218,53 +218,77 @@ DI void walk_rows_s(uint32_t lane, uint32_t CAND, uint32_t rp_addr, uint32_t col
 }
 
 
-// The same walk, two candidate words per loop trip so that two independent load chains overlap (more ILP per warp,
-// at the price of a wasted half trip when the word count is odd).
-template <bool NEED_FD, bool LONG_ROWS>
-DI void walk_rows_s2(uint32_t lane, uint32_t CAND, uint32_t rp_addr, uint32_t col_addr, uint32_t st_addr, uint32_t& met_w,
-                     uint32_t& fd_w) {
-  met_w = 0;
-  fd_w = 0;
-  uint32_t todo = __ballot_sync(FULL, CAND != 0);
-  const uint32_t rp_lane = rp_addr + lane * 2u;
-  while (todo) {
-    const uint32_t j1 = __ffs(todo) - 1;
+// K candidate words at once: K independent load chains in flight (ILP).  All K words exist (the driver below
+// only calls it with at least K left), so there is no wasted half trip.
+template <int K, bool NEED_FD, bool LONG_ROWS>
+DI void walk_group(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t rp_lane, uint32_t col_addr, uint32_t st_addr,
+                   uint32_t& met_w, uint32_t& fd_w) {
+  uint32_t j[K], e[K], n[K], w[K];
+  bool c[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    j[k] = __ffs(todo) - 1;
     todo &= todo - 1;
-    const bool two = todo != 0;
-    const uint32_t j2 = two ? __ffs(todo) - 1 : j1;
-    todo &= todo - 1;
-    const uint32_t cw1 = __shfl_sync(FULL, CAND, j1), cw2 = __shfl_sync(FULL, CAND, j2);
-    const bool c1 = (cw1 >> lane) & 1u, c2 = two && ((cw2 >> lane) & 1u);
-    uint32_t e1 = 0, n1 = 0, e2 = 0, n2 = 0;
-    if (c1) { const uint32_t a = rp_lane + j1 * 64u; e1 = lds_u16(a); n1 = lds_u16(a + 2u) - e1; }
-    if (c2) { const uint32_t a = rp_lane + j2 * 64u; e2 = lds_u16(a); n2 = lds_u16(a + 2u) - e2; }
-    const uint32_t p1 = col_addr + e1 * 2u, p2 = col_addr + e2 * 2u;
-    const uint32_t x0 = lds_u16(p1), x1 = lds_u16(p1 + 2u), x2 = lds_u16(p1 + 4u), x3 = lds_u16(p1 + 6u);
-    const uint32_t y0 = lds_u16(p2), y1 = lds_u16(p2 + 2u), y2 = lds_u16(p2 + 4u), y3 = lds_u16(p2 + 6u);
-    const uint32_t s0 = lds_u8(st_addr + x0), s1 = lds_u8(st_addr + x1), s2 = lds_u8(st_addr + x2), s3 = lds_u8(st_addr + x3);
-    const uint32_t t0 = lds_u8(st_addr + y0), t1 = lds_u8(st_addr + y1), t2 = lds_u8(st_addr + y2), t3 = lds_u8(st_addr + y3);
-    uint32_t w1 = (((s3 * 256u + s2) * 256u + s1) * 256u + s0) & bmsk_clamp(0u, n1 * 8u);
-    uint32_t w2 = (((t3 * 256u + t2) * 256u + t1) * 256u + t0) & bmsk_clamp(0u, n2 * 8u);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint32_t cw = __shfl_sync(FULL, CAND, j[k]);
+    c[k] = (cw >> lane) & 1u;
+    e[k] = 0; n[k] = 0;
+    if (c[k]) { const uint32_t a = rp_lane + j[k] * 64u; e[k] = lds_u16(a); n[k] = lds_u16(a + 2u) - e[k]; }
+  }
+  uint32_t x[K][4];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    // may run past the row (and, for the last rows, past E): every u16 there is another row's entry or the record's
+    // zero padding (device_record.h), i.e. a valid step index; the verdict is masked below
+    const uint32_t p = col_addr + e[k] * 2u;
+    x[k][0] = lds_u16(p); x[k][1] = lds_u16(p + 2u); x[k][2] = lds_u16(p + 4u); x[k][3] = lds_u16(p + 6u);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint32_t s0 = lds_u8(st_addr + x[k][0]), s1 = lds_u8(st_addr + x[k][1]), s2 = lds_u8(st_addr + x[k][2]), s3 = lds_u8(st_addr + x[k][3]);
+    w[k] = (((s3 * 256u + s2) * 256u + s1) * 256u + s0) & bmsk_clamp(0u, n[k] * 8u);
     if (LONG_ROWS) {
-      for (uint32_t e = 4; e < n1; ++e) w1 |= lds_u8(st_addr + lds_u16(p1 + e * 2u));
-      for (uint32_t e = 4; e < n2; ++e) w2 |= lds_u8(st_addr + lds_u16(p2 + e * 2u));
+      const uint32_t p = col_addr + e[k] * 2u;
+      for (uint32_t q = 4; q < n[k]; ++q) w[k] |= lds_u8(st_addr + lds_u16(p + q * 2u));
     }
-    const uint32_t m1 = __ballot_sync(FULL, c1 && (w1 & 0x01010101u) == 0), m2 = __ballot_sync(FULL, c2 && (w2 & 0x01010101u) == 0);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint32_t m = __ballot_sync(FULL, c[k] && (w[k] & 0x01010101u) == 0);
+    if (lane == j[k]) met_w = m;
     if (NEED_FD) {
-      const uint32_t f1 = __ballot_sync(FULL, (w1 & 0x02020202u) != 0), f2 = __ballot_sync(FULL, (w2 & 0x02020202u) != 0);
-      if (lane == j1) fd_w = f1;
-      if (two && lane == j2) fd_w = f2;
+      const uint32_t f = __ballot_sync(FULL, (w[k] & 0x02020202u) != 0);
+      if (lane == j[k]) fd_w = f;
     }
-    if (lane == j1) met_w = m1;
-    if (two && lane == j2) met_w = m2;
   }
 }
 
-template <bool TWO, bool NEED_FD, bool LONG_ROWS>
-DI void walk_dispatch(uint32_t lane, uint32_t CAND, uint32_t rp_addr, uint32_t col_addr, uint32_t st_addr, uint32_t& met_w,
-                      uint32_t& fd_w) {
-  if (TWO) walk_rows_s2<NEED_FD, LONG_ROWS>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
-  else walk_rows_s<NEED_FD, LONG_ROWS>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
+// Stage D driver: the candidate words of a run, KMAX at a time while that many are left, then 2, then 1.
+// KMAX = 1 is the plain walk; 2 pays at two CTAs per SM (+2 %), 4 where one CTA per SM leaves little else to hide
+// latency (S = 1024: +10 %).  Measured on B200, see DESIGN.md section 5.
+template <int KMAX, bool NEED_FD, bool LONG_ROWS>
+DI void walk_words(uint32_t lane, uint32_t CAND, uint32_t rp_addr, uint32_t col_addr, uint32_t st_addr, uint32_t& met_w,
+                   uint32_t& fd_w) {
+  met_w = 0;
+  fd_w = 0;
+  uint32_t todo = __ballot_sync(FULL, CAND != 0);  // words with at least one candidate step
+  const uint32_t rp_lane = rp_addr + lane * 2u;
+  if (KMAX >= 4)
+    while (__popc(todo) >= 4) walk_group<4, NEED_FD, LONG_ROWS>(lane, CAND, todo, rp_lane, col_addr, st_addr, met_w, fd_w);
+  if (KMAX >= 2) {
+    if (KMAX >= 4) {
+      if (__popc(todo) >= 2) walk_group<2, NEED_FD, LONG_ROWS>(lane, CAND, todo, rp_lane, col_addr, st_addr, met_w, fd_w);
+    } else {
+      while (__popc(todo) >= 2) walk_group<2, NEED_FD, LONG_ROWS>(lane, CAND, todo, rp_lane, col_addr, st_addr, met_w, fd_w);
+    }
+  }
+  if (KMAX >= 2) {
+    if (todo) walk_group<1, NEED_FD, LONG_ROWS>(lane, CAND, todo, rp_lane, col_addr, st_addr, met_w, fd_w);
+  } else {
+    while (todo) walk_group<1, NEED_FD, LONG_ROWS>(lane, CAND, todo, rp_lane, col_addr, st_addr, met_w, fd_w);
+  }
 }
 
 // ------------------------------------------------------------------ the same walk for packed lanes (R runs per trip)
