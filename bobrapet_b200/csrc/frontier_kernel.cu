@@ -370,14 +370,9 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         __syncwarp();
         // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
         uint32_t met_w, fd_w;
-        // words per walk group: see walk_words (kernel_common.cuh)
-#ifndef BF_X_K2
-#define BF_X_K2 2
-#endif
-#ifndef BF_X_KCD
-#define BF_X_KCD 1
-#endif
-        constexpr int WK = OCC2 ? (CD ? BF_X_KCD : BF_X_K2) : 4;
+        // candidate words per walk group (walk_words, kernel_common.cuh): 4 where one CTA per SM leaves little else to
+        // hide latency, 2 at two CTAs per SM, 1 in the register-tight CD builds for two CTAs (2 measured no faster)
+        constexpr int WK = OCC2 ? (CD ? 1 : 2) : 4;
         if (max_deg > 4) {  // warp-uniform: rows longer than the straight-line four exist in this topology
           if (skip_on_failed) walk_words<WK, true, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
           else walk_words<WK, false, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
