@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         if (has_dec) { const uint32_t dw = sr_a + P.off_decision + lane * 4u; d0 = lds_u32(dw); d1 = lds_u32(dw + ds); }
       }
     }
-    const uint32_t q0 = p0, q1 = p1, q2 = p2, q3 = p3;  // input planes (for the "changed" flag)
+    uint32_t gdirty = 0;  // steps whose code a stage-G rewrite really changed (for the "changed" flag; every other
+                          // rewrite of the pass sets `marked` and always changes the code)
     const uint32_t GM = VALID & ~G1 & ~G2;
     const uint32_t SYNC_T = t0 & (t1 | t2);          // sleep(3) | wait(5) | gate(7)
     const uint32_t T_COND = t0 & ~t1 & ~t2;          // 1
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
           const uint32_t n1 = d0 & ~(d1 & TS);
           const uint32_t n2 = d1 & (~d0 | TS);
           const uint32_t n3 = ~(d0 ^ d1);
+          gdirty |= syn & ((p0 ^ n0) | (p1 ^ n1) | (p2 ^ n2) | (p3 ^ n3));
           p0 = (p0 & ~syn) | (n0 & syn);
           p1 = (p1 & ~syn) | (n1 & syn);
           p2 = (p2 & ~syn) | (n2 & syn);
@@ -370,9 +372,9 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         __syncwarp();
         // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
         uint32_t met_w, fd_w;
-        // candidate words per walk group (walk_words, kernel_common.cuh): 4 where one CTA per SM leaves little else to
-        // hide latency, 2 at two CTAs per SM, 1 in the register-tight CD builds for two CTAs (2 measured no faster)
-        constexpr int WK = OCC2 ? (CD ? 1 : 2) : 4;
+        // candidate words per walk group (walk_words, kernel_common.cuh): 2 at two CTAs per SM, 4 where one CTA per
+        // SM leaves little else to hide latency
+        constexpr int WK = OCC2 ? 2 : 4;
         if (max_deg > 4) {  // warp-uniform: rows longer than the straight-line four exist in this topology
           if (skip_on_failed) walk_words<WK, true, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
           else walk_words<WK, false, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
@@ -448,9 +450,9 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
       }
       n_exp = redux_add(mine);
     }
-    // G rewrites (decision codes) are not tracked by `marked`: compare planes when they can occur
+    // G rewrites (decision codes) may write the code a step already has: `gdirty` holds the ones that really changed
     bool changed = marked;
-    if (CD) changed = __any_sync(FULL, ((p0 ^ q0) | (p1 ^ q1) | (p2 ^ q2) | (p3 ^ q3)) != 0);
+    if (CD) changed = __any_sync(FULL, gdirty != 0) || marked;
     summary |= (changed ? BF_SUM_PHASE_CHANGED : 0u) | (iters << BF_SUM_ITER_SHIFT);
     if (lane == 0) {
       *reinterpret_cast<uint4*>(rr) = make_uint4(summary, n_ready, n_skip, n_exp);
