@@ -389,12 +389,12 @@ def main():
     cpu = None
     if not args.no_cpu and rank == 0 and world == 1:
         sample = args.cpu_sample_runs or min(20_000, 250 * cores)
-        evals, times = cpu_arm(args, cfg, S, sample, cores, 3, "refshape")
-        ev8, t8 = cpu_arm(args, cfg, S, sample, min(8, cores), 3, "refshape")
+        evals, times = cpu_arm(args, cfg, S, sample, cores, 5, "refshape")
+        ev8, t8 = cpu_arm(args, cfg, S, sample, min(8, cores), 5, "refshape")
         evp, tp = cpu_arm(args, cfg, S, sample, cores, 5, "packed")
         cpu = {"value": evals / float(np.median(times)), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle/refshape.cc (reference-shaped: string-keyed maps, per-pass graph rebuild) on %d StoryRuns x %d steps, "
-                         "%d threads, median of 3; the Go reference itself cannot be built here" % (sample, S, cores),
+                         "%d threads, median of 5; the Go reference itself cannot be built here" % (sample, S, cores),
                "at_8_threads": ev8 / float(np.median(t8)),   # the reference's default MaxConcurrentReconciles
                "packed_cpu": {"value": evp / float(np.median(tp)), "threads": cores, "impl": "oracle/packed_ref.c (bitmask)"}}
 
