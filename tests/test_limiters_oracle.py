@@ -49,6 +49,18 @@ def test_kat_story_concurrency_queues_everything():
     assert res.launch == ["step-a", "step-b"] and not res.queued_story
 
 
+def test_kat_global_count_is_running_step_runs_only():
+    """dag_test.go:136-152: countRunningStepRunsGlobal lists StepRuns by the field selector status.phase=Running — the
+    global limiter sees Running StepRuns of every story and queue, and nothing else."""
+    sr = [LM.ClusterStepRun("a", "s1", "default", "Running"), LM.ClusterStepRun("b", "s2", "gpu", "Running"),
+          LM.ClusterStepRun("a", "s1", "default", "Succeeded"), LM.ClusterStepRun("a", "s1", "default", "Pending"),
+          LM.ClusterStepRun("a", "s1", "default", "")]
+    cfg = LM.SchedulingConfig(global_concurrency=3, queues={"default": LM.QueueConfig()})
+    srun = LM.ClusterStoryRun("r", "a", "default", "0", "Running")
+    ready, queued, reason = LM.enforce_scheduling_limits(sr, [srun], srun, "", 0, cfg, ["x", "y"], now=0.0)
+    assert ready == ["x"] and queued == ["y"] and "(2 running, limit 3)" in reason
+
+
 def test_scheduling_limit_reasons():
     """dag.go:1845-1859: which limit names the reason."""
     cfg = LM.SchedulingConfig(global_concurrency=3, queues={"default": LM.QueueConfig(2, 0, 0)})
