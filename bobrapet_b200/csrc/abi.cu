@@ -920,6 +920,8 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
   }
   if (chunks > 1)
     if (int rc = ensure_pipe(c)) return rc;
+  const char* shape_env = getenv("BF_E2E_SHAPE");
+  const bool taper = shape_env && !strcmp(shape_env, "taper");
   bf_counts hc{};
   auto body = [&]() -> int {
     BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
@@ -928,7 +930,15 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
     const uint8_t* hs = static_cast<const uint8_t*>(b->state);
     uint8_t* hr = static_cast<uint8_t*>(b->result);
     for (uint32_t k = 0; k < chunks; ++k) {
-      const size_t lo = (size_t)b->n_runs * k / chunks, hi = (size_t)b->n_runs * (k + 1) / chunks;
+      // chunk sizes shrink linearly (weights c, c-1, .., 1) when BF_E2E_SHAPE=taper: big early copies overlap best,
+      // a small last chunk leaves a short un-overlapped tail (kernel + download of that chunk)
+      size_t lo = (size_t)b->n_runs * k / chunks, hi = (size_t)b->n_runs * (k + 1) / chunks;
+      if (taper && chunks > 1) {
+        const uint64_t tot = (uint64_t)chunks * (chunks + 1) / 2;
+        auto cum = [&](uint32_t kk) { return (uint64_t)kk * chunks - (uint64_t)kk * (kk - 1) / 2; };  // sum of the first kk weights
+        lo = (size_t)((uint64_t)b->n_runs * cum(k) / tot);
+        hi = (size_t)((uint64_t)b->n_runs * cum(k + 1) / tot);
+      }
       const size_t so = lo * L.state_stride, ro = lo * L.result_stride;
       const size_t sb = (hi - lo) * L.state_stride, rb = (hi - lo) * L.result_stride;
       const bool piped = chunks > 1;
