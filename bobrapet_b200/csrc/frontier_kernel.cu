@@ -1,26 +1,24 @@
 // frontier_kernel.cu — the StoryRun ready-frontier pass for sm_100a.
 //
-// One WARP evaluates one StoryRun per trip of a persistent loop.  For every run the
-// warp's elected lane issues two cp.async.bulk (TMA) copies — the run's dynamic state
-// record and its Story topology record (CSR + bit-sliced static flags) — into a
-// per-warp, multi-stage shared-memory ring guarded by mbarriers; the copies of the
-// next runs are in flight while the current one is evaluated, so HBM streams at full
-// rate with no register staging.
+// One WARP evaluates one StoryRun per trip of a persistent loop.  For every run two cp.async.bulk (TMA) copies —
+// the run's dynamic state record and its Story topology record (CSR + bit-sliced static flags) — land in a
+// per-warp, multi-stage shared-memory ring guarded by mbarriers; the copies of the next runs are in flight while
+// the current one is evaluated, so HBM streams with no register staging.  The chain run -> slot id -> slot entry
+// is prefetched for 32 runs at a time (one run per lane) and the lane that owns a run issues its copies.
 //
-// Evaluation is BIT-SLICED: the 4-bit phase codes of a run are transposed into four
-// bit planes (one u32 word = 32 steps), after which every classification of
-// buildStateMaps (dag.go:3358-3391), the gate/sleep/wait rewrite (dag.go:1455-1547),
-// fail-fast / compensation marking and group selection (dag.go:422-511) are a
-// handful of LOP3s per 32 steps, held by lanes 0..W-1, and the per-run reductions of
-// group selection are ONE redux.or.  The dependency walk of findReadySteps
-// (dag.go:2711-2733) then runs one step per lane over the CSR row in shared memory
-// against a per-step status byte, and __ballot_sync folds the 32 per-step verdicts of a
-// trip straight into one word of the ready / skip bit masks.
+// Evaluation is BIT-SLICED: the 4-bit phase codes of a run arrive as four bit planes (one u32 word = 32 steps),
+// so every classification of buildStateMaps (dag.go:3358-3391), the gate/sleep/wait rewrite (dag.go:1455-1547),
+// fail-fast / compensation marking and group selection (dag.go:422-511) are a handful of LOP3s per 32 steps,
+// held by lanes 0..W-1, and the per-run reductions of group selection are ONE redux.or.  The dependency walk of
+// findReadySteps (dag.go:2711-2733) then runs one step per lane over the CSR row in shared memory against a
+// per-step status byte, several candidate words at a time (independent load chains), and __ballot_sync folds
+// the 32 per-step verdicts of a word straight into one word of the ready / skip bit masks.
 //
-// The kernel is compiled in 16 variants <CD, CH, FX, XO> (cond/decision codes present,
-// parallel steps present, device fixpoint, extra outputs) so the common pass carries
-// no dead work.  Integer only; no tensor cores.  HBM-bound: ~3 KB in, 80 B out per run
-// at the BASELINE configuration.  See DESIGN.md for the roofline accounting.
+// All shared-memory traffic of the loop uses 32-bit shared-window addresses (ld.shared / st.shared through inline
+// PTX).  The kernel is compiled in variants <CD, CH, FX, XO, LIST, OCC2> (cond/decision codes present, parallel
+// steps present, device fixpoint, extra outputs, run-list tier, build for two resident CTAs per SM) so the common
+// pass carries no dead work.  Integer only; no tensor cores.  ~3 KB in, 80 B out per run at the BASELINE
+// configuration; 78 % of the measured HBM copy peak there, bounded by instruction issue.
 #include "kernel_common.cuh"
 
 namespace bf {
@@ -115,7 +113,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
     for (uint32_t s = 0; s < ST; ++s) issue(wb + s * P.stage_bytes, bar_base + 8 * s);
   }
 
-  // scratch (per warp): fix-up fail mask words, then one status byte per step (+16 clamp guard)
+  // scratch (per warp): fix-up fail mask words, then one status byte per step (+16 guard bytes)
   // (all shared-memory traffic of the loop below goes through 32-bit shared-window addresses: no generic
   //  pointers, no cvta, no 64-bit address arithmetic)
   const uint32_t Wmax = P.words;
