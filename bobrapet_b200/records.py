@@ -21,6 +21,44 @@ def make_layout(steps_max: int, child_nibbles: int = 0, fields: int = 0) -> A.La
     return L
 
 
+def layout_py(steps_max: int, child_nibbles: int = 0, fields: int = 0) -> A.Layout:
+    """The rule of bf_layout_init restated in Python, for callers that must not load the CUDA library
+    (bench.py's CPU reference arm); tests/test_abi_symbols.py checks it field by field against bf_layout_init."""
+    def up(v, a):
+        return (v + a - 1) // a * a
+    L = A.Layout()
+    W = (steps_max + 31) // 32
+    L.steps_max, L.words, L.fields = steps_max, W, fields
+    L.child_nibbles = child_nibbles if fields & A.F_CHILD else 0
+    off = 16
+    L.off_phase = off
+    off += W * 16
+    L.off_cond = L.off_decision = L.off_child = A.OFF_NONE
+    if fields & A.F_COND:
+        L.off_cond = off
+        off += W * 8
+    if fields & A.F_DECISION:
+        L.off_decision = off
+        off += W * 8
+    if fields & A.F_CHILD:
+        L.off_child = off
+        off += up((L.child_nibbles + 1) // 2, 4)
+    L.state_stride = up(off, 16)
+    off = 16
+    L.off_ready = off
+    off += W * 4
+    L.off_skip = off
+    off += W * 4
+    L.off_fail = L.off_needs_cond = L.off_skip_dep = L.off_phase_out = A.OFF_NONE
+    for flag, name, size in ((A.F_OUT_FAIL, "off_fail", 4), (A.F_OUT_NEEDS_COND, "off_needs_cond", 4),
+                             (A.F_OUT_SKIP_DEP, "off_skip_dep", 4), (A.F_OUT_PHASE, "off_phase_out", 16)):
+        if fields & flag:
+            setattr(L, name, off)
+            off += W * size
+    L.result_stride = up(off, 16)
+    return L
+
+
 def _pack_nibbles(codes: np.ndarray, n_bytes: int) -> np.ndarray:
     """codes [N, C] (values 0..15) -> [N, n_bytes] with item i at byte i/2, low nibble first (child area)."""
     n, s = codes.shape

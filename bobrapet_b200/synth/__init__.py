@@ -13,6 +13,18 @@ from ..records import PAR_DTYPE
 _LIB = None
 _PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libsynth.so")
 
+
+def use_library(path: str) -> None:
+    """Load the generator from `path` instead (bench.py's CPU arm uses the copy built under oracle/_build so that
+    process maps nothing from bobrapet_b200/lib)."""
+    global _PATH, _LIB
+    _PATH, _LIB = path, None
+
+
+def set_threads(n: int) -> None:
+    """Runs are independent PRNG streams: generate them on `n` OpenMP threads."""
+    _lib().synth_set_threads(int(n))
+
 # (S, parallel steps P, branches B) of the named configurations
 CONFIGS = {1: (3, 0, 0), 2: (64, 0, 0), 3: (256, 0, 0), 4: (256, 0, 0), 5: (1024, 8, 128)}
 
@@ -30,6 +42,8 @@ def _lib():
         lib.synth_state.restype = None
         lib.synth_state.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(A.Layout), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        lib.synth_set_threads.restype = None
+        lib.synth_set_threads.argtypes = [C.c_int]
         _LIB = lib
     return _LIB
 

@@ -16,12 +16,17 @@
  * Paused 2 (%); i>=p: none 97 / Pending-queued 3; allowFailure on 10% of steps;
  * failFast false on 50% of runs.
  *
- * Build: gcc -O2 -shared -fPIC synth.c -o libsynth.so
+ * Runs are independent streams, so the loops over runs are OpenMP-parallel (synth_set_threads).
+ *
+ * Build: gcc -O2 -fopenmp -shared -fPIC synth.c -o libsynth.so
  */
 #include <stdint.h>
 #include <string.h>
 
 #include "../../include/bobrafrontier.h"
+
+static int g_threads = 1;
+void synth_set_threads(int t) { g_threads = t < 1 ? 1 : t; }
 
 static inline uint64_t sm64(uint64_t* s) {
   uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
@@ -91,6 +96,7 @@ static void topo_one(uint32_t cfg, uint64_t run, uint32_t S, uint32_t* row_ptr, 
 void synth_topologies(uint32_t cfg, uint64_t run_lo, uint32_t n, uint32_t S, uint32_t* row_ptr, uint16_t* col,
                       uint8_t* flags, bf_parallel_desc* par, uint8_t* allow_bits) {
   const uint32_t E = synth_edges(cfg, S);
+#pragma omp parallel for schedule(static) num_threads(g_threads)
   for (uint32_t r = 0; r < n; ++r) {
     topo_one(cfg, run_lo + r, S, row_ptr + (size_t)r * (S + 1), col + (size_t)r * E, flags + (size_t)r * S);
     if (cfg == 5 && par) {
@@ -126,6 +132,7 @@ static inline void put_code(uint8_t* base, uint32_t W, int nbits, uint32_t i, ui
 void synth_state(uint32_t cfg, uint64_t run_lo, uint32_t n, uint32_t S, const bf_layout* L, const uint32_t* slots,
                  const uint8_t* flags, const uint32_t* child_first, uint32_t P, uint32_t B, uint8_t* state) {
   memset(state, 0, (size_t)n * L->state_stride);
+#pragma omp parallel for schedule(static) num_threads(g_threads)
   for (uint32_t r = 0; r < n; ++r) {
     uint8_t* rec = state + (size_t)r * L->state_stride;
     bf_run_header* h = (bf_run_header*)rec;

@@ -39,3 +39,15 @@ def test_version_strerror_layout_without_gpu():
 def test_struct_sizes_match_header_comments():
     # bf_run_header / bf_result_header are 16 bytes (records start with them)
     assert make_layout(32, 0, 0).off_phase == 16 and make_layout(32, 0, 0).off_ready == 16
+
+
+def test_python_layout_rule_matches_bf_layout_init():
+    """records.layout_py (used by bench.py's CPU arm, which must not load the CUDA library) == bf_layout_init"""
+    import itertools
+    from bobrapet_b200.records import layout_py
+    import bench
+    assert (bench.F_COND, bench.F_DECISION, bench.F_CHILD) == (A.F_COND, A.F_DECISION, A.F_CHILD)
+    for S, child, fields in itertools.product((1, 31, 32, 33, 64, 256, 1000, 1024), (0, 8, 120, 1024),
+                                              (0, A.F_COND, A.F_DECISION | A.F_CHILD, A.F_COND | A.F_DECISION | A.F_CHILD | A.F_ALL_OUT,
+                                               A.F_OUT_FAIL | A.F_OUT_PHASE, A.F_CHILD | A.F_OUT_SKIP_DEP | A.F_OUT_NEEDS_COND)):
+        assert layout_py(S, child, fields).as_dict() == make_layout(S, child, fields).as_dict(), (S, child, fields)

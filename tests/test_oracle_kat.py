@@ -16,14 +16,73 @@ from bobrapet_b200.records import unpack_result
 from tests import packing as P
 
 
+# Backend of _packed_pass: "oracle" (CPU, pins the oracle) or "cuda" (marked gpu): the SAME transcribed dag_test.go
+# vectors go straight through bf_eval on the GPU and the reference's expected answers are asserted on the CUDA output
+# (the records are also compared byte for byte with the packed oracle).
+_BACKEND = {"name": "oracle", "frontier": None, "calls": 0}
+
+
+def _uses_packed_pass():
+    """names of this module's functions that reach _packed_pass (directly or through a helper)"""
+    import ast
+    import inspect
+    import sys
+    tree = ast.parse(inspect.getsource(sys.modules[__name__]))
+    calls = {}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef):
+            calls[node.name] = {n.func.id for n in ast.walk(node) if isinstance(n, ast.Call) and isinstance(n.func, ast.Name)}
+    reach = {"_packed_pass"}
+    changed = True
+    while changed:
+        changed = False
+        for fn, cs in calls.items():
+            if fn not in reach and cs & reach:
+                reach.add(fn)
+                changed = True
+    return reach
+
+
+_REACH = None
+
+
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)], autouse=True)
+def backend(request):
+    global _REACH
+    if request.param == "cuda":
+        if _REACH is None:
+            _REACH = _uses_packed_pass()
+        if request.function.__name__ not in _REACH:
+            pytest.skip("no packed vector in this test (oracle-only KAT)")
+        from bobrapet_b200 import Frontier
+        if _BACKEND["frontier"] is None:
+            _BACKEND["frontier"] = Frontier(0)
+    _BACKEND["name"], _BACKEND["calls"] = request.param, 0
+    yield request.param
+    if request.param == "cuda":
+        assert _BACKEND["calls"] > 0, "cuda variant ran without a bf_eval call"
+    _BACKEND["name"] = "oracle"
+
+
 def _packed_pass(story, srun, step_runs=None, evaluator=None, vars_=None, now=0.0, timers=None,
                  host_group=None, flags=0):
     ps = P.pack_story(story)
     ts = P.topology_set([ps])
-    pt = PK.PackedTopologies(ts)
     L, state = P.pack_runs([story], [ps], [srun], [0], [0], [step_runs], evaluator, vars_, now,
                            [timers], None, [host_group])
-    res, counts = PK.evaluate(pt, L, state, flags)
+    if _BACKEND["name"] == "cuda":
+        fr = _BACKEND["frontier"]
+        slots = fr.put_topologies(ts)
+        try:
+            state[:, 0:4] = np.ascontiguousarray(slots[:1], dtype="<u4").view(np.uint8)
+            res, counts = fr.eval(L, state, flags=flags | A.EVAL_VALIDATE)
+            want, wcounts = PK.evaluate(PK.PackedTopologies(ts, slots), L, state, flags)
+            assert np.array_equal(res, want) and counts == wcounts, "bf_eval differs from oracle/packed_ref.c on a reference KAT"
+        finally:
+            fr.drop_topology(int(slots[0]))
+        _BACKEND["calls"] += 1
+    else:
+        res, counts = PK.evaluate(PK.PackedTopologies(ts), L, state, flags)
     out = unpack_result(L, res, ps.S)
     names = ps.names
     pick = lambda key: [names[i] for i in np.nonzero(out[key][0])[0]]
