@@ -23,12 +23,7 @@ cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes
 cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, unsigned long long* offsets,
                              bf_expansion* out, unsigned long long cap, cudaStream_t stream, uint32_t* launches);
 int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes, uint32_t* occ2);
-cudaError_t launch_frontier_quad(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
-int frontier_quad_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
-uint32_t split_entry_bytes(const KParams& P);
-int walk_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes);
-cudaError_t launch_classify(const KParams& P, uint32_t sm_count, cudaStream_t stream);
-cudaError_t launch_walk(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_frontier_pack(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_apply_deltas(const DeltaParams& P, cudaStream_t stream);
 cudaError_t launch_schedule(const SchedParams& P, uint32_t sm_count, cudaStream_t stream);
 cudaError_t launch_closure(const Slot* slots, const uint32_t* slot_ids, const uint32_t* starts, uint32_t n, uint32_t n_slots,
@@ -79,10 +74,10 @@ struct bf_ctx {
   std::vector<bf::Slot> slots_host;
   bf::Slot* slots_dev = nullptr;
   size_t slots_dev_cap = 0;
-  std::vector<bf::SlotInfo> info_host;
-  bf::SlotInfo* info_dev = nullptr;
   bool slots_dirty = true;
-  uint32_t max_rec_bytes = 0;
+  uint32_t max_rec_bytes = 0;          // largest live record
+  uint32_t max_rec_by_w[33] = {};      // ... among the topologies of W = ceil(S/32) words (a batch of layout.words = w stages only W <= w)
+  bool rec_max_dirty = false;          // a drop may have lowered the maxima: recomputed at the next plan
   uint32_t n_alive = 0;
   uint32_t n_with_parallel = 0;  // live topologies that have parallel steps
 
@@ -97,9 +92,6 @@ struct bf_ctx {
   unsigned long long* d_offsets = nullptr; size_t d_offsets_cap = 0;
   unsigned long long* d_block_sums = nullptr; size_t d_block_sums_cap = 0;
   uint32_t* d_defer = nullptr; size_t d_defer_cap = 0;  // [0] = count, [1..] = run ids
-  uint8_t* d_walk = nullptr; size_t d_walk_cap = 0;      // phase-1 -> phase-2 entries
-  uint32_t* d_walk_count = nullptr;
-  uint32_t max_csr_bytes = 0;
 
   // limiters (bf_schedule): what the last bf_eval left on the device + scratch
   bool last_eval_valid = false;
@@ -115,7 +107,7 @@ struct bf_ctx {
 
   // cached shared-memory plan (recomputed when the layout or the largest record changes)
   uint32_t plan_key_stride = 0, plan_key_words = 0, plan_key_rec = 0, plan_key_variant = 0xFFFFFFFFu;
-  uint32_t plan_stages = 0, plan_wpb = 0, plan_per_sm = 0, plan_wq = 0, plan_lg = 0, plan_occ2 = 0;
+  uint32_t plan_stages = 0, plan_wpb = 0, plan_per_sm = 0, plan_occ2 = 0;
 
   bf_stats stats{};
 };
@@ -163,12 +155,15 @@ int ensure_dev(bf_ctx* c, T*& p, size_t& cap, size_t need_elems) {
 }
 
 // ---- record building -----------------------------------------------------------------------
+// BF_TOPO_FORMAT=csr keeps every topology in CSR form (A/B timing and the parity tests of that path); read per upload
+static bool force_csr() { const char* e = getenv("BF_TOPO_FORMAT"); return e && !strcmp(e, "csr"); }
+
 struct RecPlan {
-  uint32_t off_col, off_planes, off_par, off_allow, rec_bytes, W, child_nibbles;
+  uint32_t off_col, off_planes, off_par, off_allow, rec_bytes, W, child_nibbles, ell, max_deg;
   std::vector<uint32_t> child_first, allow_off;
 };
 
-int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_kahn = true) {
+int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_kahn = true, bool csr_only = false) {
   if (t.n_steps == 0 || t.n_steps > BF_MAX_STEPS) { why = "n_steps out of range (1..1024)"; return BF_ETOPO; }
   if (t.n_edges > BF_MAX_EDGES) { why = "n_edges exceeds 65535"; return BF_ETOPO; }
   if (!t.row_ptr || !t.step_flags || (t.n_edges && !t.col_idx)) { why = "null topology array"; return BF_EINVAL; }
@@ -221,12 +216,26 @@ int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_ka
   p.child_nibbles = round_up(nib, 8);
   p.W = (S + 31) / 32;
   uint32_t off = sizeof(bf::TopoHeader);
-  off += round_up(2 * (S + 1), 16);
-  p.off_col = off;
+  // Row format (device_record.h): fixed-width rows of K = 2 / 4 entries (no row_ptr; unused entries = PAD) when no step
+  // has more than K needs and the block is not larger than the CSR block it replaces, else CSR.
+  uint32_t md = 0;
+  for (uint32_t i = 0; i < S; ++i) { const uint32_t d = t.row_ptr[i + 1] - t.row_ptr[i]; if (d > md) md = d; }
+  p.max_deg = md;
   // + 4 zero entries: the branch-free walk fetches col[e0..e0+3] whatever the row length (e0 = E for trailing
   // rows without deps), so the last rows read past E; zero padding keeps every fetched index a valid step index
   // and the walk needs no clamp
-  off += round_up(2 * E + 8, 16);
+  const uint32_t csr_bytes = round_up(2 * (S + 1), 16) + round_up(2 * E + 8, 16);
+  const uint32_t K = md <= 2 ? 2u : (md <= 4 ? 4u : 0u);
+  p.ell = 0;
+  if (K && round_up(2 * K * S, 16) <= csr_bytes && !csr_only) p.ell = K;
+  if (p.ell) {
+    p.off_col = off;
+    off += round_up(2 * p.ell * S, 16);
+  } else {
+    off += round_up(2 * (S + 1), 16);
+    p.off_col = off;
+    off += round_up(2 * E + 8, 16);
+  }
   p.off_planes = off;
   off += round_up(bf::PL_COUNT * p.W * 4, 16);
   p.off_par = off;
@@ -247,16 +256,22 @@ void build_record(const bf_topology& t, const RecPlan& p, uint8_t* rec) {
   const uint32_t S = t.n_steps, E = t.n_edges, W = p.W;
   bf::TopoHeader h{};
   h.S = (uint16_t)S; h.W = (uint16_t)W; h.P = (uint16_t)t.n_parallel;
-  {
-    uint32_t md = 0;
-    for (uint32_t i = 0; i < S; ++i) { const uint32_t d = t.row_ptr[i + 1] - t.row_ptr[i]; if (d > md) md = d; }
-    h.max_deg = (uint16_t)(md > 0xFFFF ? 0xFFFF : md);
-  }
+  h.max_deg = (uint16_t)(p.max_deg > 0xFFFF ? 0xFFFF : p.max_deg);
   h.child_nibbles = (uint16_t)p.child_nibbles;
-  h.off_col = p.off_col; h.off_planes = p.off_planes; h.off_par = p.off_par; h.rec_bytes = p.rec_bytes;
-  uint16_t* rp = reinterpret_cast<uint16_t*>(rec + sizeof(bf::TopoHeader));
-  for (uint32_t i = 0; i <= S; ++i) rp[i] = (uint16_t)t.row_ptr[i];
-  if (E) memcpy(rec + p.off_col, t.col_idx, 2 * (size_t)E);
+  h.off_col = (uint16_t)p.off_col; h.ell = (uint16_t)p.ell; h.off_planes = p.off_planes; h.off_par = p.off_par; h.rec_bytes = p.rec_bytes;
+  if (p.ell) {
+    uint16_t* col = reinterpret_cast<uint16_t*>(rec + p.off_col);
+    const uint16_t pad = (uint16_t)(32 * W);  // the status byte just past the last step word: always "satisfied"
+    for (uint32_t i = 0; i < S; ++i) {
+      const uint32_t e0 = t.row_ptr[i], n = t.row_ptr[i + 1] - e0;
+      for (uint32_t k = 0; k < p.ell; ++k) col[i * p.ell + k] = k < n ? t.col_idx[e0 + k] : pad;
+    }
+    for (uint32_t x = S * p.ell; x < round_up(2 * p.ell * S, 16) / 2; ++x) col[x] = pad;
+  } else {
+    uint16_t* rp = reinterpret_cast<uint16_t*>(rec + sizeof(bf::TopoHeader));
+    for (uint32_t i = 0; i <= S; ++i) rp[i] = (uint16_t)t.row_ptr[i];
+    if (E) memcpy(rec + p.off_col, t.col_idx, 2 * (size_t)E);
+  }
   uint32_t* planes = reinterpret_cast<uint32_t*>(rec + p.off_planes);
   uint32_t nm = 0, nc = 0, nf = 0;
   for (uint32_t i = 0; i < S; ++i) {
@@ -312,7 +327,6 @@ int grow_arena(bf_ctx* c, size_t need_total) {
   for (size_t s = 0; s < c->meta.size(); ++s)
     if (c->meta[s].alive) {
       c->slots_host[s].addr = (uint64_t)(uintptr_t)(c->arena + c->meta[s].offset);
-      c->info_host[s].addr = c->slots_host[s].addr;
     }
   c->slots_dirty = true;
   return BF_OK;
@@ -328,14 +342,9 @@ int sync_slots(bf_ctx* c, cudaStream_t stream) {
     BF_CUDA(c, cudaMalloc(&np, ncap * sizeof(bf::Slot)));
     if (c->slots_dev) cudaFree(c->slots_dev);
     c->slots_dev = np;
-    bf::SlotInfo* ip = nullptr;
-    BF_CUDA(c, cudaMalloc(&ip, ncap * sizeof(bf::SlotInfo)));
-    if (c->info_dev) cudaFree(c->info_dev);
-    c->info_dev = ip;
     c->slots_dev_cap = ncap;
   }
   if (n) BF_CUDA(c, cudaMemcpyAsync(c->slots_dev, c->slots_host.data(), n * sizeof(bf::Slot), cudaMemcpyHostToDevice, stream));
-  if (n) BF_CUDA(c, cudaMemcpyAsync(c->info_dev, c->info_host.data(), n * sizeof(bf::SlotInfo), cudaMemcpyHostToDevice, stream));
   BF_CUDA(c, cudaStreamSynchronize(stream));
   c->slots_dirty = false;
   return BF_OK;
@@ -365,7 +374,23 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
              unsigned long long* d_counts, cudaStream_t stream) {
   const bf_layout& L = b.layout;
   if (int rc = sync_slots(c, stream)) return rc;
+  if (c->rec_max_dirty) {  // drops since the last plan: the largest live record per word count
+    c->max_rec_bytes = 0;
+    memset(c->max_rec_by_w, 0, sizeof c->max_rec_by_w);
+    for (const TopoMeta& m : c->meta)
+      if (m.alive) {
+        const uint32_t w = (m.S + 31) / 32;
+        if (m.bytes > c->max_rec_bytes) c->max_rec_bytes = m.bytes;
+        if (m.bytes > c->max_rec_by_w[w]) c->max_rec_by_w[w] = m.bytes;
+      }
+    c->rec_max_dirty = false;
+  }
   if (c->max_rec_bytes == 0) return fail(c, BF_ETOPO, "no topology has been uploaded");
+  // the largest record a run of this batch can stage: topologies wider than the layout are rejected by the kernels
+  uint32_t batch_rec_bytes = 0;
+  for (uint32_t w = 1; w <= L.words && w <= 32; ++w)
+    if (c->max_rec_by_w[w] > batch_rec_bytes) batch_rec_bytes = c->max_rec_by_w[w];
+  if (batch_rec_bytes == 0) batch_rec_bytes = 64;   // no topology fits the layout: every run will be marked dead
 
   bf::KParams P{};
   P.state = d_state; P.result = d_result; P.slots = c->slots_dev;
@@ -396,200 +421,132 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
     P.exp_counts = c->d_exp_counts;
   }
 
-  // ---- kernel choice: packed-lanes (R runs per warp trip) for single-pass batches without parallel
-  //      steps, the general one-run-per-warp kernel for fixpoint mode and parallel joins ----
-  // No parallel steps anywhere: packed-lanes only.  Only parallel-bearing topologies: general only.  Mixed:
-  // packed-lanes first, it defers the runs whose topology has parallel steps to a device list that the
-  // general kernel then takes (second launch; exits at once when the list is empty).
-  // Default: the general kernel (one run per warp).  The packed-lanes kernel executes ~17% fewer warp
-  // instructions per run but measured no faster (the same ~64 runs fit an SM's shared memory either way and
-  // its per-trip walk is longer), so it stays an opt-in experiment: BF_KERNEL=quad.
-  bool quad = false, split = false;
-  if (const char* env_k = getenv("BF_KERNEL")) {
-    if (!strcmp(env_k, "split")) split = !(b.flags & BF_EVAL_FIXPOINT) && c->n_with_parallel != c->n_alive;
-    if (!strcmp(env_k, "quad")) quad = !(b.flags & BF_EVAL_FIXPOINT) && c->n_with_parallel != c->n_alive;
-  }
-  if (split) {
-    // ---- two-phase path: classify every run, walk only the runs that have candidate steps ----
-    P.wq = 1; P.wq_log2 = 0;
-    while (P.wq < L.words) { P.wq <<= 1; P.wq_log2++; }
-    P.slot_info = c->info_dev;
-    P.walk_entry_bytes = bf::split_entry_bytes(P);
-    if (int rc = ensure_dev(c, c->d_walk, c->d_walk_cap, (size_t)b.n_runs * P.walk_entry_bytes + 16)) return rc;
-    if (!c->d_walk_count) BF_CUDA(c, cudaMalloc(&c->d_walk_count, 16));
-    P.walk_entries = c->d_walk; P.walk_count = c->d_walk_count;
-    const bool tiered = c->n_with_parallel != 0;
-    if (tiered) {
-      if (int rc = ensure_dev(c, c->d_defer, c->d_defer_cap, (size_t)b.n_runs + 1)) return rc;
-      P.defer_count = c->d_defer; P.defer_list = c->d_defer + 1;
-      BF_CUDA(c, cudaMemsetAsync(c->d_defer, 0, sizeof(uint32_t), stream));
-    }
-    BF_CUDA(c, cudaMemsetAsync(c->d_walk_count, 0, sizeof(uint32_t), stream));
-    // phase-2 shared-memory plan: stage = entry + CSR block
-    P.topo_buf_bytes = round_up(c->max_csr_bytes, 16);
-    P.work_bytes = round_up(4 * L.words, 16) + 32 * L.words + 16;
-    const uint32_t stage2 = P.walk_entry_bytes + P.topo_buf_bytes;
-    const uint32_t budget = 227u * 1024u - 128u;
-    uint32_t st = 2, wpb = 16;
-    if (const char* e = getenv("BF_STAGES")) st = (uint32_t)atoi(e);
-    if (const char* e = getenv("BF_WARPS")) wpb = (uint32_t)atoi(e);
-    if (st < 1) st = 1;
-    if (st > 8) st = 8;
-    while (wpb > 1 && 128 + wpb * (st * stage2 + P.work_bytes + 64) > budget / 2) wpb = wpb > 4 ? wpb - 4 : wpb - 1;  // aim at 2 CTAs per SM
-    while (st > 1 && 128 + wpb * (st * stage2 + P.work_bytes + 64) > budget) --st;
-    if (128 + wpb * (st * stage2 + P.work_bytes + 64) > budget) return fail(c, BF_ETOPO, "CSR block does not fit shared memory");
-    P.stages = st; P.warps_per_block = wpb;
-    const uint32_t smem2 = 128 + wpb * (st * stage2 + P.work_bytes + 64);
-    int per_sm = bf::walk_max_blocks_per_sm(P, wpb * 32, smem2);
-    if (per_sm < 1) per_sm = 1;
-    uint32_t grid2 = (uint32_t)c->sm_count * (uint32_t)per_sm;
-    const uint32_t nb2 = (b.n_runs + wpb - 1) / wpb;
-    if (grid2 > nb2) grid2 = nb2 ? nb2 : 1;
-    if (b.n_runs) {
-      BF_CUDA(c, bf::launch_classify(P, (uint32_t)c->sm_count, stream));
-      BF_CUDA(c, bf::launch_walk(P, grid2, smem2, stream));
-      c->stats.kernel_launches += 2;
-      if (tiered) {  // third tier: runs whose topology has parallel steps -> general kernel over the defer list
-        bf::KParams P2 = P;
-        P2.defer_list = nullptr; P2.defer_count = nullptr;
-        P2.run_list = c->d_defer + 1; P2.run_list_count = c->d_defer;
-        P2.topo_buf_bytes = round_up(c->max_rec_bytes, 16);
-        P2.stage_bytes = L.state_stride + P2.topo_buf_bytes;
-        uint32_t st3 = 2, wpb3 = 16;
-        while (wpb3 > 1 && 128 + wpb3 * (st3 * P2.stage_bytes + P2.work_bytes + 64) > budget) wpb3 = wpb3 > 4 ? wpb3 - 4 : wpb3 - 1;
-        if (128 + wpb3 * (st3 * P2.stage_bytes + P2.work_bytes + 64) > budget) st3 = 1;
-        if (128 + wpb3 * (st3 * P2.stage_bytes + P2.work_bytes + 64) > budget)
-          return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
-        P2.stages = st3; P2.warps_per_block = wpb3;
-        uint32_t grid3 = (uint32_t)c->sm_count;
-        const uint32_t nb3 = (b.n_runs + wpb3 - 1) / wpb3;
-        if (grid3 > nb3) grid3 = nb3 ? nb3 : 1;
-        BF_CUDA(c, bf::launch_frontier(P2, grid3, 128 + wpb3 * (st3 * P2.stage_bytes + P2.work_bytes + 64), stream));
-        c->stats.kernel_launches += 1;
-      }
-      if (want_exp) {
-        uint32_t nl = 0;
-        BF_CUDA(c, bf::launch_expansion(P, c->d_block_sums, c->d_offsets, d_exp, b.expansion_cap, stream, &nl));
-        c->stats.kernel_launches += nl;
-      }
-    }
-    c->stats.last_kernel = tiered ? 4u : 3u; c->stats.last_runs_per_trip = 32u / P.wq;
-    c->stats.last_grid = grid2; c->stats.last_block = wpb * 32; c->stats.last_smem_bytes = smem2; c->stats.last_stages = st;
-    return BF_OK;
-  }
-  uint32_t wq_min = 1, lg_min = 0;
-  while (wq_min < L.words) { wq_min <<= 1; lg_min++; }
-
-  // ---- shared-memory plan ----
-  P.topo_buf_bytes = round_up(c->max_rec_bytes, 16);
+  // ---- kernel choice ----
+  // Packed lanes (frontier_pack.cu, a group of R = 32 / Wq runs per warp trip) for single-pass batches whose records
+  // leave room for at least kMinGroups slot groups per SM; the one-run-per-warp kernel (frontier_kernel.cu) for the
+  // device fixpoint, for S > 512 and when every live topology has `parallel` steps.  Mixed batches: the packed kernel
+  // defers the runs whose topology has parallel steps to a device list that the general kernel then takes (second
+  // launch; exits at once when the list is empty).  BF_KERNEL=general forces the general kernel (A/B timing).
+  const uint32_t budget = 227u * 1024u;
+  const uint32_t work_general = round_up(4 * L.words, 16) + 32 * L.words + 16;  // fix-up mask words + status bytes + PAD guard
+  P.topo_buf_bytes = round_up(batch_rec_bytes, 16);
   P.stage_bytes = L.state_stride + P.topo_buf_bytes;
-  const uint32_t work_general = round_up(4 * L.words, 16) + 32 * L.words + 16;  // fix-up mask words + status bytes (+ clamp guard)
-  const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | ((uint32_t)quad << 9) | (L.fields << 16);
-  if (c->plan_wpb == 0 || c->plan_key_stride != L.state_stride || c->plan_key_words != L.words ||
-      c->plan_key_rec != c->max_rec_bytes || c->plan_key_variant != variant) {
-    // Plan: as many resident warps (x runs per warp trip) per SM as registers / shared memory allow — the pass
-    // is latency/issue bound before it is HBM bound — then ring depth: >= 2 stages keep the next trip's TMA
-    // copies in flight under the current evaluation.
-    const uint32_t budget = 227u * 1024u - 128u;
-    uint32_t best_st = 0, best_wpb = 0, best_score = 0, best_wq = 0, best_lg = 0, best_occ2 = 0;
-    int per_sm_q = 1;
-    const char* env_st = getenv("BF_STAGES");
-    const char* env_w = getenv("BF_WARPS");
-    const char* env_b = getenv("BF_BLOCKS_PER_SM");
-    const char* env_q = getenv("BF_WQ");
-    for (int pass = quad ? 0 : 1; pass < 2 && best_wpb == 0; ++pass) {
-      const bool q = pass == 0;
-      for (uint32_t wq = q ? wq_min : 32u, lgq = q ? lg_min : 5u; wq <= 32u; wq <<= 1, ++lgq) {
-        if (q && env_q && (uint32_t)atoi(env_q) != wq) continue;
-        const uint32_t R = q ? 32u / wq : 1u;
-        P.wq = wq; P.wq_log2 = lgq;
-        P.work_bytes = q ? 1424u : work_general;
-        for (uint32_t st = 1; st <= 4; ++st) {
-          if (env_st && (uint32_t)atoi(env_st) != st) continue;
-          for (uint32_t wpb = 16; wpb >= 1; wpb = (wpb > 4 ? wpb - 4 : wpb - 1)) {
-            if (env_w && (uint32_t)atoi(env_w) != wpb) continue;
-            const uint32_t smem_try = 128 + wpb * (st * R * P.stage_bytes + P.work_bytes + 64);
-            if (smem_try > budget + 128) continue;
-            uint32_t occ2 = 0;
-            int ctas = q ? bf::frontier_quad_max_blocks_per_sm(P, wpb * 32, smem_try) : bf::frontier_max_blocks_per_sm(P, wpb * 32, smem_try, &occ2);
-            if (ctas < 1) continue;
-            if (env_b && atoi(env_b) >= 1 && atoi(env_b) < ctas) ctas = atoi(env_b);
-            const uint32_t warps_sm = (uint32_t)ctas * wpb;
-            const uint32_t depth = st >= 3 ? 2 : st - 1;           // 0, 1, 2, 2
-            const uint32_t score = q ? (warps_sm * R > 128 ? 128 : warps_sm * R) * 8 + warps_sm * 2 + depth * 24 + (wpb >= 4 ? 2 : 0)
-                                     : warps_sm * 16 + depth * 24 + (wpb >= 8 ? 2 : 0) + (4 - st);
-            if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; per_sm_q = ctas; best_wq = wq; best_lg = lgq; best_occ2 = occ2; }
-          }
-        }
-        if (!q) break;
-      }
-      if (best_wpb == 0 && q) quad = false;  // the R-run stage does not fit: one run per warp
-    }
-    if (best_wpb == 0) return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
-    c->plan_stages = best_st; c->plan_wpb = best_wpb; c->plan_per_sm = (uint32_t)per_sm_q;
-    c->plan_wq = quad ? best_wq : 0; c->plan_lg = best_lg; c->plan_occ2 = best_occ2;
-    c->plan_key_stride = L.state_stride; c->plan_key_words = L.words; c->plan_key_rec = c->max_rec_bytes;
-    c->plan_key_variant = variant;
+  bool pack = !(b.flags & BF_EVAL_FIXPOINT) && L.words <= 16 && c->n_with_parallel != c->n_alive;
+  if (const char* env_k = getenv("BF_KERNEL")) pack = pack && strcmp(env_k, "general") != 0;
+  uint32_t wq = 1, lg = 0;
+  while (wq < L.words) { wq <<= 1; lg++; }
+  const uint32_t R = 32u / wq;
+  constexpr uint32_t kMinGroups = 8;
+  uint32_t nw = 16, ng = 0, pack_smem = 0;
+  if (pack) {
+    if (const char* e = getenv("BF_WARPS")) nw = (uint32_t)atoi(e);
+    if (nw < 1) nw = 1;
+    if (nw > 16) nw = 16;
+    const uint32_t group_bytes = R * P.stage_bytes;
+    const uint32_t work = 128u + 1024u + 32u * R;   // fix-up words | status bytes R x (32 Wq + 16) | walk table R x 16
+    auto groups_for = [&](uint32_t warps) -> uint32_t {   // slot groups that fit beside `warps` scratch areas
+      const uint32_t fixed = 128u + 768u + warps * work;      // 768: mbarriers + armed words of up to 64 groups
+      const uint32_t n = fixed < budget ? (budget - fixed) / group_bytes : 0;
+      return n > 64 ? 64 : n;
+    };
+    while (nw > 1 && groups_for(nw) < nw) --nw;               // never more warps than slot groups
+    ng = groups_for(nw);
+    if (const char* e = getenv("BF_GROUPS")) { const uint32_t v = (uint32_t)atoi(e); if (v >= nw && v <= ng) ng = v; }
+    if (ng < kMinGroups || ng < nw) pack = false;   // records too large for a useful ring: one run per warp instead
+    else pack_smem = 128u + round_up(ng * 12u, 128) + ng * group_bytes + nw * work;
+    P.work_bytes = work;
   }
-  quad = c->plan_wq != 0;
-  P.wq = quad ? c->plan_wq : 32u; P.wq_log2 = quad ? c->plan_lg : 5u;
-  P.work_bytes = quad ? 1424u : work_general;
-  const uint32_t R = quad ? 32u / P.wq : 1u;
-  const uint32_t stage_total = R * P.stage_bytes;
-  const bool two_tier = quad && c->n_with_parallel != 0;
-  if (two_tier) {
-    if (int rc = ensure_dev(c, c->d_defer, c->d_defer_cap, (size_t)b.n_runs + 1)) return rc;
-    P.defer_count = c->d_defer;
-    P.defer_list = c->d_defer + 1;
-  }
-  const uint32_t best_st = c->plan_stages, best_wpb = c->plan_wpb;
-  const int per_sm = (int)c->plan_per_sm;
-  P.stages = best_st;
-  P.warps_per_block = best_wpb;
-  P.occ2 = c->plan_occ2;
-  const uint32_t smem = 128 + best_wpb * (best_st * stage_total + P.work_bytes + 64);
-  uint32_t grid = (uint32_t)c->sm_count * (uint32_t)per_sm;
-  const uint32_t trips = (b.n_runs + R - 1) / R;
-  const uint32_t need_blocks = (trips + best_wpb - 1) / best_wpb;
-  if (grid > need_blocks) grid = need_blocks ? need_blocks : 1;
+  const bool two_tier = pack && c->n_with_parallel != 0;
 
-  if (b.n_runs) {
-    if (quad) {
+  // ---- shared-memory plan of the general kernel (also the second tier of a mixed batch) ----
+  uint32_t g_st = 0, g_wpb = 0, g_occ2 = 0;
+  int g_per_sm = 1;
+  if (!pack || two_tier) {
+    bf::KParams PG = P;
+    PG.work_bytes = work_general;
+    const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | (L.fields << 16);
+    if (c->plan_wpb == 0 || c->plan_key_stride != L.state_stride || c->plan_key_words != L.words ||
+        c->plan_key_rec != batch_rec_bytes || c->plan_key_variant != variant) {
+      // Plan: as many resident warps per SM as registers / shared memory allow — the pass is latency/issue bound
+      // before it is HBM bound — then ring depth: >= 2 stages keep the next trip's TMA copies in flight under the
+      // current evaluation.
+      uint32_t best_st = 0, best_wpb = 0, best_score = 0, best_occ2 = 0;
+      int best_ctas = 1;
+      const char* env_st = getenv("BF_STAGES");
+      const char* env_w = getenv("BF_WARPS");
+      const char* env_b = getenv("BF_BLOCKS_PER_SM");
+      for (uint32_t st = 1; st <= 4; ++st) {
+        if (env_st && (uint32_t)atoi(env_st) != st) continue;
+        for (uint32_t wpb = 16; wpb >= 1; wpb = (wpb > 4 ? wpb - 4 : wpb - 1)) {
+          if (env_w && !pack && (uint32_t)atoi(env_w) != wpb) continue;
+          const uint32_t smem_try = 128 + wpb * (st * P.stage_bytes + work_general + 64);
+          if (smem_try > budget) continue;
+          uint32_t occ2 = 0;
+          int ctas = bf::frontier_max_blocks_per_sm(PG, wpb * 32, smem_try, &occ2);
+          if (ctas < 1) continue;
+          if (env_b && atoi(env_b) >= 1 && atoi(env_b) < ctas) ctas = atoi(env_b);
+          const uint32_t warps_sm = (uint32_t)ctas * wpb;
+          const uint32_t depth = st >= 3 ? 2 : st - 1;           // 0, 1, 2, 2
+          const uint32_t score = warps_sm * 16 + depth * 24 + (wpb >= 8 ? 2 : 0) + (4 - st);
+          if (score > best_score) { best_score = score; best_st = st; best_wpb = wpb; best_ctas = ctas; best_occ2 = occ2; }
+        }
+      }
+      if (best_wpb == 0) return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
+      c->plan_stages = best_st; c->plan_wpb = best_wpb; c->plan_per_sm = (uint32_t)best_ctas; c->plan_occ2 = best_occ2;
+      c->plan_key_stride = L.state_stride; c->plan_key_words = L.words; c->plan_key_rec = batch_rec_bytes;
+      c->plan_key_variant = variant;
+    }
+    g_st = c->plan_stages; g_wpb = c->plan_wpb; g_occ2 = c->plan_occ2; g_per_sm = (int)c->plan_per_sm;
+  }
+  const uint32_t g_smem = 128 + g_wpb * (g_st * P.stage_bytes + work_general + 64);
+
+  uint32_t grid = 0, smem = 0;
+  if (pack) {
+    P.wq = wq; P.wq_log2 = lg; P.warps_per_block = nw; P.slot_groups = ng; P.stages = 1;
+    if (two_tier) {
+      if (int rc = ensure_dev(c, c->d_defer, c->d_defer_cap, (size_t)b.n_runs + 1)) return rc;
+      P.defer_count = c->d_defer;
+      P.defer_list = c->d_defer + 1;
+    }
+    const uint32_t n_groups = (b.n_runs + R - 1) / R;
+    grid = (uint32_t)c->sm_count < n_groups ? (uint32_t)c->sm_count : (n_groups ? n_groups : 1);
+    smem = pack_smem;
+    if (b.n_runs) {
       if (two_tier) BF_CUDA(c, cudaMemsetAsync(c->d_defer, 0, sizeof(uint32_t), stream));
-      BF_CUDA(c, bf::launch_frontier_quad(P, grid, smem, stream));
+      BF_CUDA(c, bf::launch_frontier_pack(P, grid, smem, stream));
       c->stats.kernel_launches += 1;
-      if (two_tier) {
-        // second tier: the general kernel over the deferred runs (its own shared-memory plan)
+      if (two_tier) {  // second tier: the general kernel over the deferred runs
         bf::KParams P2 = P;
         P2.defer_list = nullptr; P2.defer_count = nullptr;
         P2.run_list = c->d_defer + 1; P2.run_list_count = c->d_defer;
-        P2.work_bytes = round_up(4 * L.words, 16) + 32 * L.words + 16;
-        uint32_t st2 = 2, wpb2 = 16;
-        const uint32_t budget2 = 227u * 1024u - 128u;
-        while (wpb2 > 1 && 128 + wpb2 * (st2 * P.stage_bytes + P2.work_bytes + 64) > budget2) wpb2 = wpb2 > 4 ? wpb2 - 4 : wpb2 - 1;
-        if (128 + wpb2 * (st2 * P.stage_bytes + P2.work_bytes + 64) > budget2) st2 = 1;
-        if (128 + wpb2 * (st2 * P.stage_bytes + P2.work_bytes + 64) > budget2)
-          return fail(c, BF_ETOPO, "topology record + run state do not fit shared memory");
-        P2.stages = st2; P2.warps_per_block = wpb2;
-        const uint32_t smem2 = 128 + wpb2 * (st2 * P.stage_bytes + P2.work_bytes + 64);
+        P2.work_bytes = work_general; P2.stages = g_st; P2.warps_per_block = g_wpb; P2.occ2 = 0; P2.wq = 32; P2.wq_log2 = 5;
         uint32_t grid2 = (uint32_t)c->sm_count;
-        const uint32_t nb2 = (b.n_runs + wpb2 - 1) / wpb2;
+        const uint32_t nb2 = (b.n_runs + g_wpb - 1) / g_wpb;
         if (grid2 > nb2) grid2 = nb2 ? nb2 : 1;
-        BF_CUDA(c, bf::launch_frontier(P2, grid2, smem2, stream));
+        BF_CUDA(c, bf::launch_frontier(P2, grid2, g_smem, stream));
         c->stats.kernel_launches += 1;
       }
-    } else {
+    }
+  } else {
+    P.wq = 32u; P.wq_log2 = 5u; P.work_bytes = work_general;
+    P.stages = g_st; P.warps_per_block = g_wpb; P.occ2 = g_occ2;
+    grid = (uint32_t)c->sm_count * (uint32_t)g_per_sm;
+    const uint32_t need_blocks = (b.n_runs + g_wpb - 1) / g_wpb;
+    if (grid > need_blocks) grid = need_blocks ? need_blocks : 1;
+    smem = g_smem;
+    if (b.n_runs) {
       BF_CUDA(c, bf::launch_frontier(P, grid, smem, stream));
       c->stats.kernel_launches += 1;
     }
-    if (want_exp) {
-      uint32_t nl = 0;
-      BF_CUDA(c, bf::launch_expansion(P, c->d_block_sums, c->d_offsets, d_exp, b.expansion_cap, stream, &nl));
-      c->stats.kernel_launches += nl;
-    }
   }
-  c->stats.last_kernel = quad ? (two_tier ? 2u : 1u) : 0u; c->stats.last_runs_per_trip = R;
-  c->stats.last_grid = grid; c->stats.last_block = best_wpb * 32; c->stats.last_smem_bytes = smem; c->stats.last_stages = best_st;
+  if (b.n_runs && want_exp) {
+    uint32_t nl = 0;
+    BF_CUDA(c, bf::launch_expansion(P, c->d_block_sums, c->d_offsets, d_exp, b.expansion_cap, stream, &nl));
+    c->stats.kernel_launches += nl;
+  }
+  c->stats.last_kernel = pack ? (two_tier ? 2u : 1u) : 0u; c->stats.last_runs_per_trip = pack ? R : 1u;
+  c->stats.last_grid = grid; c->stats.last_block = (pack ? nw : g_wpb) * 32; c->stats.last_smem_bytes = smem;
+  c->stats.last_stages = pack ? ng : g_st;
   return BF_OK;
 }
 
@@ -597,8 +554,9 @@ int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_
   std::vector<RecPlan> plans(count);
   size_t total = 0;
   std::string why;
+  const bool csr_only = force_csr();
   for (uint32_t i = 0; i < count; ++i) {
-    const int rc = plan_record(topos[i], plans[i], why, host_kahn);
+    const int rc = plan_record(topos[i], plans[i], why, host_kahn, csr_only);
     if (rc != BF_OK) return fail(c, rc, "topology " + std::to_string(i) + ": " + why);
     total += plans[i].rec_bytes;
   }
@@ -616,26 +574,14 @@ int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_
   for (uint32_t i = 0; i < count; ++i) {
     uint32_t slot;
     if (!c->free_slots.empty()) { slot = c->free_slots.back(); c->free_slots.pop_back(); }
-    else { slot = (uint32_t)c->meta.size(); c->meta.emplace_back(); c->slots_host.push_back(bf::Slot{0, 0, 0}); c->info_host.push_back(bf::SlotInfo{0, 0, 0, 0, 0, 0, 0}); }
+    else { slot = (uint32_t)c->meta.size(); c->meta.emplace_back(); c->slots_host.push_back(bf::Slot{0, 0, 0}); }
     TopoMeta& m = c->meta[slot];
     m.alive = true; m.S = topos[i].n_steps; m.E = topos[i].n_edges; m.P = topos[i].n_parallel;
     m.bytes = plans[i].rec_bytes; m.offset = base + off; m.child_first = plans[i].child_first;
     m.child_nibbles = plans[i].child_nibbles;
     c->slots_host[slot] = bf::Slot{(uint64_t)(uintptr_t)(c->arena + m.offset), m.bytes, m.S | (m.P << 16)};
     if (m.bytes > c->max_rec_bytes) c->max_rec_bytes = m.bytes;
-    {
-      const bf::TopoHeader* th = reinterpret_cast<const bf::TopoHeader*>(staging.data() + off);
-      bf::SlotInfo si;
-      si.addr = c->slots_host[slot].addr;
-      si.csr_bytes = th->off_planes - (uint32_t)sizeof(bf::TopoHeader);
-      si.off_planes = th->off_planes;
-      si.s_w = (uint32_t)th->S | ((uint32_t)th->W << 16);
-      si.deg_p = (uint32_t)th->max_deg | ((uint32_t)th->P << 16);
-      si.main_comp = (uint32_t)th->n_main | ((uint32_t)th->n_comp << 16);
-      si.n_final = th->n_final;
-      c->info_host[slot] = si;
-      if (si.csr_bytes > c->max_csr_bytes) c->max_csr_bytes = si.csr_bytes;
-    }
+    if (m.bytes > c->max_rec_by_w[plans[i].W]) c->max_rec_by_w[plans[i].W] = m.bytes;
     off += plans[i].rec_bytes;
     slots_out[i] = slot;
     c->n_alive++;
@@ -711,7 +657,7 @@ void bf_destroy(bf_ctx* c) {
   }
   cudaFreeHost(c->h_counts);
   cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
-  cudaFree(c->d_defer); cudaFree(c->d_walk); cudaFree(c->d_walk_count); cudaFree(c->info_dev); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums); cudaFree(c->d_sched); cudaFree(c->d_deltas); cudaFree(c->d_rejected);
+  cudaFree(c->d_defer); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums); cudaFree(c->d_sched); cudaFree(c->d_deltas); cudaFree(c->d_rejected);
   for (Resident& r : c->resident) { cudaFree(r.d_state); cudaFree(r.d_result); }
   delete c;
 }
@@ -802,14 +748,12 @@ static int drop_locked(bf_ctx* c, uint32_t slot) {
   c->meta[slot].alive = false;
   if (c->meta[slot].P) c->n_with_parallel--;
   c->slots_host[slot] = bf::Slot{0, 0, 0};
-  c->info_host[slot] = bf::SlotInfo{0, 0, 0, 0, 0, 0, 0};
   c->free_slots.push_back(slot);
   c->n_alive--;
   c->slots_dirty = true;
+  c->rec_max_dirty = true;
   if (c->n_alive == 0) {  // arena is a bump allocator: it resets when the last topology goes
     c->arena_used = 0;
-    c->max_rec_bytes = 0;
-    c->max_csr_bytes = 0;
   }
   return BF_OK;
 }

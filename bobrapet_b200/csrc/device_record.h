@@ -2,18 +2,30 @@
 //
 // A topology (one Story generation: needs-adjacency + static step flags) is one
 // contiguous, 16-byte aligned, 16-byte padded record in the arena so that a warp
-// stages it into shared memory with ONE cp.async.bulk (TMA) copy:
+// stages it into shared memory with ONE cp.async.bulk (TMA) copy.  Two adjacency formats,
+// chosen per topology when it is uploaded (plan_record, abi.cu):
 //
+//   CSR (ell = 0)
 //   +0            TopoHeader (32 B)
 //   +32           row_ptr   u16[S+1]          CSR over allStorySteps (dag.go:3270), pad 16
 //   +off_col      col_idx   u16[E]            dependency step indices, then >= 4 zero entries, pad 16
+//
+//   fixed-width rows (ell = K in {2, 4}; taken when no step has more than K needs and S*K entries are not
+//   larger than the CSR block they replace): row_ptr is implicit (row i starts at entry i*K)
+//   +32 = off_col col_idx   u16[S][K]         the needs of step i, unused entries = PAD, pad 16
+//                                             PAD = 32*W: the status byte just past the last step word, always 0
+//                                             ("satisfied, not failed"), so a padded entry never changes a verdict
+//
+//   both
 //   +off_planes   planes    u32[8][W]         static step flags, BIT-SLICED (W = ceil(S/32)):
 //                                             t0,t1,t2 (type), AF, TS, HAS_IF, G1 (comp), G2 (finally)
 //                                             = S bytes, same size as the canonical u8 step_flags[S]
 //   +off_par      ParDesc[P] (16 B each) followed by the branch allowFailure bit words
 //
 // Canonical ("algorithmic") bytes per topology, SURVEY.md section 8(d):
-//   2*(S+1) + 2*E + S.  The header and the 16-byte paddings are overhead (~1.5% at cfg3).
+//   2*(S+1) + 2*E + S  (u16 CSR + u8 flags).  The CSR record adds the header and the 16-byte paddings
+//   (~1.5% at cfg3); the fixed-width record drops row_ptr, so it is SMALLER than the canonical figure
+//   (cfg3: 2 336 B against 2 798 B).
 #pragma once
 #include <stdint.h>
 
@@ -26,7 +38,8 @@ struct TopoHeader {
   uint16_t P;          // parallel descs
   uint16_t n_main, n_comp, n_final;
   uint16_t child_nibbles;  // total child nibbles of all descs
-  uint32_t off_col;
+  uint16_t off_col;    // byte offset of col_idx
+  uint16_t ell;        // 0 = CSR (row_ptr at +32), K = 2 / 4: fixed-width rows of K entries, no row_ptr
   uint32_t off_planes;
   uint32_t off_par;
   uint32_t rec_bytes;  // multiple of 16
@@ -51,31 +64,6 @@ struct Slot {          // device slot table entry
 };
 static_assert(sizeof(Slot) == 16, "Slot must be 16 bytes");
 
-// Wide slot entry for the two-phase path (frontier_split.cu): everything phase 1 needs about a topology
-// without touching its record header.
-struct SlotInfo {
-  uint64_t addr;        // record address (0 = dead slot)
-  uint32_t csr_bytes;   // bytes of row_ptr + col_idx (record bytes [32, off_planes))
-  uint32_t off_planes;
-  uint32_t s_w;         // S | W << 16
-  uint32_t deg_p;       // max_deg | P << 16
-  uint32_t main_comp;   // n_main | n_comp << 16
-  uint32_t n_final;
-};
-static_assert(sizeof(SlotInfo) == 32, "SlotInfo must be 32 bytes");
-
-// Phase-1 -> phase-2 hand-over entry header (followed by W-word arrays: CAND, U, FD [, c0, c1] [, HIF] [, p0..p3])
-struct WalkEntry {
-  uint64_t csr_addr;    // record address + 32 (row_ptr); col_idx follows, 16-byte aligned
-  uint32_t csr_bytes;
-  uint32_t run;
-  uint32_t meta;        // Wt | max_deg << 16
-  uint32_t summary;     // result-header summary computed by phase 1
-  uint32_t fclass;      // status class of a step set Failed in the loop (0 sat, 1 unmet, 3 unmet+failed-dep)
-  uint32_t col_off;     // byte offset of col_idx inside the CSR block
-};
-static_assert(sizeof(WalkEntry) == 32, "WalkEntry must be 32 bytes");
-
 struct KParams {
   const uint8_t* state;
   uint8_t* result;
@@ -88,11 +76,6 @@ struct KParams {
   uint32_t* defer_count;
   const uint32_t* run_list;
   const uint32_t* run_list_count;
-  // two-phase path
-  const SlotInfo* slot_info;
-  uint8_t* walk_entries;        // [n_runs * walk_entry_bytes], compacted by phase 1
-  uint32_t* walk_count;
-  uint32_t walk_entry_bytes;
   uint32_t n_slots;
   uint32_t n_runs;
   uint32_t flags;               // BF_EVAL_*
@@ -104,15 +87,16 @@ struct KParams {
   uint32_t result_tail;         // first byte after the last result field (padding up to the stride is zeroed)
   uint32_t result_stride, off_ready, off_skip, off_fail, off_needs_cond, off_skip_dep, off_phase_out;
   // shared-memory plan
-  uint32_t stages;
-  uint32_t topo_buf_bytes;      // per-stage room for a topology record
-  uint32_t stage_bytes;         // state_stride + topo_buf_bytes (multiple of 16)
+  uint32_t stages;              // general kernel: ring depth per warp
+  uint32_t topo_buf_bytes;      // per-run room for a topology record
+  uint32_t stage_bytes;         // general kernel: state_stride + topo_buf_bytes (multiple of 16)
   uint32_t work_bytes;          // per-warp scratch
   uint32_t warps_per_block;
-  uint32_t occ2;                // launch the build compiled for two resident CTAs per SM
-  uint32_t run_blocked;         // 1: a warp takes a contiguous block of runs, 0: every G-th run
-  // packed-lanes kernel (frontier_quad.cu): words per run rounded up to a power of two
+  uint32_t occ2;                // general kernel: launch the build compiled for two resident CTAs per SM
+  uint32_t run_blocked;         // general kernel: 1: a warp takes a contiguous block of runs, 0: every G-th run
+  // packed-lanes kernel (frontier_pack.cu): words per run rounded up to a power of two, slot groups per CTA
   uint32_t wq, wq_log2;
+  uint32_t slot_groups;
 };
 
 // resident.cu (row f2)

@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
       issue(cur_stage, cur_bar);
       continue;
     }
-    const uint4 h1 = lds_v4(tr_a + 16);                          // off_col, off_planes, off_par, rec_bytes
+    const uint4 h1 = lds_v4(tr_a + 16);                          // off_col | ell << 16, off_planes, off_par, rec_bytes
     const uint32_t rflags = lds_u8(sr_a + 4);
+    const uint32_t ell = h1.x >> 16;                             // 0 = CSR, 2 / 4 = fixed-width rows (device_record.h)
+    const int fmt = fmt_of(ell, max_deg);
 
     // ---------------- planes of word `lane`: dynamic codes (state record) + static flags (topology) ----------------
     const bool act = lane < Wt;
@@ -193,7 +195,8 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
     uint32_t summary = 0, iters = 0;
     bool marked = false;  // some phase was rewritten (lane-uniform)
     const uint32_t cap = FX ? (P.max_iter ? P.max_iter : S + 1) : 1u;
-    const uint32_t rp_a = tr_a + (uint32_t)sizeof(TopoHeader), col_a = tr_a + h1.x;  // CSR: row_ptr u16[S+1], col_idx u16[E]
+    const uint32_t rp_a = tr_a + (uint32_t)sizeof(TopoHeader), col_a = tr_a + (h1.x & 0xFFFFu);  // row_ptr u16[S+1] (CSR only), col_idx
+    if (ell && lane == 0) sts_u32(st_a + 32u * Wt, 0u);  // status byte PAD = 32*W: what unused row entries point at
 
     for (uint32_t it = 0; it < cap; ++it) {
       ++iters;
@@ -373,13 +376,8 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         // candidate words per walk group (walk_words, kernel_common.cuh): 2 at two CTAs per SM, 4 where one CTA per
         // SM leaves little else to hide latency
         constexpr int WK = OCC2 ? 2 : 4;
-        if (max_deg > 4) {  // warp-uniform: rows longer than the straight-line four exist in this topology
-          if (skip_on_failed) walk_words<WK, true, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
-          else walk_words<WK, false, true>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
-        } else {
-          if (skip_on_failed) walk_words<WK, true, false>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
-          else walk_words<WK, false, false>(lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
-        }
+        if (skip_on_failed) walk_words_fmt<WK, true>(fmt, lane, CAND, rp_a, col_a, st_a, met_w, fd_w);  // warp-uniform dispatch
+        else walk_words_fmt<WK, false>(fmt, lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
         uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
         if (CD) {
           ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
@@ -394,9 +392,13 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
               __syncwarp();
               if (act) sts_u32(mfail_a + lane * 4u, fail_w);
               __syncwarp();
-              walk_rows<true>(lane, CAND, 32u * Wt, max_deg, reinterpret_cast<const uint16_t*>(gptr(rp_a)),
-                              reinterpret_cast<const uint16_t*>(gptr(col_a)), gptr(st_a),
-                              reinterpret_cast<const uint32_t*>(gptr(mfail_a)), fclass, met_w, fd_w);
+              met_w = 0; fd_w = 0;
+              for (uint32_t todo = __ballot_sync(FULL, CAND != 0); todo; todo &= todo - 1) {
+                const uint32_t j = __ffs(todo) - 1;
+                uint32_t mb, fb;
+                fixup_item(lane, __shfl_sync(FULL, CAND, j), j, ell, rp_a, col_a, st_a, mfail_a, fclass, mb, fb);
+                if (lane == j) { met_w = mb; fd_w = fb; }
+              }
               const uint32_t nf = met_w & c0 & c1;
               const bool same = !__any_sync(FULL, nf != fail_w);
               fail_w = nf;

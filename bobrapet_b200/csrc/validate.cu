@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const Slot* sl
   }
   const uint8_t* rec = reinterpret_cast<const uint8_t*>(slots[sid].addr);
   const TopoHeader* th = reinterpret_cast<const TopoHeader*>(rec);
-  const uint32_t S = th->S, W = th->W;
+  const uint32_t S = th->S, W = th->W, ell = th->ell;  // ell: fixed-width rows, no row_ptr (device_record.h)
   const uint16_t* row_ptr = reinterpret_cast<const uint16_t*>(rec + sizeof(TopoHeader));
   const uint16_t* col = reinterpret_cast<const uint16_t*>(rec + th->off_col);
   uint32_t* done = done_s[warp];
@@ -40,8 +40,10 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const Slot* sl
     for (uint32_t i = lane, k = 0; i < S; i += 32, ++k) {
       if ((done[i >> 5] >> (i & 31u)) & 1u) continue;
       bool ok = true;
-      for (uint32_t e = row_ptr[i]; e < row_ptr[i + 1] && ok; ++e) {
+      const uint32_t e0 = ell ? i * ell : row_ptr[i], e1 = ell ? e0 + ell : row_ptr[i + 1];
+      for (uint32_t e = e0; e < e1 && ok; ++e) {
         const uint32_t d = col[e];
+        if (d >= S) continue;  // unused entry of a fixed-width row
         ok = (done[d >> 5] >> (d & 31u)) & 1u;
       }
       if (ok) newly |= 1u << k;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) closure_kernel(const Slot* slo
   if (sid >= n_slots || slots[sid].addr == 0) return;
   const uint8_t* rec = reinterpret_cast<const uint8_t*>(slots[sid].addr);
   const TopoHeader* th = reinterpret_cast<const TopoHeader*>(rec);
-  const uint32_t S = th->S, W = th->W, start = starts[t];
+  const uint32_t S = th->S, W = th->W, start = starts[t], ell = th->ell;
   if (start >= S || W > words_out) return;
   const uint16_t* row_ptr = reinterpret_cast<const uint16_t*>(rec + sizeof(TopoHeader));
   const uint16_t* col = reinterpret_cast<const uint16_t*>(rec + th->off_col);
@@ -98,9 +100,10 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) closure_kernel(const Slot* slo
     for (uint32_t i = lane; i < S; i += 32) {
       if ((sel[i >> 5] >> (i & 31u)) & 1u) continue;
       if (group_of(i) != g0) continue;
-      for (uint32_t e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+      const uint32_t e0 = ell ? i * ell : row_ptr[i], e1 = ell ? e0 + ell : row_ptr[i + 1];
+      for (uint32_t e = e0; e < e1; ++e) {
         const uint32_t d = col[e];
-        if ((sel[d >> 5] >> (d & 31u)) & 1u) {
+        if (d < S && ((sel[d >> 5] >> (d & 31u)) & 1u)) {
           atomicOr(&sel[i >> 5], 1u << (i & 31u));
           changed = true;
           break;

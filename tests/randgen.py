@@ -10,7 +10,9 @@ from oracle.packed import child_first_of
 
 
 def random_topologies(rng: np.random.Generator, count: int, s_min: int, s_max: int, max_deg: int = 5,
-                      groups: bool = True, parallel: bool = True, forward_refs: bool = True) -> TopologySet:
+                      groups: bool = True, parallel: bool = True, forward_refs: bool = True, fill: float = 0.0) -> TopologySet:
+    """fill: probability that a step takes the full max_deg needs (dense low-degree graphs qualify for the
+    fixed-width row format of the device records; sparse ones stay CSR)"""
     S_l, E_l, P_l, rp_l, ci_l, fl_l, par_l, allow_bits = [], [], [], [], [], [], [], []
     for _ in range(count):
         S = int(rng.integers(s_min, s_max + 1))
@@ -20,7 +22,7 @@ def random_topologies(rng: np.random.Generator, count: int, s_min: int, s_max: i
         rows = []
         for i in range(S):
             r = int(rank[i])
-            k = int(min(r, rng.integers(0, max_deg + 1)))
+            k = int(min(r, max_deg if rng.random() < fill else rng.integers(0, max_deg + 1)))
             if k and rng.random() < 0.7:  # local window, like real workflows
                 lo = max(0, r - 16)
                 cands = order[lo:r]

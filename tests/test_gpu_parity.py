@@ -24,16 +24,22 @@ def fr():
     f.close()
 
 
-@pytest.fixture(params=["general", "quad", "split"])
+@pytest.fixture(params=["pack-ell", "pack-csr", "general-ell", "general-csr"])
 def kernel(request, monkeypatch):
-    """general = the default one-run-per-warp kernel; quad = the opt-in packed-lanes kernel (R runs per warp trip,
-    runs whose topology has parallel steps deferred to the general kernel); split = the two-phase path (classify
-    every run, walk only runs with candidates).  All must equal the oracle."""
-    if request.param in ("quad", "split"):
-        monkeypatch.setenv("BF_KERNEL", request.param)
+    """pack = the default: packed lanes (a group of R runs per warp trip, frontier_pack.cu; runs whose topology has
+    parallel steps are deferred to the general kernel), general = the one-run-per-warp kernel forced for every run
+    (BF_KERNEL=general).  ell / csr = the row format of the topology records: fixed-width rows where they qualify
+    (the default) or CSR only (BF_TOPO_FORMAT=csr, read at upload).  All must equal the oracle."""
+    k, fmt = request.param.split("-")
+    if k == "general":
+        monkeypatch.setenv("BF_KERNEL", "general")
     else:
         monkeypatch.delenv("BF_KERNEL", raising=False)
-    return request.param
+    if fmt == "csr":
+        monkeypatch.setenv("BF_TOPO_FORMAT", "csr")
+    else:
+        monkeypatch.delenv("BF_TOPO_FORMAT", raising=False)
+    return k
 
 
 def _compare(fr, ts, slots, L, state, flags=0, max_iter=0, expansion=False):
@@ -90,7 +96,8 @@ def test_synthetic_configs(fr, kernel, cfg, n, S):
 def test_random_adversarial(fr, seed, mode):
     rng = np.random.default_rng(1000 + seed)
     smax = [40, 257, 1024, 96, 600, 33][seed]
-    ts = randgen.random_topologies(rng, 60, 1, smax)
+    deg, fill = [(5, 0.0), (4, 0.9), (5, 0.0), (2, 0.9), (4, 0.85), (5, 0.0)][seed]
+    ts = randgen.random_topologies(rng, 60, 1, smax, max_deg=deg, fill=fill)
     slots = fr.put_topologies(ts)
     L, state, _ = randgen.random_state(rng, ts, slots, 4000, ALL, phase_mix=("any" if seed % 2 else "progress"))
     _compare(fr, ts, slots, L, state, flags=(A.EVAL_FIXPOINT if mode == "fixpoint" else 0), expansion=True)
@@ -101,15 +108,18 @@ def test_random_adversarial_no_parallel(fr, kernel, seed):
     """all phase codes / groups / flags / FAIL codes, no parallel steps: the packed-lanes kernel's domain"""
     rng = np.random.default_rng(5000 + seed)
     smax = [40, 257, 1024, 96, 600, 33, 8, 130][seed]
-    ts = randgen.random_topologies(rng, 60, 1, smax, parallel=False)
+    # seeds 0-2: sparse rows up to 5 needs (CSR, long rows); 3-5: dense rows of <= 4 (fixed-width 4); 6-7: dense <= 2
+    deg, fill = [(5, 0.0), (5, 0.0), (5, 0.0), (4, 0.9), (4, 0.85), (4, 0.9), (2, 0.9), (2, 0.8)][seed]
+    ts = randgen.random_topologies(rng, 60, 1, smax, max_deg=deg, parallel=False, fill=fill)
     slots = fr.put_topologies(ts)
     n = [4000, 4001, 999, 4003, 1500, 4005, 4006, 4007][seed]
     L, state, _ = randgen.random_state(rng, ts, slots, n, ALL if seed % 3 else (A.F_COND | A.F_ALL_OUT),
                                        phase_mix=("any" if seed % 2 else "progress"))
     _compare(fr, ts, slots, L, state)
     st = fr.stats()
-    # the ctx also holds topologies with parallel steps (earlier tests): auto = packed lanes + deferred general
-    assert st["last_kernel"] == {"general": 0, "quad": 2, "split": 4}[kernel], st
+    # the ctx also holds topologies with parallel steps (earlier tests): packed lanes + deferred general; layouts wider
+    # than 16 words (S > 512) always take the general kernel
+    assert st["last_kernel"] == (2 if kernel == "pack" and L.words <= 16 else 0), st
 
 
 def test_minimal_layout_outputs_only_ready_skip(fr, kernel):
@@ -161,9 +171,15 @@ def test_topology_rejections(fr):
     assert "unknown step dependency" in str(e.value)                          # dag_test.go:206
 
 
-def test_packed_lanes_only_context(monkeypatch):
-    """a ctx whose topologies have no parallel steps runs the packed-lanes kernel alone (4 runs per trip at S=256)"""
-    monkeypatch.setenv("BF_KERNEL", "quad")
+@pytest.mark.parametrize("fmt", ["ell", "csr"])
+def test_packed_lanes_only_context(monkeypatch, fmt):
+    """a ctx whose topologies have no parallel steps runs the packed-lanes kernel alone (4 runs per trip at S=256, 16 at
+    S=64: the ring is planned from the largest record a run of the batch's layout can stage, not the ctx-wide largest)"""
+    monkeypatch.delenv("BF_KERNEL", raising=False)
+    if fmt == "csr":
+        monkeypatch.setenv("BF_TOPO_FORMAT", "csr")
+    else:
+        monkeypatch.delenv("BF_TOPO_FORMAT", raising=False)
     f = Frontier(0)
     try:
         ts = synth.topologies(4, 0, 3001, 256)
@@ -173,11 +189,41 @@ def test_packed_lanes_only_context(monkeypatch):
         _compare(f, ts, slots, L, state)
         st = f.stats()
         assert st["last_kernel"] == 1 and st["last_runs_per_trip"] == 4, st
+        _, nbytes = f.topology_record(int(slots[0]))
+        assert nbytes == (2336 if fmt == "ell" else 2864), nbytes     # 32 + 256 x 8 + 256 | 32 + 528 + 2048 + 256
         ts2 = synth.topologies(2, 0, 777, 64)
         s2 = f.put_topologies(ts2)
         L2 = make_layout(64, 0, A.F_ALL_OUT)
         _compare(f, ts2, s2, L2, synth.state(2, 0, 777, L2, s2, ts2))
-        assert f.stats()["last_runs_per_trip"] in (8, 16)  # the ctx-wide largest record bounds the stage
+        assert f.stats()["last_runs_per_trip"] == 16, f.stats()
+        # runs of mixed step counts and row formats inside one group (S = 5 .. 250, some rows longer than 4)
+        rng = np.random.default_rng(4242)
+        ts3 = randgen.random_topologies(rng, 25, 5, 250, parallel=False)
+        ts3b = randgen.random_topologies(rng, 25, 5, 250, max_deg=4, parallel=False, fill=0.9)
+        s3b = f.put_topologies(ts3b)
+        L3b, state3b, _ = randgen.random_state(rng, ts3b, s3b, 3001, ALL)
+        _compare(f, ts3b, s3b, L3b, state3b)
+        s3 = f.put_topologies(ts3)
+        L3, state3, _ = randgen.random_state(rng, ts3, s3, 5003, ALL)
+        _compare(f, ts3, s3, L3, state3)
+        assert f.stats()["last_kernel"] == 1, f.stats()
+    finally:
+        f.close()
+
+
+def test_group_tail_and_tiny_batches():
+    """batch sizes around the group size R and the CTA count: partial last group, fewer groups than warps / CTAs"""
+    f = Frontier(0)
+    try:
+        ts = synth.topologies(3, 0, 700, 256)
+        slots = f.put_topologies(ts)
+        L = make_layout(256, 0, A.F_ALL_OUT)
+        for n in (1, 2, 3, 4, 5, 63, 64, 65, 147 * 4 + 1, 148 * 4, 148 * 4 + 3, 700):
+            state = synth.state(3, 0, n, L, slots[:n], synth.topologies(3, 0, n, 256))
+            want, wc = PK.evaluate(PK.PackedTopologies(ts, slots), L, state, threads=4)
+            got, gc = f.eval(L, state)
+            assert np.array_equal(got, want) and gc == wc, n
+            assert f.stats()["last_kernel"] == 1
     finally:
         f.close()
 
