@@ -294,7 +294,10 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
     for k in range(ROT):
         ts = synth.topologies(cfg, run_lo + k * 10_000_019, n_topo, S)
         E = int(ts.E[0])
+        t_put = time.perf_counter()
         slots = fr.put_topologies(ts)
+        if k == 0:
+            put_ms = 1e3 * (time.perf_counter() - t_put)
         cf = fr.child_first(int(slots[0])) if int(ts.P[0]) else None
         if cf is not None:
             child = int((int(cf[-1]) + int(ts.parallel["branches"][int(ts.P[0]) - 1]) + 7) // 8 * 8)
@@ -480,6 +483,7 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
     live = Ctx()
     live.fr, live.sets, live.L, live.graph, live.graph_nc = fr, sets, L, graph, graph_nc
     live.timed_launches = int(round(steps * launches_per_pass))
+    live.topology_put_ms, live.counts0 = put_ms, counts_host
     return out, live
 
 
@@ -525,9 +529,26 @@ def e2e_legs(g, live, n_runs, S, steps):
     full = {"value": evals_per_pass * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": int(n_runs * Lk.state_stride),
             "d2h_bytes_per_step": int(n_runs * Lk.result_stride + 32), "steps": k_e2e,
             "api": "bf_eval (host buffers, synchronous): H2D of every state record + frontier kernel + D2H of every result record"}
-    e2e = dict(full)
-    # row f2 — the state stays resident on the device, a tick sends only deltas (1 % of all (run, step) phase codes
-    # change per tick) and reads the results back
+    legs = {"full_upload": full}
+    # compact results: (run, step, kind) events + one summary word per run instead of 80-byte mask records
+    ev_cap = int(1.5 * (live.counts0[0] + live.counts0[1])) + 65536
+    h_sum = fr.alloc_pinned(n_runs * 4).view(np.uint32)
+    h_ev = fr.alloc_pinned(ev_cap * 8).view(fr.EVENT_DTYPE)
+    n_ev = [0]
+
+    def call_compact(i):
+        n_ev[0] = fr.eval_compact(Lk, hs, ev_cap, summary=h_sum, events=h_ev)[2]
+    try:
+        dtc = timed_calls(call_compact)
+        legs["full_upload_compact"] = {"value": evals_per_pass * k_e2e / dtc, "unit": UNIT, "h2d_bytes_per_step": int(n_runs * Lk.state_stride),
+                                       "d2h_bytes_per_step": int(n_runs * 4 + n_ev[0] * 8 + 40), "events_per_step": int(n_ev[0]),
+                                       "api": "bf_eval_compact: H2D of every state record + kernels + D2H of summary words and (run, step, kind) events"}
+    except Exception as ex:
+        legs["full_upload_compact"] = {"error": str(ex)[:200]}
+    # row f2 — the steady-state tick of the operator: the state stays resident on the device, a tick sends only deltas
+    # (1 % of all (run, step) phase codes change per tick: a reconcile is triggered by ONE StepRun changing, 1 / 256 = 0.4 %
+    # of a run's codes) and reads the results back
+    e2e = None
     try:
         rng = np.random.default_rng(1234 + rank)
         hres = fr.resident_create(Lk, n_runs)
@@ -541,15 +562,31 @@ def e2e_legs(g, live, n_runs, S, steps):
             d["code"] = rng.choice([0, 2, 3, 3, 3, 4, 13], size=k_delta)
             dsets.append(d)
         dti = timed_calls(lambda i: fr.resident_tick(hres, Lk, n_runs, dsets[i % 3], hr))
-        e2e["incremental"] = {"value": evals_per_pass * k_e2e / dti, "unit": UNIT, "change_rate": 0.01,
-                              "h2d_bytes_per_step": int(k_delta * 8), "d2h_bytes_per_step": int(n_runs * Lk.result_stride + 32),
-                              "api": "bf_resident_tick (deltas + pass + results, one call): state stays on the device (row f2)"}
+        legs["incremental_dense"] = {"value": evals_per_pass * k_e2e / dti, "unit": UNIT, "change_rate": 0.01,
+                                     "h2d_bytes_per_step": int(k_delta * 8), "d2h_bytes_per_step": int(n_runs * Lk.result_stride + 32),
+                                     "api": "bf_resident_tick (deltas + pass + mask records, one call): state stays on the device (row f2)"}
+
+        def call_tick_compact(i):
+            n_ev[0] = fr.resident_tick_compact(hres, n_runs, dsets[i % 3], ev_cap, summary=h_sum, events=h_ev)[2]
+        dtk = timed_calls(call_tick_compact)
+        e2e = {"value": evals_per_pass * k_e2e / dtk, "unit": UNIT, "h2d_bytes_per_step": int(k_delta * 8),
+               "d2h_bytes_per_step": int(n_runs * 4 + n_ev[0] * 8 + 40), "steps": k_e2e, "change_rate": 0.01,
+               "events_per_step": int(n_ev[0]),
+               "api": "bf_resident_tick_compact (host buffers, synchronous): H2D of the tick's deltas (8 B per changed code) + scatter + "
+                      "frontier kernel + on-device compaction + D2H of one summary word per run and one 8-byte event per ready / skipped step"}
         fr.resident_destroy(hres)
         for d in dsets:
             fr.free_pinned(d.view(np.uint8))
-    except Exception as ex:  # never lose the contract line over a secondary leg
-        e2e["incremental"] = {"error": str(ex)[:200]}
-    e2e["full_upload"] = full
+    except Exception as ex:  # never lose the contract line over this leg: fall back to the full-upload figure, flagged
+        legs["incremental_error"] = str(ex)[:200]
+    if e2e is None:
+        e2e = dict(full)
+    e2e.update(legs)
+    e2e["topology_put_ms"] = live.topology_put_ms
+    e2e["topology_put_note"] = ("bf_topology_put_many of this rank's %d topologies (%.0f MB of records), once per Story generation, "
+                                "outside the per-tick figure" % (n_runs, live.fr.stats()["arena_used_bytes"] / 3e6))
+    fr.free_pinned(h_sum.view(np.uint8))
+    fr.free_pinned(h_ev.view(np.uint8))
     fr.free_pinned(hs.reshape(-1))
     fr.free_pinned(hr.reshape(-1))
     return e2e

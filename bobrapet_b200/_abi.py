@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BF_LIB") or os.path.join(_HERE, "lib", "libbobrafrontier.so")  # BF_LIB: A/B builds
 
-BF_ABI_VERSION = 2
+BF_ABI_VERSION = 3
 BF_OK, BF_EINVAL, BF_ENOMEM, BF_ECUDA, BF_ENCCL, BF_ETOPO, BF_ENODEV = 0, -1, -2, -3, -4, -5, -6
 
 # phase codes (pkg/enums/enums.go:44-97 order; 14 = Pending + "Queued due to ..." message)
@@ -97,6 +97,18 @@ class Stats(C.Structure):
                 ("last_eval_chunks", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
+EVT_READY, EVT_SKIP, EVT_FAIL, EVT_NEEDS_COND, EVT_SKIP_DEP = 0x1, 0x2, 0x4, 0x8, 0x10  # BF_EVT_*
+
+
+class StepEvent(C.Structure):
+    _fields_ = [("run", C.c_uint32), ("step", C.c_uint16), ("kind", C.c_uint16)]
+
+
+class CompactOut(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("summary", C.c_void_p), ("events", C.c_void_p),
+                ("events_cap", C.c_uint64), ("n_events", C.c_uint64)]
+
+
 class SchedTables(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_stories", C.c_uint32), ("n_queues", C.c_uint32), ("global_limit", C.c_int32),
                 ("global_running_base", C.c_uint32), ("story_limit", C.c_void_p), ("story_running_base", C.c_void_p),
@@ -138,6 +150,8 @@ SYMBOLS = [
     ("bf_resident_eval", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(Counts)]),
     ("bf_resident_tick", C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(Counts)]),
     ("bf_resident_download", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    ("bf_eval_compact", C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(CompactOut)]),
+    ("bf_resident_tick_compact", C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(CompactOut), C.POINTER(Counts)]),
     ("bf_alloc_pinned", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     ("bf_free_pinned", C.c_int, [C.c_void_p, C.c_void_p]),
     ("bf_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),

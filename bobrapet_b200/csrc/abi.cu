@@ -25,6 +25,7 @@ cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, u
 int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes, uint32_t* occ2);
 cudaError_t launch_frontier_pack(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_apply_deltas(const DeltaParams& P, cudaStream_t stream);
+cudaError_t launch_compact(const CompactParams& P, cudaStream_t stream);
 cudaError_t launch_schedule(const SchedParams& P, uint32_t sm_count, cudaStream_t stream);
 cudaError_t launch_closure(const Slot* slots, const uint32_t* slot_ids, const uint32_t* starts, uint32_t n, uint32_t n_slots,
                            uint32_t words_out, uint32_t* masks, cudaStream_t stream);
@@ -87,6 +88,11 @@ struct bf_ctx {
   unsigned long long* d_counts = nullptr;
   bf_counts* h_counts = nullptr;  // pinned landing zone for the counts block (a pageable target would make the copy synchronous)
   bf_expansion* d_exp = nullptr; size_t d_exp_cap = 0;
+  // compact results (bf_eval_compact / bf_resident_tick_compact)
+  uint32_t* d_summary = nullptr; size_t d_summary_cap = 0;
+  bf_step_event* d_events = nullptr; size_t d_events_cap = 0;
+  unsigned long long* d_cblock = nullptr; size_t d_cblock_cap = 0;   // [0] = total, [1..] = per-block sums
+  uint64_t last_events = 0;                                          // events of the previous compact pass (sizes the first D2H)
   // scratch shared by both entry points
   uint32_t* d_exp_counts = nullptr; size_t d_exp_counts_cap = 0;
   unsigned long long* d_offsets = nullptr; size_t d_offsets_cap = 0;
@@ -550,6 +556,44 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   return BF_OK;
 }
 
+// ---- compact results: masks -> events on the device, then the two small D2H copies ----
+// Enqueue on `s` (after the passes that wrote d_result): compaction kernels, D2H of the summary words, of the event total
+// and of a first slice of the event list sized from the previous pass (the total is only known after the sync).
+int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, uint32_t n_runs, bf_compact_out* out, cudaStream_t s,
+                    uint64_t* first_slice) {
+  const uint64_t cap = out->events ? out->events_cap : 0;
+  if (int rc = ensure_dev(c, c->d_summary, c->d_summary_cap, n_runs ? n_runs : 1)) return rc;
+  if (int rc = ensure_dev(c, c->d_events, c->d_events_cap, cap ? (size_t)cap : 1)) return rc;
+  if (int rc = ensure_dev(c, c->d_cblock, c->d_cblock_cap, (size_t)(n_runs + 511) / 512 + 2)) return rc;
+  bf::CompactParams P{};
+  P.result = d_result; P.summary = c->d_summary; P.events = c->d_events; P.cap = cap;
+  P.block_sums = c->d_cblock + 1; P.total = c->d_cblock;
+  P.n_runs = n_runs; P.words = L.words; P.result_stride = L.result_stride; P.off_ready = L.off_ready; P.off_skip = L.off_skip;
+  P.off_fail = L.off_fail; P.off_needs_cond = L.off_needs_cond; P.off_skip_dep = L.off_skip_dep;
+  BF_CUDA(c, bf::launch_compact(P, s));
+  c->stats.kernel_launches += n_runs ? 2 : 0;
+  unsigned long long* h_total = reinterpret_cast<unsigned long long*>(c->h_counts + 2);
+  BF_CUDA(c, cudaMemcpyAsync(h_total, c->d_cblock, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  if (out->summary && n_runs) BF_CUDA(c, cudaMemcpyAsync(out->summary, c->d_summary, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
+  uint64_t guess = c->last_events + c->last_events / 4 + 4096;
+  if (guess > cap) guess = cap;
+  if (guess) BF_CUDA(c, cudaMemcpyAsync(out->events, c->d_events, (size_t)guess * sizeof(bf_step_event), cudaMemcpyDeviceToHost, s));
+  *first_slice = guess;
+  return BF_OK;
+}
+// after the stream has been synchronised: fetch what the first slice missed
+int compact_finish(bf_ctx* c, bf_compact_out* out, uint64_t first_slice) {
+  const uint64_t total = *reinterpret_cast<const unsigned long long*>(c->h_counts + 2);
+  const uint64_t cap = out->events ? out->events_cap : 0;
+  const uint64_t have = total < cap ? total : cap;
+  if (have > first_slice)
+    BF_CUDA(c, cudaMemcpy(out->events + first_slice, c->d_events + first_slice, (size_t)(have - first_slice) * sizeof(bf_step_event),
+                          cudaMemcpyDeviceToHost));
+  out->n_events = total;
+  c->last_events = total;
+  return BF_OK;
+}
+
 int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_t* slots_out, bool host_kahn = true) {
   std::vector<RecPlan> plans(count);
   size_t total = 0;
@@ -631,7 +675,7 @@ int bf_create(bf_ctx** out, const bf_config* cfg) {
   c->stats.sm_count = (uint32_t)prop.multiProcessorCount;
   if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&c->d_counts, sizeof(bf_counts)) != cudaSuccess ||
-      cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 2 * sizeof(bf_counts), cudaHostAllocDefault) != cudaSuccess) {
+      cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 4 * sizeof(bf_counts), cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
     bf_destroy(c);  // releases whatever was created
     return BF_ECUDA;
@@ -658,6 +702,7 @@ void bf_destroy(bf_ctx* c) {
   cudaFreeHost(c->h_counts);
   cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
   cudaFree(c->d_defer); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums); cudaFree(c->d_sched); cudaFree(c->d_deltas); cudaFree(c->d_rejected);
+  cudaFree(c->d_summary); cudaFree(c->d_events); cudaFree(c->d_cblock);
   for (Resident& r : c->resident) { cudaFree(r.d_state); cudaFree(r.d_result); }
   delete c;
 }
@@ -816,12 +861,14 @@ int bf_eval_device(bf_ctx* c, const bf_batch* b, void* stream) {
                   reinterpret_cast<unsigned long long*>(b->counts), static_cast<cudaStream_t>(stream));
 }
 
-int bf_eval(bf_ctx* c, const bf_batch* b) {
+static int eval_host(bf_ctx* c, const bf_batch* b, bf_compact_out* co) {
   if (!c) return BF_EINVAL;
   std::lock_guard<std::mutex> g(c->mu);
   if (!b || b->struct_size != sizeof(bf_batch)) return fail(c, BF_EINVAL, "bad bf_batch.struct_size");
+  if (co && co->struct_size != sizeof(bf_compact_out)) return fail(c, BF_EINVAL, "bad bf_compact_out.struct_size");
+  if (co && co->events_cap && !co->events) return fail(c, BF_EINVAL, "null events with a non-zero events_cap");
   if (int rc = check_layout(c, b->layout)) return rc;
-  if (b->n_runs && (!b->state || !b->result)) return fail(c, BF_EINVAL, "null state/result");
+  if (b->n_runs && (!b->state || (!b->result && !co))) return fail(c, BF_EINVAL, "null state/result");
   c->last_eval_valid = false;
   const bf_layout& L = b->layout;
   const size_t sbytes = (size_t)b->n_runs * L.state_stride, rbytes = (size_t)b->n_runs * L.result_stride;
@@ -867,6 +914,7 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
   const char* shape_env = getenv("BF_E2E_SHAPE");
   const bool taper = shape_env && !strcmp(shape_env, "taper");
   bf_counts hc{};
+  uint64_t first_slice = 0;
   auto body = [&]() -> int {
     BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
     bf_batch db = *b;
@@ -897,9 +945,11 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
         BF_CUDA(c, cudaEventRecord(c->ev_k[k], s));
         BF_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
       }
-      if (rb) BF_CUDA(c, cudaMemcpyAsync(hr + ro, c->d_result + ro, rb, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
+      if (rb && !co) BF_CUDA(c, cudaMemcpyAsync(hr + ro, c->d_result + ro, rb, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
     }
     BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof hc, cudaMemcpyDeviceToHost, s));
+    if (co)
+      if (int rc = compact_enqueue(c, L, c->d_result, b->n_runs, co, s, &first_slice)) return rc;
     return BF_OK;
   };
   const int body_rc = body();
@@ -920,7 +970,14 @@ int bf_eval(bf_ctx* c, const bf_batch* b) {
     if (n) BF_CUDA(c, cudaMemcpy(b->expansion, c->d_exp, (size_t)n * sizeof(bf_expansion), cudaMemcpyDeviceToHost));
   }
   if (b->counts) *b->counts = hc;
+  if (co) return compact_finish(c, co, first_slice);
   return BF_OK;
+}
+
+int bf_eval(bf_ctx* c, const bf_batch* b) { return eval_host(c, b, nullptr); }
+int bf_eval_compact(bf_ctx* c, const bf_batch* b, bf_compact_out* out) {
+  if (!out) return c ? fail(c, BF_EINVAL, "null bf_compact_out") : BF_EINVAL;
+  return eval_host(c, b, out);
 }
 
 // ---- limiters (rows a9 / f4) ----------------------------------------------------------------------------
@@ -1119,9 +1176,11 @@ int bf_resident_apply(bf_ctx* c, uint32_t h, const bf_delta* deltas, uint32_t n)
 // deltas (optional) + one pass + results, one synchronisation: the pass is cut into run chunks whose kernels overlap
 // the download of the previous chunk's result records (as bf_eval does for both directions)
 static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs, uint32_t flags,
-                                uint32_t max_iterations, void* result, bf_counts* counts) {
+                                uint32_t max_iterations, void* result, bf_counts* counts, bf_compact_out* co = nullptr) {
   c->last_eval_valid = false;
-  if (n_runs > r->cap || (n_runs && !result)) return fail(c, BF_EINVAL, "n_runs exceeds the resident batch / null result");
+  if (co && co->struct_size != sizeof(bf_compact_out)) return fail(c, BF_EINVAL, "bad bf_compact_out.struct_size");
+  if (co && co->events_cap && !co->events) return fail(c, BF_EINVAL, "null events with a non-zero events_cap");
+  if (n_runs > r->cap || (n_runs && !result && !co)) return fail(c, BF_EINVAL, "n_runs exceeds the resident batch / null result");
   if (flags & BF_EVAL_EXPANSION) return fail(c, BF_EINVAL, "expansion is not offered on the resident path");
   if (n_deltas && !deltas) return fail(c, BF_EINVAL, "null deltas");
   BF_CUDA(c, cudaSetDevice(c->device));
@@ -1129,7 +1188,8 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
   const bf_layout& L = r->L;
   const size_t rbytes = (size_t)n_runs * L.result_stride;
   uint32_t chunks = 1;
-  if (rbytes >= (2u << 20)) {
+  uint64_t first_slice = 0;
+  if (!co && rbytes >= (2u << 20)) {
     chunks = (uint32_t)((rbytes + (1u << 20)) / (2u << 20));   // ~2 MB of result records per chunk
     if (const char* e = getenv("BF_E2E_CHUNKS")) chunks = (uint32_t)atoi(e);
     if (chunks > bf_ctx::kMaxChunks) chunks = bf_ctx::kMaxChunks;
@@ -1153,11 +1213,13 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
         BF_CUDA(c, cudaEventRecord(c->ev_k[k], s));
         BF_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
       }
-      if (hi > lo)
+      if (hi > lo && !co)
         BF_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(result) + lo * L.result_stride, r->d_result + lo * L.result_stride,
                                    (hi - lo) * L.result_stride, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
     }
     BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(bf_counts), cudaMemcpyDeviceToHost, s));
+    if (co)
+      if (int rc2 = compact_enqueue(c, L, r->d_result, n_runs, co, s, &first_slice)) return rc2;
     BF_CUDA(c, cudaMemcpyAsync(h_rej, c->d_rejected, 4, cudaMemcpyDeviceToHost, s));
     return BF_OK;
   };
@@ -1173,6 +1235,8 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
   c->stats.last_eval_chunks = chunks;
   c->last_eval_valid = true; c->last_eval_runs = n_runs; c->last_eval_layout = L;
   c->last_state = r->d_state; c->last_result = r->d_result;
+  if (co)
+    if (int rc2 = compact_finish(c, co, first_slice)) return rc2;
   if (n_deltas && *h_rej) return fail(c, BF_EINVAL, std::to_string(*h_rej) + " delta(s) outside the record (run, index, code or absent field); the others were applied and the pass ran");
   return BF_OK;
 }
@@ -1192,6 +1256,16 @@ int bf_resident_tick(bf_ctx* c, uint32_t h, const bf_delta* deltas, uint32_t n_d
   Resident* r = resident_of(c, h);
   if (!r) return fail(c, BF_EINVAL, "unknown resident batch");
   return resident_tick_locked(c, r, deltas, n_deltas, n_runs, flags, max_iterations, result, counts);
+}
+
+int bf_resident_tick_compact(bf_ctx* c, uint32_t h, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs, uint32_t flags,
+                             uint32_t max_iterations, bf_compact_out* out, bf_counts* counts) {
+  if (!c) return BF_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!out) return fail(c, BF_EINVAL, "null bf_compact_out");
+  Resident* r = resident_of(c, h);
+  if (!r) return fail(c, BF_EINVAL, "unknown resident batch");
+  return resident_tick_locked(c, r, deltas, n_deltas, n_runs, flags, max_iterations, nullptr, counts, out);
 }
 
 int bf_alloc_pinned(bf_ctx* c, size_t bytes, void** out) {

@@ -99,6 +99,17 @@ struct KParams {
   uint32_t slot_groups;
 };
 
+// compact.cu: result records -> (run, step, kind) events + one summary word per run
+struct CompactParams {
+  const uint8_t* result;
+  uint32_t* summary;                 // [n_runs] or nullptr
+  bf_step_event* events;             // [cap]
+  unsigned long long cap;
+  unsigned long long* block_sums;    // scratch: ceil(n_runs / 512)
+  unsigned long long* total;         // out: events of the batch
+  uint32_t n_runs, words, result_stride, off_ready, off_skip, off_fail, off_needs_cond, off_skip_dep;
+};
+
 // resident.cu (row f2)
 struct DeltaParams {
   uint8_t* state;

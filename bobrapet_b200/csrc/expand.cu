@@ -4,7 +4,7 @@
 // with.steps, in branch order.  The frontier kernel leaves a per-run expansion count;
 // here an exclusive scan turns the counts into offsets and a second kernel writes the
 // (run, step, branch) tuples in (run, step, branch) order — deterministic, so the
-// tuple list is bit-exact against the oracle.
+// tuple list is bit-exact against the oracle.  Two launches: per-block totals, then scan + emit.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -50,36 +50,29 @@ __global__ void __launch_bounds__(SCAN_BLOCK) exp_block_sums(const uint32_t* cou
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
-// exclusive scan of block_sums in place, single block, any length
-__global__ void __launch_bounds__(SCAN_BLOCK) exp_scan_block_sums(unsigned long long* block_sums, uint32_t nb) {
-  unsigned long long carry = 0;
-  for (uint32_t base = 0; base < nb; base += SCAN_BLOCK) {
-    const uint32_t i = base + threadIdx.x;
-    const unsigned long long v = i < nb ? block_sums[i] : 0ull;
-    unsigned long long tot;
-    const unsigned long long inc = block_incl_scan(v, &tot);
-    if (i < nb) block_sums[i] = carry + inc - v;
-    carry += tot;
-  }
-}
-
-__global__ void __launch_bounds__(SCAN_BLOCK) exp_offsets(const uint32_t* counts, uint32_t n, const unsigned long long* block_sums,
-                                                          unsigned long long* offsets) {
+// Second launch: block b sums the totals of the blocks before it, scans its own 1024 runs in shared memory and its warps
+// emit the tuples: one warp per group of 32 runs, runs with a non-zero count are expanded cooperatively.
+__global__ void __launch_bounds__(SCAN_BLOCK) exp_scan_emit(const KParams P, const unsigned long long* block_sums, bf_expansion* out,
+                                                            unsigned long long cap) {
+  __shared__ unsigned long long off_s[SCAN_BLOCK];
+  __shared__ unsigned long long part_s[32];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  unsigned long long part = 0;
+  for (uint32_t b = threadIdx.x; b < blockIdx.x; b += SCAN_BLOCK) part += block_sums[b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+  if (lane == 0) part_s[warp] = part;
+  __syncthreads();
+  unsigned long long base = 0;
+  for (int k = 0; k < 32; ++k) base += part_s[k];
+  __syncthreads();
   const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
-  const uint32_t c = i < n ? counts[i] : 0u;
+  const uint32_t c = i < P.n_runs ? P.exp_counts[i] : 0u;
   const unsigned long long inc = block_incl_scan(c, nullptr);
-  if (i < n) offsets[i] = block_sums[blockIdx.x] + inc - c;
-}
-
-// one warp per group of 32 runs; runs with a non-zero count are expanded cooperatively
-__global__ void __launch_bounds__(256) exp_emit(const KParams P, const unsigned long long* offsets, bf_expansion* out,
-                                                unsigned long long cap) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t r0 = gw * 32;
-  if (r0 >= P.n_runs) return;
-  const uint32_t mine = r0 + lane < P.n_runs ? P.exp_counts[r0 + lane] : 0u;
-  uint32_t todo = __ballot_sync(0xffffffffu, mine != 0);
+  off_s[threadIdx.x] = base + inc - c;
+  __syncthreads();
+  const uint32_t r0 = blockIdx.x * SCAN_BLOCK + warp * 32;
+  uint32_t todo = __ballot_sync(0xffffffffu, c != 0);
   while (todo) {
     const uint32_t l = __ffs(todo) - 1;
     todo &= todo - 1;
@@ -93,7 +86,7 @@ __global__ void __launch_bounds__(256) exp_emit(const KParams P, const unsigned 
     const TopoHeader* th = reinterpret_cast<const TopoHeader*>(tr);
     const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + th->off_par);
     const uint32_t* ready = reinterpret_cast<const uint32_t*>(P.result + (size_t)r * P.result_stride + P.off_ready);
-    unsigned long long pos = offsets[r];
+    unsigned long long pos = off_s[warp * 32 + l];
     for (uint32_t q = 0; q < th->P; ++q) {
       const uint32_t stp = pd[q].step, B = pd[q].branches;
       if (!((ready[stp >> 5] >> (stp & 31u)) & 1u)) continue;
@@ -109,19 +102,15 @@ __global__ void __launch_bounds__(256) exp_emit(const KParams P, const unsigned 
   }
 }
 
-// scratch: block_sums needs ceil(n/1024) u64, offsets n u64
-cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, unsigned long long* offsets,
+// scratch: block_sums needs ceil(n/1024) u64
+cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, unsigned long long* /*offsets: unused*/,
                              bf_expansion* out, unsigned long long cap, cudaStream_t stream, uint32_t* launches) {
   const uint32_t n = P.n_runs;
   if (n == 0) return cudaSuccess;
   const uint32_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
   exp_block_sums<<<nb, SCAN_BLOCK, 0, stream>>>(P.exp_counts, n, block_sums);
-  exp_scan_block_sums<<<1, SCAN_BLOCK, 0, stream>>>(block_sums, nb);
-  exp_offsets<<<nb, SCAN_BLOCK, 0, stream>>>(P.exp_counts, n, block_sums, offsets);
-  const uint32_t warps = (n + 31) / 32;
-  const uint32_t blocks = (warps + 7) / 8;
-  exp_emit<<<blocks, 256, 0, stream>>>(P, offsets, out, cap);
-  if (launches) *launches += 4;
+  exp_scan_emit<<<nb, SCAN_BLOCK, 0, stream>>>(P, block_sums, out, cap);
+  if (launches) *launches += 2;
   return cudaGetLastError();
 }
 

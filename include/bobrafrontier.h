@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define BF_ABI_VERSION 2u
+#define BF_ABI_VERSION 3u
 
 /* ------------------------------------------------------------------ status */
 typedef enum bf_status {
@@ -428,6 +428,41 @@ int bf_resident_tick(bf_ctx* ctx, uint32_t handle, const bf_delta* deltas, uint3
                      uint32_t max_iterations, void* result, bf_counts* counts);
 /* Read the device copy back (tests / resync checks).                                                            */
 int bf_resident_download(bf_ctx* ctx, uint32_t handle, uint32_t first_run, uint32_t n_runs, void* state_records);
+
+/* ------------------------------------------------------------------ compact results
+ * What the consumer of a pass needs (findAndLaunchReadySteps, dag.go:1735-1775) is two short LISTS per run — the
+ * ready steps to hand to StepExecutor.Execute and the skipped steps to mark — plus the run's summary word, not 80+
+ * bytes of masks per run.  The compact entry points turn the result masks into events ON THE DEVICE and ship only
+ * those: one 8-byte event per (run, step) that has any result bit set, run-major and step-ascending (the order of
+ * the reference's lists), and one summary word per run.  At BASELINE configs[2] that is ~2.9 MB per pass instead
+ * of 8 MB.  The dense records stay on the device (bf_schedule may follow).                                        */
+#define BF_EVT_READY 0x1u      /* step is in `ready`                                                            */
+#define BF_EVT_SKIP 0x2u       /* step is in `skip`  (failed dependency or `if` false)                          */
+#define BF_EVT_FAIL 0x4u       /* step is in `fail`        (only when the layout has BF_F_OUT_FAIL)              */
+#define BF_EVT_NEEDS_COND 0x8u /* step is in `needs_cond`  (only with BF_F_OUT_NEEDS_COND)                       */
+#define BF_EVT_SKIP_DEP 0x10u  /* step is in `skip_dep`    (only with BF_F_OUT_SKIP_DEP)                         */
+typedef struct bf_step_event { /* 8 B */
+  uint32_t run;                /* index in the batch                                                            */
+  uint16_t step;
+  uint16_t kind;               /* BF_EVT_* bits                                                                 */
+} bf_step_event;
+
+typedef struct bf_compact_out {
+  uint32_t struct_size;
+  uint32_t reserved;
+  uint32_t* summary;           /* [n_runs] BF_SUM_* word of every run (0xFFFFFFFF = dead topology slot); may be NULL */
+  bf_step_event* events;       /* [events_cap]                                                                   */
+  uint64_t events_cap;
+  uint64_t n_events;           /* out: events the pass produced; when > events_cap only the first events_cap were written */
+} bf_compact_out;
+
+/* bf_eval with compact results: H2D(state) -> kernels -> D2H(summary words + events).  batch->result is ignored
+ * (may be NULL); expansion as for bf_eval.  Host buffers, synchronous.                                           */
+int bf_eval_compact(bf_ctx* ctx, const bf_batch* batch, bf_compact_out* out);
+/* bf_resident_tick with compact results: H2D(deltas) -> scatter -> pass -> D2H(summary words + events).  This is the
+ * steady-state tick of the operator: both directions are proportional to what changed.                           */
+int bf_resident_tick_compact(bf_ctx* ctx, uint32_t handle, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs,
+                             uint32_t flags, uint32_t max_iterations, bf_compact_out* out, bf_counts* counts);
 
 /* Pinned host memory for batches (cgo: memory with no Go pointers).           */
 int bf_alloc_pinned(bf_ctx* ctx, size_t bytes, void** out);

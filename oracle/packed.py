@@ -111,6 +111,25 @@ def evaluate(pt: PackedTopologies, L, state: np.ndarray, flags: int = 0, max_ite
     return result, {"ready": counts.ready, "skip": counts.skip, "expansion": counts.expansion, "evals": counts.evals}
 
 
+def compact_events(L, result: np.ndarray):
+    """The compact form of oracle result records (the checker of bf_eval_compact / bf_resident_tick_compact):
+    -> (summary [N] uint32, events structured array (run, step, kind) run-major / step-ascending).
+    kind bits: 1 ready, 2 skip, 4 fail, 8 needs_cond, 16 skip_dep (BF_EVT_*); dead slots (summary 0xFFFFFFFF) have none."""
+    n = result.shape[0]
+    W = L.words
+    summary = np.ascontiguousarray(result[:, 0:4]).view("<u4").reshape(n).copy()
+    kind = np.zeros((n, W * 32), dtype=np.uint16)
+    for bit, off in ((1, L.off_ready), (2, L.off_skip), (4, L.off_fail), (8, L.off_needs_cond), (16, L.off_skip_dep)):
+        if off != 0xFFFFFFFF:
+            m = np.unpackbits(np.ascontiguousarray(result[:, off:off + 4 * W]), axis=1, bitorder="little")
+            kind |= m.astype(np.uint16) * np.uint16(bit)
+    kind[summary == 0xFFFFFFFF] = 0
+    run, step = np.nonzero(kind)
+    ev = np.zeros(run.shape[0], dtype=np.dtype([("run", "<u4"), ("step", "<u2"), ("kind", "<u2")]))
+    ev["run"], ev["step"], ev["kind"] = run, step, kind[run, step]
+    return summary, ev
+
+
 def expand(pt: PackedTopologies, L, state: np.ndarray, result: np.ndarray, cap: int):
     from bobrapet_b200.records import EXP_DTYPE
     out = np.zeros(max(cap, 1), dtype=EXP_DTYPE)

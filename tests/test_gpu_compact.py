@@ -1,0 +1,96 @@
+"""Compact results (bf_eval_compact / bf_resident_tick_compact): the (run, step, kind) event list and the per-run summary
+words must be exactly what the oracle's mask records say, in run-major / step-ascending order."""
+import numpy as np
+import pytest
+
+from bobrapet_b200 import _abi as A
+from bobrapet_b200 import Frontier, synth
+from bobrapet_b200.records import make_layout
+from oracle import packed as PK
+from tests import randgen
+
+pytestmark = pytest.mark.gpu
+
+ALL = A.F_COND | A.F_DECISION | A.F_ALL_OUT
+
+
+@pytest.fixture(scope="module")
+def fr():
+    f = Frontier(0)
+    yield f
+    f.close()
+
+
+def _check(fr, ts, slots, L, state, flags=0, cap=None):
+    want, wcounts = PK.evaluate(PK.PackedTopologies(ts, slots), L, state, flags, 0, threads=8)
+    wsum, wev = PK.compact_events(L, want)
+    cap = len(wev) + 16 if cap is None else cap
+    summary, events, n_events, counts = fr.eval_compact(L, state, cap, flags=flags)
+    assert n_events == len(wev) and counts == wcounts
+    assert np.array_equal(summary, wsum)
+    assert np.array_equal(events, wev[:cap])
+    return n_events
+
+
+@pytest.mark.parametrize("cfg,n,S,fields", [(3, 5003, 256, 0), (4, 4001, 256, ALL), (2, 3000, 64, A.F_ALL_OUT), (5, 700, 1024, ALL),
+                                            (3, 600, 33, A.F_OUT_FAIL), (3, 1, 256, 0), (3, 513, 100, A.F_OUT_SKIP_DEP)])
+def test_compact_matches_oracle_masks(fr, cfg, n, S, fields):
+    ts = synth.topologies(cfg, 0, n, S)
+    slots = fr.put_topologies(ts)
+    pt = PK.PackedTopologies(ts, slots)
+    child = pt.max_child_nibbles()
+    f = fields | (A.F_COND | A.F_DECISION if cfg in (4, 5) else 0) | (A.F_CHILD if child else 0)
+    L = make_layout(S, child, f)
+    cf = fr.child_first(int(slots[0])) if child else None
+    state = synth.state(cfg, 0, n, L, slots, ts, cf)
+    assert _check(fr, ts, slots, L, state) > 0 or n < 10
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_compact_adversarial_and_fixpoint(fr, seed):
+    rng = np.random.default_rng(900 + seed)
+    ts = randgen.random_topologies(rng, 40, 1, [60, 300, 1024, 130][seed], max_deg=[5, 4, 5, 2][seed], fill=[0, 0.9, 0, 0.9][seed])
+    slots = fr.put_topologies(ts)
+    L, state, _ = randgen.random_state(rng, ts, slots, 3001, ALL, phase_mix=("any" if seed % 2 else "progress"))
+    _check(fr, ts, slots, L, state)
+    _check(fr, ts, slots, L, state, flags=A.EVAL_FIXPOINT)
+
+
+def test_compact_capacity_smaller_than_the_list_and_dead_slot(fr):
+    ts = synth.topologies(3, 0, 2000, 256)
+    slots = fr.put_topologies(ts)
+    L = make_layout(256, 0, 0)
+    state = synth.state(3, 0, 2000, L, slots, ts)
+    state[7, 0:4] = np.frombuffer(np.uint32(0x7FFFFFF0).tobytes(), np.uint8)   # dead slot: summary all-ones, no events
+    n = _check(fr, ts, slots, L, state)
+    assert n > 200
+    _check(fr, ts, slots, L, state, cap=100)     # only the first `cap` events are written, n_events still says how many
+    _check(fr, ts, slots, L, state, cap=0)
+    _check(fr, ts, slots, L, state)              # and a larger list after a tiny one (the first D2H slice is a guess)
+
+
+def test_resident_tick_compact(fr):
+    n, S = 6007, 256
+    ts = synth.topologies(4, 0, n, S)
+    slots = fr.put_topologies(ts)
+    L = make_layout(S, 0, ALL)
+    state = synth.state(4, 0, n, L, slots, ts)
+    h = fr.resident_create(L, n)
+    try:
+        fr.resident_upload(h, 0, state)
+        rng = np.random.default_rng(3)
+        for tick in range(3):
+            k = 500
+            flat = rng.choice(n * S, size=k, replace=False)
+            d = np.zeros(k, dtype=fr.DELTA_DTYPE)
+            d["run"], d["index"], d["field"] = flat // S, flat % S, A.DELTA_PHASE
+            d["code"] = rng.choice([0, 2, 3, 3, 4, 13], size=k)
+            summary, events, n_events, counts = fr.resident_tick_compact(h, n, d, 200000)
+            cur = fr.resident_download(h, 0, n, L.state_stride)
+            want, wcounts = PK.evaluate(PK.PackedTopologies(ts, slots), L, cur, 0, 0, threads=8)
+            wsum, wev = PK.compact_events(L, want)
+            assert n_events == len(wev) and counts == wcounts and np.array_equal(summary, wsum) and np.array_equal(events, wev)
+            assert not np.array_equal(cur, state)
+            state = cur
+    finally:
+        fr.resident_destroy(h)

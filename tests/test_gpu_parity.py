@@ -211,6 +211,26 @@ def test_packed_lanes_only_context(monkeypatch, fmt):
         f.close()
 
 
+@pytest.mark.parametrize("cfg,n", [(3, 70001), (4, 66003), (2, 300000)])
+def test_long_ring_sequences(cfg, n):
+    """enough groups per CTA that every warp wraps its prefetch batches and the slot ring many times"""
+    f = Frontier(0)
+    try:
+        S = 64 if cfg == 2 else 256
+        synth.set_threads(16)
+        ts = synth.topologies(cfg, 0, n, S)
+        slots = f.put_topologies(ts)
+        L = make_layout(S, 0, ALL if cfg == 4 else 0)
+        state = synth.state(cfg, 0, n, L, slots, ts)
+        want, wc = PK.evaluate(PK.PackedTopologies(ts, slots), L, state, threads=16)
+        got, gc = f.eval(L, state)
+        assert f.stats()["last_kernel"] == 1
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0 and gc == wc, (bad[:10], bad.size, gc, wc)
+    finally:
+        f.close()
+
+
 def test_group_tail_and_tiny_batches():
     """batch sizes around the group size R and the CTA count: partial last group, fewer groups than warps / CTAs"""
     f = Frontier(0)
