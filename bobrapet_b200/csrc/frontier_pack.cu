@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(512, 1) frontier_pack_kernel(const KParams P) 
     // The slot group is shared between warps: its use `cur_use` is armed by the warp that consumed the previous use.
     // A parity wait alone cannot tell "use u - 1 still pending" from "use u complete" (the parity then names the phase
     // before), so first wait until the arming warp has published use u; from then on the barrier is in phase u.
-    while ((int32_t)(lds_u32(armed_a + 4u * cur_sg) - (cur_use + 1u)) < 0) {
+    while ((int32_t)(lds_poll_u32(armed_a + 4u * cur_sg) - (cur_use + 1u)) < 0) {
     }
     mbar_wait(bars + 8u * cur_sg, cur_use & 1u);
     sg += NW;
