@@ -24,6 +24,7 @@ cudaError_t launch_expansion(const KParams& P, unsigned long long* block_sums, u
                              bf_expansion* out, unsigned long long cap, cudaStream_t stream, uint32_t* launches);
 int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes, uint32_t* occ2);
 cudaError_t launch_frontier_pack(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream);
+uint32_t frontier_pack_max_warps();
 cudaError_t launch_apply_deltas(const DeltaParams& P, cudaStream_t stream);
 cudaError_t launch_compact(const CompactParams& P, cudaStream_t stream);
 cudaError_t launch_schedule(const SchedParams& P, uint32_t sm_count, cudaStream_t stream);
@@ -233,10 +234,12 @@ int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_ka
   const uint32_t csr_bytes = round_up(2 * (S + 1), 16) + round_up(2 * E + 8, 16);
   const uint32_t K = md <= 2 ? 2u : (md <= 4 ? 4u : 0u);
   p.ell = 0;
-  if (K && round_up(2 * K * S, 16) <= csr_bytes && !csr_only) p.ell = K;
+  p.W = (S + 31) / 32;
+  const uint32_t ell_rows = 32 * p.W;   // a row for every step of every word, so the walk fetches without a bounds test
+  if (K && 2 * K * ell_rows <= csr_bytes && !csr_only) p.ell = K;
   if (p.ell) {
     p.off_col = off;
-    off += round_up(2 * p.ell * S, 16);
+    off += 2 * p.ell * ell_rows;
   } else {
     off += round_up(2 * (S + 1), 16);
     p.off_col = off;
@@ -272,7 +275,7 @@ void build_record(const bf_topology& t, const RecPlan& p, uint8_t* rec) {
       const uint32_t e0 = t.row_ptr[i], n = t.row_ptr[i + 1] - e0;
       for (uint32_t k = 0; k < p.ell; ++k) col[i * p.ell + k] = k < n ? t.col_idx[e0 + k] : pad;
     }
-    for (uint32_t x = S * p.ell; x < round_up(2 * p.ell * S, 16) / 2; ++x) col[x] = pad;
+    for (uint32_t x = S * p.ell; x < 32 * W * p.ell; ++x) col[x] = pad;
   } else {
     uint16_t* rp = reinterpret_cast<uint16_t*>(rec + sizeof(bf::TopoHeader));
     for (uint32_t i = 0; i <= S; ++i) rp[i] = (uint16_t)t.row_ptr[i];
@@ -441,13 +444,17 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   if (const char* env_k = getenv("BF_KERNEL")) pack = pack && strcmp(env_k, "general") != 0;
   uint32_t wq = 1, lg = 0;
   while (wq < L.words) { wq <<= 1; lg++; }
+  if (const char* e = getenv("BF_WQ")) {   // experiment knob: fewer runs per group (lanes per run rounded up further)
+    const uint32_t v = (uint32_t)atoi(e);
+    while (wq < v && wq < 32) { wq <<= 1; lg++; }
+  }
   const uint32_t R = 32u / wq;
   constexpr uint32_t kMinGroups = 8;
-  uint32_t nw = 16, ng = 0, pack_smem = 0;
+  uint32_t nw = bf::frontier_pack_max_warps(), ng = 0, pack_smem = 0;
   if (pack) {
     if (const char* e = getenv("BF_WARPS")) nw = (uint32_t)atoi(e);
     if (nw < 1) nw = 1;
-    if (nw > 16) nw = 16;
+    if (nw > bf::frontier_pack_max_warps()) nw = bf::frontier_pack_max_warps();
     const uint32_t group_bytes = R * P.stage_bytes;
     const uint32_t work = 128u + 1024u + 32u * R;   // fix-up words | status bytes R x (32 Wq + 16) | walk table R x 16
     auto groups_for = [&](uint32_t warps) -> uint32_t {   // slot groups that fit beside `warps` scratch areas
@@ -490,6 +497,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
           uint32_t occ2 = 0;
           int ctas = bf::frontier_max_blocks_per_sm(PG, wpb * 32, smem_try, &occ2);
           if (ctas < 1) continue;
+          if (ctas > 2) ctas = 2;   // the builds are compiled for one or two resident CTAs; many small CTAs measured slower
           if (env_b && atoi(env_b) >= 1 && atoi(env_b) < ctas) ctas = atoi(env_b);
           const uint32_t warps_sm = (uint32_t)ctas * wpb;
           const uint32_t depth = st >= 3 ? 2 : st - 1;           // 0, 1, 2, 2

@@ -12,7 +12,7 @@
 //
 //   fixed-width rows (ell = K in {2, 4}; taken when no step has more than K needs and S*K entries are not
 //   larger than the CSR block they replace): row_ptr is implicit (row i starts at entry i*K)
-//   +32 = off_col col_idx   u16[S][K]         the needs of step i, unused entries = PAD, pad 16
+//   +32 = off_col col_idx   u16[32*W][K]      the needs of step i, unused entries (and the rows past S) = PAD
 //                                             PAD = 32*W: the status byte just past the last step word, always 0
 //                                             ("satisfied, not failed"), so a padded entry never changes a verdict
 //

@@ -28,11 +28,29 @@ namespace bf {
 
 extern __shared__ __align__(128) uint8_t smem_p[];
 
-// ---- stage D over the (run, word) items of a group.  tab: per-run entries {col_a, rp_a, st_a, max_deg | ell << 16}.
+#ifndef WALK_K
+#define WALK_K 4   // (run, word) items walked at once: independent load chains per warp (measured: 2: 50.9 us, 3: 50.0, 4: 49.5)
+#endif
+#ifndef PACK_MAX_WARPS
+#define PACK_MAX_WARPS 16   // warps per CTA the kernel is compiled for (registers: 65536 / (32 * PACK_MAX_WARPS) per thread)
+#endif
+
+// ---- stage D over the (run, word) items of a group.
+// Where the rows and status bytes of run g live: CSR formats read the per-run table {col_a, rp_a, st_a, max_deg | ell << 16}
+// written in stage C; fixed-width rows always start 32 bytes into the run's topology buffer, so their addresses are
+// computed (two multiply-adds, no dependent shared-memory load in front of the row fetch).
+struct WalkCtx {
+  uint32_t tab_a;      // per-run table (16 B entries)
+  uint32_t col0;       // fixed-width formats: col_idx of run 0 of the group (topology buffer 0 + 32)
+  uint32_t topo_buf;   // bytes between the topology buffers of consecutive runs
+  uint32_t st0;        // status bytes of run 0
+  uint32_t st_stride;  // bytes between the status areas of consecutive runs
+};
+
 // K items at once (independent load chains); FMT as in kernel_common.cuh — the caller guarantees that every live run
 // of the group has this row format (else it takes walk_items_any).
 template <int K, int FMT, bool NEED_FD>
-DI void walk_items_k(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t lg, uint32_t tab_a, uint32_t& met_w, uint32_t& fd_w) {
+DI void walk_items_k(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t lg, const WalkCtx& C, uint32_t& met_w, uint32_t& fd_w) {
   const uint32_t wmask = (1u << lg) - 1u;
   uint32_t L[K], p[K], n[K], wv[K], st[K], x[K][4];
   bool c[K];
@@ -44,10 +62,17 @@ DI void walk_items_k(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t lg, 
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const uint32_t cw = __shfl_sync(FULL, CAND, L[k]);
-    const uint4 t = lds_v4(tab_a + (L[k] >> lg) * 16u);
+    const uint32_t g = L[k] >> lg, i = (L[k] & wmask) * 32u + lane;
     c[k] = (cw >> lane) & 1u;
-    st[k] = t.z;
-    row_locate<FMT>(c[k], (L[k] & wmask) * 32u + lane, t.y, t.x, p[k], n[k]);
+    if (FMT == FMT_ELL4 || FMT == FMT_ELL2) {
+      st[k] = C.st0 + g * C.st_stride;
+      p[k] = C.col0 + g * C.topo_buf + i * (FMT == FMT_ELL4 ? 8u : 4u);   // rows exist for every step of the word (device_record.h)
+      n[k] = (uint32_t)FMT;
+    } else {
+      const uint4 t = lds_v4(C.tab_a + g * 16u);
+      st[k] = t.z;
+      row_locate<FMT>(c[k], i, t.y, t.x, p[k], n[k]);
+    }
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) row_fetch<FMT>(p[k], x[k]);
@@ -65,37 +90,39 @@ DI void walk_items_k(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t lg, 
 }
 
 template <int FMT, bool NEED_FD>
-DI void walk_items(uint32_t lane, uint32_t CAND, uint32_t lg, uint32_t tab_a, uint32_t& met_w, uint32_t& fd_w) {
+DI void walk_items(uint32_t lane, uint32_t CAND, uint32_t lg, const WalkCtx& C, uint32_t& met_w, uint32_t& fd_w) {
   met_w = 0;
   fd_w = 0;
   uint32_t todo = __ballot_sync(FULL, CAND != 0);  // (run, word) pairs with at least one candidate step
-  while (__popc(todo) >= 2) walk_items_k<2, FMT, NEED_FD>(lane, CAND, todo, lg, tab_a, met_w, fd_w);
-  if (todo) walk_items_k<1, FMT, NEED_FD>(lane, CAND, todo, lg, tab_a, met_w, fd_w);
+  while (__popc(todo) >= WALK_K) walk_items_k<WALK_K, FMT, NEED_FD>(lane, CAND, todo, lg, C, met_w, fd_w);
+  if (WALK_K > 2)
+    if (__popc(todo) >= 2) walk_items_k<2, FMT, NEED_FD>(lane, CAND, todo, lg, C, met_w, fd_w);
+  if (todo) walk_items_k<1, FMT, NEED_FD>(lane, CAND, todo, lg, C, met_w, fd_w);
 }
 
 // mixed row formats inside one group (rare): one item at a time, format read from the item's table entry
 template <bool NEED_FD>
-DI void walk_items_any(uint32_t lane, uint32_t CAND, uint32_t lg, uint32_t tab_a, uint32_t& met_w, uint32_t& fd_w) {
+DI void walk_items_any(uint32_t lane, uint32_t CAND, uint32_t lg, const WalkCtx& C, uint32_t& met_w, uint32_t& fd_w) {
   met_w = 0;
   fd_w = 0;
   for (uint32_t todo = __ballot_sync(FULL, CAND != 0); todo;) {
     const uint32_t L = __ffs(todo) - 1;
-    const uint32_t meta = lds_u32(tab_a + (L >> lg) * 16u + 12u);
+    const uint32_t meta = lds_u32(C.tab_a + (L >> lg) * 16u + 12u);
     const int fmt = fmt_of(meta >> 16, meta & 0xFFFFu);  // warp-uniform
     uint32_t one = todo & (0u - todo);
     todo ^= one;
-    if (fmt == FMT_ELL4) walk_items_k<1, FMT_ELL4, NEED_FD>(lane, CAND, one, lg, tab_a, met_w, fd_w);
-    else if (fmt == FMT_CSR4) walk_items_k<1, FMT_CSR4, NEED_FD>(lane, CAND, one, lg, tab_a, met_w, fd_w);
-    else if (fmt == FMT_ELL2) walk_items_k<1, FMT_ELL2, NEED_FD>(lane, CAND, one, lg, tab_a, met_w, fd_w);
-    else walk_items_k<1, FMT_CSRL, NEED_FD>(lane, CAND, one, lg, tab_a, met_w, fd_w);
+    if (fmt == FMT_ELL4) walk_items_k<1, FMT_ELL4, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
+    else if (fmt == FMT_CSR4) walk_items_k<1, FMT_CSR4, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
+    else if (fmt == FMT_ELL2) walk_items_k<1, FMT_ELL2, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
+    else walk_items_k<1, FMT_CSRL, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
   }
 }
 
 // CD: cond and/or decision codes present   XO: any of fail/needs_cond/skip_dep/phase_out requested
 template <bool CD, bool XO>
-__global__ void __launch_bounds__(512, 1) frontier_pack_kernel(const KParams P) {
+__global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(const KParams P) {
   const uint32_t lane = pin(threadIdx.x & 31u);  // pinned: otherwise rematerialised from S2R inside the loop
-  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t warp = __shfl_sync(FULL, threadIdx.x >> 5, 0);  // through a shuffle: the compiler then treats it as warp-uniform
   const uint32_t NW = P.warps_per_block, NG = P.slot_groups;
   const uint32_t Wq = P.wq, lg = P.wq_log2, R = 32u >> lg;
   const uint32_t g = pin(lane >> lg), w = pin(lane & (Wq - 1u));
@@ -205,8 +232,7 @@ __global__ void __launch_bounds__(512, 1) frontier_pack_kernel(const KParams P) 
     // The slot group is shared between warps: its use `cur_use` is armed by the warp that consumed the previous use.
     // A parity wait alone cannot tell "use u - 1 still pending" from "use u complete" (the parity then names the phase
     // before), so first wait until the arming warp has published use u; from then on the barrier is in phase u.
-    while ((int32_t)(lds_poll_u32(armed_a + 4u * cur_sg) - (cur_use + 1u)) < 0) {
-    }
+    while ((int32_t)(lds_poll_u32(armed_a + 4u * cur_sg) - (cur_use + 1u)) < 0) __nanosleep(32);
     mbar_wait(bars + 8u * cur_sg, cur_use & 1u);
     sg += NW;
     while (sg >= NG) { sg -= NG; ++use; }
@@ -379,21 +405,22 @@ __global__ void __launch_bounds__(512, 1) frontier_pack_kernel(const KParams P) 
     __syncwarp();
     // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
     uint32_t met_w, fd_w;
+    const WalkCtx wctx{tab_a, grp_a + R * P.state_stride + (uint32_t)sizeof(TopoHeader), P.topo_buf_bytes, st0_a, st_stride};
     if (mixed) {
-      if (any_fd) walk_items_any<true>(lane, CAND, lg, tab_a, met_w, fd_w);
-      else walk_items_any<false>(lane, CAND, lg, tab_a, met_w, fd_w);
+      if (any_fd) walk_items_any<true>(lane, CAND, lg, wctx, met_w, fd_w);
+      else walk_items_any<false>(lane, CAND, lg, wctx, met_w, fd_w);
     } else if (fmt0 == FMT_ELL4) {
-      if (any_fd) walk_items<FMT_ELL4, true>(lane, CAND, lg, tab_a, met_w, fd_w);
-      else walk_items<FMT_ELL4, false>(lane, CAND, lg, tab_a, met_w, fd_w);
+      if (any_fd) walk_items<FMT_ELL4, true>(lane, CAND, lg, wctx, met_w, fd_w);
+      else walk_items<FMT_ELL4, false>(lane, CAND, lg, wctx, met_w, fd_w);
     } else if (fmt0 == FMT_CSR4) {
-      if (any_fd) walk_items<FMT_CSR4, true>(lane, CAND, lg, tab_a, met_w, fd_w);
-      else walk_items<FMT_CSR4, false>(lane, CAND, lg, tab_a, met_w, fd_w);
+      if (any_fd) walk_items<FMT_CSR4, true>(lane, CAND, lg, wctx, met_w, fd_w);
+      else walk_items<FMT_CSR4, false>(lane, CAND, lg, wctx, met_w, fd_w);
     } else if (fmt0 == FMT_ELL2) {
-      if (any_fd) walk_items<FMT_ELL2, true>(lane, CAND, lg, tab_a, met_w, fd_w);
-      else walk_items<FMT_ELL2, false>(lane, CAND, lg, tab_a, met_w, fd_w);
+      if (any_fd) walk_items<FMT_ELL2, true>(lane, CAND, lg, wctx, met_w, fd_w);
+      else walk_items<FMT_ELL2, false>(lane, CAND, lg, wctx, met_w, fd_w);
     } else {
-      if (any_fd) walk_items<FMT_CSRL, true>(lane, CAND, lg, tab_a, met_w, fd_w);
-      else walk_items<FMT_CSRL, false>(lane, CAND, lg, tab_a, met_w, fd_w);
+      if (any_fd) walk_items<FMT_CSRL, true>(lane, CAND, lg, wctx, met_w, fd_w);
+      else walk_items<FMT_CSRL, false>(lane, CAND, lg, wctx, met_w, fd_w);
     }
     uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
     if (CD) {
@@ -486,6 +513,8 @@ static PackFn pick_pack(const KParams& P) {
   if (cd) return xo ? frontier_pack_kernel<true, true> : frontier_pack_kernel<true, false>;
   return xo ? frontier_pack_kernel<false, true> : frontier_pack_kernel<false, false>;
 }
+
+uint32_t frontier_pack_max_warps() { return PACK_MAX_WARPS; }
 
 cudaError_t launch_frontier_pack(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream) {
   PackFn fn = pick_pack(P);

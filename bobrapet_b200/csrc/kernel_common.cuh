@@ -137,8 +137,8 @@ DI int fmt_of(uint32_t ell, uint32_t max_deg) { return ell ? (int)ell : (max_deg
 // phase 1 of an item: where the row of step `i` starts (shared address) and, for CSR, its length
 template <int FMT>
 DI void row_locate(bool cand, uint32_t i, uint32_t rp_addr, uint32_t col_addr, uint32_t& p, uint32_t& n) {
-  if (FMT == FMT_ELL4) { p = col_addr + (cand ? i : 0u) * 8u; n = 4u; }
-  else if (FMT == FMT_ELL2) { p = col_addr + (cand ? i : 0u) * 4u; n = 2u; }
+  if (FMT == FMT_ELL4) { p = col_addr + i * 8u; n = 4u; }        // rows exist for every step of the word (padded to 32*W)
+  else if (FMT == FMT_ELL2) { p = col_addr + i * 4u; n = 2u; }
   else {
     uint32_t e0 = 0;
     n = 0;
