@@ -94,7 +94,7 @@ class Stats(C.Structure):
                 ("n_topologies", C.c_uint32), ("sm_count", C.c_uint32), ("last_grid", C.c_uint32),
                 ("last_block", C.c_uint32), ("last_smem_bytes", C.c_uint32), ("last_stages", C.c_uint32),
                 ("last_kernel", C.c_uint32), ("last_runs_per_trip", C.c_uint32),
-                ("last_eval_chunks", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("last_eval_chunks", C.c_uint32), ("arena_compactions", C.c_uint32)]
 
 
 EVT_READY, EVT_SKIP, EVT_FAIL, EVT_NEEDS_COND, EVT_SKIP_DEP = 0x1, 0x2, 0x4, 0x8, 0x10  # BF_EVT_*
@@ -112,7 +112,8 @@ class CompactOut(C.Structure):
 class SchedTables(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_stories", C.c_uint32), ("n_queues", C.c_uint32), ("global_limit", C.c_int32),
                 ("global_running_base", C.c_uint32), ("story_limit", C.c_void_p), ("story_running_base", C.c_void_p),
-                ("queue_limit", C.c_void_p), ("queue_aging_s", C.c_void_p), ("queue_running_base", C.c_void_p)]
+                ("queue_limit", C.c_void_p), ("queue_aging_s", C.c_void_p), ("queue_running_base", C.c_void_p),
+                ("queue_max_priority_base", C.c_void_p)]
 
 
 class SchedOut(C.Structure):

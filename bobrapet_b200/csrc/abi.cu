@@ -27,6 +27,7 @@ cudaError_t launch_frontier_pack(const KParams& P, uint32_t grid, uint32_t smem_
 uint32_t frontier_pack_max_warps();
 cudaError_t launch_apply_deltas(const DeltaParams& P, cudaStream_t stream);
 cudaError_t launch_compact(const CompactParams& P, cudaStream_t stream);
+cudaError_t launch_move_records(const uint8_t* src, uint8_t* dst, const void* moves, uint32_t n, cudaStream_t stream);
 cudaError_t launch_schedule(const SchedParams& P, uint32_t sm_count, cudaStream_t stream);
 cudaError_t launch_closure(const Slot* slots, const uint32_t* slot_ids, const uint32_t* starts, uint32_t n, uint32_t n_slots,
                            uint32_t words_out, uint32_t* masks, cudaStream_t stream);
@@ -71,6 +72,8 @@ struct bf_ctx {
 
   uint8_t* arena = nullptr;
   size_t arena_cap = 0, arena_used = 0;
+  size_t arena_dead = 0;               // bytes of dropped records below arena_used (reclaimed by compact_arena)
+  uint64_t arena_compactions = 0;
   std::vector<TopoMeta> meta;
   std::vector<uint32_t> free_slots;
   std::vector<bf::Slot> slots_host;
@@ -367,8 +370,11 @@ int check_layout(bf_ctx* c, const bf_layout& L) {
   if (L.off_phase == BF_OFF_NONE || L.off_ready == BF_OFF_NONE || L.off_skip == BF_OFF_NONE)
     return fail(c, BF_EINVAL, "phase / ready / skip fields are mandatory");
   const uint32_t W = L.words;
-  auto in_state = [&](uint32_t off, uint32_t len) { return off == BF_OFF_NONE || (off % 4 == 0 && off >= 16 && off + len <= L.state_stride); };
-  auto in_res = [&](uint32_t off, uint32_t len) { return off == BF_OFF_NONE || (off % 4 == 0 && off >= 16 && off + len <= L.result_stride); };
+  // 64-bit sums: a caller-supplied offset near 2^32 must not wrap past the bound
+  auto in_state = [&](uint32_t off, uint32_t len) { return off == BF_OFF_NONE || (off % 4 == 0 && off >= 16 && (uint64_t)off + len <= L.state_stride); };
+  auto in_res = [&](uint32_t off, uint32_t len) { return off == BF_OFF_NONE || (off % 4 == 0 && off >= 16 && (uint64_t)off + len <= L.result_stride); };
+  if (L.child_nibbles > 0xFFFFu) return fail(c, BF_EINVAL, "layout.child_nibbles exceeds 65535");
+  if (L.state_stride > (1u << 20) || L.result_stride > (1u << 20)) return fail(c, BF_EINVAL, "record stride exceeds 1 MiB");
   if (!in_state(L.off_phase, W * 16) || !in_state(L.off_cond, W * 8) || !in_state(L.off_decision, W * 8) ||
       !in_state(L.off_child, (L.child_nibbles + 1) / 2))
     return fail(c, BF_EINVAL, "state field outside the record");
@@ -564,6 +570,49 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   return BF_OK;
 }
 
+// The arena is a bump allocator; a long-lived operator puts one topology per Story generation and drops the old one, so
+// dead records pile up below arena_used.  When they outweigh the live ones the live records are re-packed into a fresh
+// arena (one warp per record on the device), the slot table follows, and the freed space is reusable again.
+int compact_arena(bf_ctx* c, size_t incoming) {
+  std::vector<uint32_t> live;
+  size_t live_bytes = 0;
+  for (uint32_t s = 0; s < c->meta.size(); ++s)
+    if (c->meta[s].alive) { live.push_back(s); live_bytes += round_up_sz(c->meta[s].bytes, 16); }
+  size_t ncap = (size_t)64 << 20;
+  while (ncap < live_bytes + incoming) ncap *= 2;
+  uint8_t* na = nullptr;
+  cudaError_t e = cudaMalloc(&na, ncap);
+  if (e != cudaSuccess) { cudaGetLastError(); return BF_OK; }   // no room for a second arena right now: keep appending
+  std::vector<unsigned long long> moves(4 * live.size());
+  size_t off = 0;
+  for (size_t i = 0; i < live.size(); ++i) {
+    const TopoMeta& m = c->meta[live[i]];
+    moves[4 * i] = m.offset; moves[4 * i + 1] = off; moves[4 * i + 2] = m.bytes; moves[4 * i + 3] = 0;
+    off += round_up_sz(m.bytes, 16);
+  }
+  void* d_moves = nullptr;
+  if (!live.empty()) {
+    e = cudaMalloc(&d_moves, moves.size() * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_moves, moves.data(), moves.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = bf::launch_move_records(c->arena, na, d_moves, (uint32_t)live.size(), c->stream);
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();   // nothing may still read the old arena when it is freed
+  cudaFree(d_moves);
+  if (e != cudaSuccess) { cudaFree(na); return cuda_fail(c, e, "arena compaction"); }
+  cudaFree(c->arena);
+  c->arena = na; c->arena_cap = ncap; c->arena_used = off; c->arena_dead = 0;
+  for (size_t i = 0; i < live.size(); ++i) {
+    TopoMeta& m = c->meta[live[i]];
+    m.offset = (size_t)moves[4 * i + 1];
+    c->slots_host[live[i]].addr = (uint64_t)(uintptr_t)(c->arena + m.offset);
+  }
+  c->slots_dirty = true;
+  c->rec_max_dirty = true;
+  c->arena_compactions++;
+  c->stats.kernel_launches += live.empty() ? 0 : 1;
+  return BF_OK;
+}
+
 // ---- compact results: masks -> events on the device, then the two small D2H copies ----
 // Enqueue on `s` (after the passes that wrote d_result): compaction kernels, D2H of the summary words, of the event total
 // and of a first slice of the event list sized from the previous pass (the total is only known after the sync).
@@ -612,6 +661,8 @@ int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_
     if (rc != BF_OK) return fail(c, rc, "topology " + std::to_string(i) + ": " + why);
     total += plans[i].rec_bytes;
   }
+  if (c->arena_dead > ((size_t)1 << 20) && c->arena_dead * 2 > c->arena_used)
+    if (int rc = compact_arena(c, total)) return rc;
   const size_t base = round_up_sz(c->arena_used, 16);
   if (int rc = grow_arena(c, base + total)) return rc;
   std::vector<uint8_t> staging;
@@ -805,8 +856,10 @@ static int drop_locked(bf_ctx* c, uint32_t slot) {
   c->n_alive--;
   c->slots_dirty = true;
   c->rec_max_dirty = true;
-  if (c->n_alive == 0) {  // arena is a bump allocator: it resets when the last topology goes
+  c->arena_dead += round_up_sz(c->meta[slot].bytes, 16);
+  if (c->n_alive == 0) {  // nothing left: the bump allocator starts over
     c->arena_used = 0;
+    c->arena_dead = 0;
   }
   return BF_OK;
 }
@@ -999,6 +1052,7 @@ static int fill_sched_params(bf_ctx* c, const bf_batch* b, const bf_sched_tables
   P.n_stories = t->n_stories; P.n_queues = t->n_queues; P.global_limit = t->global_limit; P.global_base = t->global_running_base;
   P.n_slots = (uint32_t)c->slots_host.size(); P.n_runs = b->n_runs;
   P.words = L.words; P.state_stride = L.state_stride; P.off_phase = L.off_phase; P.off_child = L.off_child;
+  P.child_nibbles = L.child_nibbles;
   P.result_stride = L.result_stride; P.off_ready = L.off_ready; P.stride = BF_SCHED_STRIDE(L.words);
   P.slots = c->slots_dev;
   return BF_OK;
@@ -1022,7 +1076,7 @@ int bf_schedule_device(bf_ctx* c, const bf_batch* b, const bf_sched_run* runs, c
   P.story_running = out->story_running; P.queue_running = out->queue_running; P.queue_maxprio = out->queue_max_priority;
   P.global_running = out->global_running;
   P.story_limit = t->story_limit; P.queue_limit = t->queue_limit; P.queue_aging = t->queue_aging_s;
-  P.story_base = t->story_running_base; P.queue_base = t->queue_running_base;
+  P.story_base = t->story_running_base; P.queue_base = t->queue_running_base; P.queue_maxprio_base = t->queue_max_priority_base;
   BF_CUDA(c, bf::launch_schedule(P, (uint32_t)c->sm_count, static_cast<cudaStream_t>(stream)));
   c->stats.kernel_launches += 3;
   return BF_OK;
@@ -1045,7 +1099,7 @@ int bf_schedule(bf_ctx* c, const bf_batch* b, const bf_sched_run* runs, const bf
   auto take = [&](size_t bytes) { const size_t o = off; off = round_up_sz(off + bytes, 16); return o; };
   const size_t o_runs = take(n * sizeof(bf_sched_run)), o_rec = take(n * (size_t)P.stride), o_sr = take(ns * 4), o_qr = take(nq * 4),
                o_mp = take(nq * 4), o_gl = take(4), o_sl = take(ns * 4), o_ql = take(nq * 4), o_qa = take(nq * 4), o_sb = take(ns * 4),
-               o_qb = take(nq * 4);
+               o_qb = take(nq * 4), o_pb = take(nq * 4);
   if (int rc = ensure_dev(c, c->d_sched, c->d_sched_cap, off ? off : 16)) return rc;
   uint8_t* d = c->d_sched;
   auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
@@ -1057,6 +1111,7 @@ int bf_schedule(bf_ctx* c, const bf_batch* b, const bf_sched_run* runs, const bf
   BF_CUDA(c, up(o_qa, t->queue_aging_s, nq * 4));
   BF_CUDA(c, up(o_sb, t->story_running_base, ns * 4));
   BF_CUDA(c, up(o_qb, t->queue_running_base, nq * 4));
+  BF_CUDA(c, up(o_pb, t->queue_max_priority_base, nq * 4));
   P.state = c->last_state; P.result = c->last_result;
   P.runs = reinterpret_cast<const bf_sched_run*>(d + o_runs); P.records = d + o_rec;
   P.story_running = reinterpret_cast<uint32_t*>(d + o_sr); P.queue_running = reinterpret_cast<uint32_t*>(d + o_qr);
@@ -1065,6 +1120,7 @@ int bf_schedule(bf_ctx* c, const bf_batch* b, const bf_sched_run* runs, const bf
   P.queue_aging = reinterpret_cast<const int32_t*>(d + o_qa);
   P.story_base = t->story_running_base ? reinterpret_cast<const uint32_t*>(d + o_sb) : nullptr;
   P.queue_base = t->queue_running_base ? reinterpret_cast<const uint32_t*>(d + o_qb) : nullptr;
+  P.queue_maxprio_base = t->queue_max_priority_base ? reinterpret_cast<const int32_t*>(d + o_pb) : nullptr;
   cudaError_t e = bf::launch_schedule(P, (uint32_t)c->sm_count, s);
   c->stats.kernel_launches += 3;
   auto down = [&](void* dst, size_t o, size_t bytes) -> cudaError_t {
@@ -1126,6 +1182,7 @@ int bf_resident_upload(bf_ctx* c, uint32_t h, uint32_t first, uint32_t n, const 
   if ((uint64_t)first + n > r->cap || (n && !records)) return fail(c, BF_EINVAL, "run range outside the resident batch");
   if (n == 0) return BF_OK;
   BF_CUDA(c, cudaSetDevice(c->device));
+  if (c->last_state == r->d_state) c->last_eval_valid = false;   // the evaluated snapshot is gone: bf_schedule must follow a new pass
   BF_CUDA(c, cudaMemcpyAsync(r->d_state + (size_t)first * r->L.state_stride, records, (size_t)n * r->L.state_stride, cudaMemcpyHostToDevice, c->stream));
   BF_CUDA(c, cudaStreamSynchronize(c->stream));
   return BF_OK;
@@ -1170,6 +1227,7 @@ int bf_resident_apply(bf_ctx* c, uint32_t h, const bf_delta* deltas, uint32_t n)
   if (n && !deltas) return fail(c, BF_EINVAL, "null deltas");
   if (n == 0) return BF_OK;
   BF_CUDA(c, cudaSetDevice(c->device));
+  if (c->last_state == r->d_state) c->last_eval_valid = false;
   const int rc = resident_apply_async(c, r, deltas, n);
   cudaError_t e = rc == BF_OK ? cudaMemcpyAsync(c->h_counts, c->d_rejected, 4, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
   const cudaError_t es = cudaStreamSynchronize(c->stream);  // the caller's delta buffer may be reused after return
@@ -1297,6 +1355,7 @@ int bf_get_stats(const bf_ctx* c, bf_stats* out) {
   if (!c || !out) return BF_EINVAL;
   *out = c->stats;
   out->arena_used_bytes = c->arena_used;
+  out->arena_compactions = (uint32_t)c->arena_compactions;
   out->arena_cap_bytes = c->arena_cap;
   out->n_topologies = c->n_alive;
   out->sm_count = (uint32_t)c->sm_count;

@@ -135,10 +135,11 @@ struct SchedParams {
   const int32_t* queue_aging;
   const uint32_t* story_base;  // StepRuns the batch does not hold, or nullptr
   const uint32_t* queue_base;
+  const int32_t* queue_maxprio_base;  // highest effective priority among runs with demand OUTSIDE the batch, or nullptr
   uint32_t global_base;
   int32_t global_limit;
   uint32_t n_stories, n_queues, n_slots, n_runs;
-  uint32_t words, state_stride, off_phase, off_child, result_stride, off_ready, stride;
+  uint32_t words, state_stride, off_phase, off_child, child_nibbles, result_stride, off_ready, stride;
 };
 
 }  // namespace bf

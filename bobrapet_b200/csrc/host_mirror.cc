@@ -408,6 +408,21 @@ int bfh_batch_remove_last_run(bfh_batch* b) {
   b->story_of_run.pop_back();
   --b->n;
   if (b->uploaded > b->n) b->uploaded = b->n;  // the slot's next occupant is uploaded as a full record
+  // pending deltas of the removed run must not land on the slot's next occupant (whose full record is uploaded first)
+  if (b->resident && !b->deltas.empty()) {
+    const uint32_t gone = b->n;
+    size_t keep = 0;
+    for (size_t i = 0; i < b->deltas.size(); ++i)
+      if (b->deltas[i].run != gone) b->deltas[keep++] = b->deltas[i];
+    if (keep != b->deltas.size()) {
+      b->deltas.resize(keep);
+      b->delta_at.clear();
+      for (size_t i = 0; i < keep; ++i) {
+        const bf_delta& d = b->deltas[i];
+        b->delta_at[((uint64_t)d.run << 32) | ((uint64_t)d.field << 16) | d.index] = (uint32_t)i;
+      }
+    }
+  }
   return BF_OK;
 }
 

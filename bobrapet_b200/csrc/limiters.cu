@@ -32,7 +32,7 @@ __global__ void sched_init(const SchedParams P) {
   if (i < P.n_stories) P.story_running[i] = P.story_base ? P.story_base[i] : 0u;
   if (i < P.n_queues) {
     P.queue_running[i] = P.queue_base ? P.queue_base[i] : 0u;
-    P.queue_maxprio[i] = INT32_MIN;
+    P.queue_maxprio[i] = P.queue_maxprio_base ? P.queue_maxprio_base[i] : INT32_MIN;
   }
   if (i == 0) *P.global_running = P.global_base;
 }
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) sched_count(const SchedParams P) {
           for (uint32_t q = 0; q < nP; ++q) {
             if (!((registered >> q) & 1ull)) continue;
             const ParDesc d = pd[q];
+            if ((uint64_t)d.child_first + d.branches > P.child_nibbles) continue;  // child area shorter than the topology's: nothing to read
             for (uint32_t b = lane; b < d.branches; b += 32) cnt += get_nibble(child, d.child_first + b) == BF_PHASE_RUNNING;
           }
         }

@@ -69,6 +69,24 @@ __global__ void __launch_bounds__(256) apply_deltas(const DeltaParams P) {
   if (!ok) atomicAdd(P.rejected, 1u);
 }
 
+// Arena compaction (abi.cu): record i moves from src + moves[i].x to dst + moves[i].y (moves[i].z bytes, multiples of 16).
+// One warp per record, 16 bytes per lane per trip.
+__global__ void __launch_bounds__(256) move_records(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const ulonglong4* __restrict__ moves,
+                                                    uint32_t n) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (w >= n) return;
+  const ulonglong4 m = moves[w];
+  const uint4* s = reinterpret_cast<const uint4*>(src + m.x);
+  uint4* d = reinterpret_cast<uint4*>(dst + m.y);
+  for (unsigned long long i = lane; i < m.z / 16; i += 32) d[i] = s[i];
+}
+
+cudaError_t launch_move_records(const uint8_t* src, uint8_t* dst, const void* moves, uint32_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  move_records<<<(n + 7) / 8, 256, 0, stream>>>(src, dst, static_cast<const ulonglong4*>(moves), n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_apply_deltas(const DeltaParams& P, cudaStream_t stream) {
   if (P.n == 0) return cudaSuccess;
   apply_deltas<<<(P.n + 255) / 256, 256, 0, stream>>>(P);

@@ -249,7 +249,8 @@ class Frontier:
 
     # -- limiters over the ready sets of the batch just evaluated (rows a9 / f4; dag.go:1780-1961)
     def schedule(self, L: A.Layout, n_runs: int, sched_runs: np.ndarray, story_limit, queue_limit, queue_aging_s,
-                 global_limit: int = 0, story_running_base=None, queue_running_base=None, global_running_base: int = 0):
+                 global_limit: int = 0, story_running_base=None, queue_running_base=None, global_running_base: int = 0,
+                 queue_max_priority_base=None):
         """bf_schedule: must follow eval() of the same batch.  sched_runs: [n_runs] records of 32 bytes (bf_sched_run).
         Returns dict(records [n, stride] uint8, story_running, queue_running, queue_max_priority, global_running)."""
         assert sched_runs.nbytes == 32 * n_runs and sched_runs.flags["C_CONTIGUOUS"]
@@ -258,11 +259,13 @@ class Frontier:
         qa = np.ascontiguousarray(queue_aging_s, dtype=np.int32)
         sb = None if story_running_base is None else np.ascontiguousarray(story_running_base, dtype=np.uint32)
         qb = None if queue_running_base is None else np.ascontiguousarray(queue_running_base, dtype=np.uint32)
+        pb = None if queue_max_priority_base is None else np.ascontiguousarray(queue_max_priority_base, dtype=np.int32)
         assert ql.shape == qa.shape
         t = A.SchedTables(struct_size=C.sizeof(A.SchedTables), n_stories=sl.size, n_queues=ql.size, global_limit=global_limit,
                           global_running_base=global_running_base, story_limit=sl.ctypes.data,
                           story_running_base=(sb.ctypes.data if sb is not None else None), queue_limit=ql.ctypes.data,
-                          queue_aging_s=qa.ctypes.data, queue_running_base=(qb.ctypes.data if qb is not None else None))
+                          queue_aging_s=qa.ctypes.data, queue_running_base=(qb.ctypes.data if qb is not None else None),
+                          queue_max_priority_base=(pb.ctypes.data if pb is not None else None))
         stride = A.sched_stride(L.words)
         rec = np.zeros((n_runs, stride), dtype=np.uint8)
         sr = np.zeros(max(sl.size, 1), dtype=np.uint32)

@@ -355,6 +355,11 @@ typedef struct bf_sched_tables {
   const int32_t* queue_limit;          /* [n_queues]  queues[q].concurrency, <= 0: none                  */
   const int32_t* queue_aging_s;        /* [n_queues]  queues[q].priorityAgingSeconds, <= 0: no aging      */
   const uint32_t* queue_running_base;  /* [n_queues] or NULL (zeros)                                      */
+  const int32_t* queue_max_priority_base; /* [n_queues] highest effective priority among non-terminal runs with demand that the
+                                          batch does NOT hold (other shards, runs the batcher left out), INT32_MIN where none;
+                                          NULL = none anywhere.  enforcePriorityOrdering (dag.go:1917-1944) compares against
+                                          EVERY non-terminal StoryRun of the queue, so a sharded / partial batch must be given
+                                          the rest here (bf_group_schedule does the exchange between shards itself)          */
 } bf_sched_tables;
 
 typedef struct bf_sched_header { /* first 16 B of a schedule record                                     */
@@ -479,7 +484,7 @@ typedef struct bf_stats {
   uint32_t last_kernel;        /* 0 = one run per warp (general), 1 = packed lanes, 2 = packed lanes + deferred general */
   uint32_t last_runs_per_trip; /* StoryRuns evaluated per warp trip by the last pass                                   */
   uint32_t last_eval_chunks;   /* run chunks the last bf_eval pipelined over its copy/compute streams (1 = serial)      */
-  uint32_t reserved0;
+  uint32_t arena_compactions;  /* times the topology arena was re-packed (dropped records reclaimed)                             */
 } bf_stats;
 int bf_get_stats(const bf_ctx* ctx, bf_stats* out);
 /* Device address + byte size of a topology record (for traffic accounting).   */

@@ -263,6 +263,32 @@ def test_drop_and_reuse_slot(fr):
     assert np.array_equal(got, want)
 
 
+def test_arena_compaction_keeps_live_topologies():
+    """one put + one drop per Story generation must not grow the arena without bound: when dropped records outweigh
+    the live ones the arena is re-packed, slots keep their ids and the surviving topologies still evaluate exactly"""
+    f = Frontier(0)
+    try:
+        n = 3000
+        ts = synth.topologies(3, 0, n, 256)
+        slots = f.put_topologies(ts)
+        L = make_layout(256, 0, A.F_ALL_OUT)
+        state = synth.state(3, 0, n, L, slots, ts)
+        want, wc = PK.evaluate(PK.PackedTopologies(ts, slots), L, state, threads=4)
+        used0 = f.stats()["arena_used_bytes"]
+        for gen in range(6):   # generations of other stories come and go
+            ts2 = synth.topologies(3, 1000000 + gen * n, n, 256)
+            s2 = f.put_topologies(ts2)
+            for s in s2:
+                f.drop_topology(int(s))
+        st = f.stats()
+        assert st["arena_compactions"] >= 1 and st["n_topologies"] == n
+        assert st["arena_used_bytes"] <= 3 * used0, st     # bounded: live records + at most the uncompacted tail
+        got, gc = f.eval(L, state)
+        assert np.array_equal(got, want) and gc == wc
+    finally:
+        f.close()
+
+
 @pytest.mark.parametrize("chunks", [0, 1, 5, 32])
 def test_pipelined_host_eval_matches_oracle(fr, monkeypatch, chunks):
     """bf_eval cuts large batches into run chunks whose H2D / kernel / D2H overlap on three streams; any chunking
