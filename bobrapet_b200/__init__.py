@@ -6,5 +6,5 @@ hand-written sm_100a CUDA kernels behind the C ABI of include/bobrafrontier.h.
 """
 from . import _abi  # noqa: F401
 from ._abi import FrontierError, load  # noqa: F401
-from .frontier import Frontier, TopologySet  # noqa: F401
+from .frontier import Frontier, FrontierGroup, TopologySet  # noqa: F401
 from .records import make_layout, pack_state, unpack_result  # noqa: F401

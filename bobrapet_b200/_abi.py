@@ -153,6 +153,15 @@ SYMBOLS = [
     ("bf_resident_download", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     ("bf_eval_compact", C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(CompactOut)]),
     ("bf_resident_tick_compact", C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(CompactOut), C.POINTER(Counts)]),
+    ("bf_group_create", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_uint32, C.POINTER(Config)]),
+    ("bf_group_destroy", None, [C.c_void_p]),
+    ("bf_group_size", C.c_uint32, [C.c_void_p]),
+    ("bf_group_ctx", C.c_void_p, [C.c_void_p, C.c_uint32]),
+    ("bf_group_last_error", C.c_char_p, [C.c_void_p]),
+    ("bf_group_shard_range", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("bf_group_topology_put_many", C.c_int, [C.c_void_p, C.POINTER(Topology), C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("bf_group_eval", C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Counts)]),
+    ("bf_group_schedule", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(SchedTables), C.POINTER(SchedOut)]),
     ("bf_alloc_pinned", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     ("bf_free_pinned", C.c_int, [C.c_void_p, C.c_void_p]),
     ("bf_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),

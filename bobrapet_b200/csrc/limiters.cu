@@ -174,15 +174,19 @@ __global__ void __launch_bounds__(256) sched_apply(const SchedParams P) {
   }
 }
 
-cudaError_t launch_schedule(const SchedParams& P, uint32_t sm_count, cudaStream_t stream) {
+// phases: 1 = totals (sched_init + sched_count), 2 = truncation against the totals (sched_apply), 3 = both.  A sharded
+// batch all-reduces the totals between the two (bf_group_schedule): sums of the running counts, maximum of the priorities.
+cudaError_t launch_schedule(const SchedParams& P, uint32_t sm_count, cudaStream_t stream, uint32_t phases) {
   const uint32_t wpb = 8;
   uint32_t grid = (P.n_runs + wpb - 1) / wpb;
   if (grid == 0) grid = 1;
   if (grid > sm_count * 8) grid = sm_count * 8;
   const uint32_t n_tab = P.n_stories > P.n_queues ? P.n_stories : P.n_queues;
-  sched_init<<<(n_tab + 255) / 256 + 1, 256, 0, stream>>>(P);
-  sched_count<<<grid, wpb * 32, 0, stream>>>(P);
-  sched_apply<<<grid, wpb * 32, 0, stream>>>(P);
+  if (phases & 1u) {
+    sched_init<<<(n_tab + 255) / 256 + 1, 256, 0, stream>>>(P);
+    sched_count<<<grid, wpb * 32, 0, stream>>>(P);
+  }
+  if (phases & 2u) sched_apply<<<grid, wpb * 32, 0, stream>>>(P);
   return cudaGetLastError();
 }
 

@@ -62,8 +62,12 @@ class TopologySet:
 
 
 class Frontier:
-    def __init__(self, device: int = 0, arena_bytes: int = 0):
+    def __init__(self, device: int = 0, arena_bytes: int = 0, _borrowed_ctx=None):
         self._lib = A.load()
+        self._owned = _borrowed_ctx is None
+        if _borrowed_ctx is not None:       # a shard's ctx owned by a FrontierGroup
+            self._ctx = C.c_void_p(_borrowed_ctx)
+            return
         self._ctx = C.c_void_p()
         cfg = A.Config(struct_size=C.sizeof(A.Config), device=device, arena_bytes=arena_bytes, max_topologies=0, flags=0)
         rc = self._lib.bf_create(C.byref(self._ctx), C.byref(cfg))
@@ -74,7 +78,8 @@ class Frontier:
     # -- lifecycle
     def close(self):
         if getattr(self, "_ctx", None):
-            self._lib.bf_destroy(self._ctx)
+            if self._owned:
+                self._lib.bf_destroy(self._ctx)
             self._ctx = None
 
     def __del__(self):
@@ -307,3 +312,89 @@ class Frontier:
         s = A.Stats()
         self._check(self._lib.bf_get_stats(self._ctx, C.byref(s)), "bf_get_stats")
         return {n: getattr(s, n) for n, _ in s._fields_}
+
+
+class FrontierGroup:
+    """One process, several GPUs: bf_group_* (a ctx per device + an NCCL communicator over them).  Runs shard into
+    contiguous blocks; the only exchange of a pass is the all-gather of the per-shard counts."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._lib = A.load()
+        self._g = C.c_void_p()
+        dev = (C.c_int32 * len(devices))(*devices)
+        rc = self._lib.bf_group_create(C.byref(self._g), dev, len(devices), None)
+        if rc != A.BF_OK:
+            self._g = None
+            raise A.FrontierError(rc, "bf_group_create(devices=%s)" % list(devices))
+        self.size = int(self._lib.bf_group_size(self._g))
+        self.shards = [Frontier(_borrowed_ctx=self._lib.bf_group_ctx(self._g, k)) for k in range(self.size)]
+
+    def close(self):
+        if getattr(self, "_g", None):
+            for s in self.shards:
+                s.close()
+            self._lib.bf_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != A.BF_OK:
+            raise A.FrontierError(rc, "%s: %s" % (what, self._lib.bf_group_last_error(self._g).decode()))
+
+    def shard_range(self, n_runs: int, shard: int):
+        first, count = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.bf_group_shard_range(self._g, n_runs, shard, C.byref(first), C.byref(count)), "bf_group_shard_range")
+        return first.value, count.value
+
+    def put_topologies_replicated(self, ts: TopologySet) -> np.ndarray:
+        desc = ts.descriptors()
+        slots = np.zeros(ts.count, dtype=np.uint32)
+        self._check(self._lib.bf_group_topology_put_many(self._g, desc.ctypes.data_as(C.POINTER(A.Topology)), ts.count,
+                                                         slots.ctypes.data_as(C.POINTER(C.c_uint32))), "bf_group_topology_put_many")
+        return slots
+
+    def eval(self, L: A.Layout, state: np.ndarray, result: Optional[np.ndarray] = None, flags: int = 0, max_iterations: int = 0):
+        """bf_group_eval -> (result, global counts, per-shard counts)"""
+        n = int(state.shape[0])
+        assert state.dtype == np.uint8 and state.flags["C_CONTIGUOUS"] and state.shape[1] == L.state_stride
+        if result is None:
+            result = np.zeros((n, L.result_stride), dtype=np.uint8)
+        counts = A.Counts()
+        per = (A.Counts * self.size)()
+        b = A.Batch(struct_size=C.sizeof(A.Batch), n_runs=n, flags=flags, max_iterations=max_iterations, layout=L,
+                    state=state.ctypes.data, result=result.ctypes.data, expansion=None, expansion_cap=0, counts=C.addressof(counts))
+        self._check(self._lib.bf_group_eval(self._g, C.byref(b), per), "bf_group_eval")
+        as_dict = lambda c: {"ready": c.ready, "skip": c.skip, "expansion": c.expansion, "evals": c.evals}
+        return result, as_dict(counts), [as_dict(c) for c in per]
+
+    def schedule(self, L: A.Layout, n_runs: int, sched_runs: np.ndarray, story_limit, queue_limit, queue_aging_s,
+                 global_limit: int = 0, story_running_base=None, queue_running_base=None, global_running_base: int = 0,
+                 queue_max_priority_base=None):
+        """bf_group_schedule: must follow eval() of the same batch; limits and priority ordering hold across all shards."""
+        assert sched_runs.nbytes == 32 * n_runs and sched_runs.flags["C_CONTIGUOUS"]
+        sl = np.ascontiguousarray(story_limit, dtype=np.int32)
+        ql = np.ascontiguousarray(queue_limit, dtype=np.int32)
+        qa = np.ascontiguousarray(queue_aging_s, dtype=np.int32)
+        sb = None if story_running_base is None else np.ascontiguousarray(story_running_base, dtype=np.uint32)
+        qb = None if queue_running_base is None else np.ascontiguousarray(queue_running_base, dtype=np.uint32)
+        pb = None if queue_max_priority_base is None else np.ascontiguousarray(queue_max_priority_base, dtype=np.int32)
+        t = A.SchedTables(struct_size=C.sizeof(A.SchedTables), n_stories=sl.size, n_queues=ql.size, global_limit=global_limit,
+                          global_running_base=global_running_base, story_limit=sl.ctypes.data,
+                          story_running_base=(sb.ctypes.data if sb is not None else None), queue_limit=ql.ctypes.data,
+                          queue_aging_s=qa.ctypes.data, queue_running_base=(qb.ctypes.data if qb is not None else None),
+                          queue_max_priority_base=(pb.ctypes.data if pb is not None else None))
+        rec = np.zeros((n_runs, A.sched_stride(L.words)), dtype=np.uint8)
+        sr, qr = np.zeros(max(sl.size, 1), dtype=np.uint32), np.zeros(max(ql.size, 1), dtype=np.uint32)
+        mp, gr = np.zeros(max(ql.size, 1), dtype=np.int32), np.zeros(1, dtype=np.uint32)
+        out = A.SchedOut(struct_size=C.sizeof(A.SchedOut), records=rec.ctypes.data, story_running=sr.ctypes.data,
+                         queue_running=qr.ctypes.data, queue_max_priority=mp.ctypes.data, global_running=gr.ctypes.data)
+        b = A.Batch(struct_size=C.sizeof(A.Batch), n_runs=n_runs, layout=L)
+        self._check(self._lib.bf_group_schedule(self._g, C.byref(b), C.c_void_p(sched_runs.ctypes.data), C.byref(t), C.byref(out)),
+                    "bf_group_schedule")
+        return {"records": rec, "story_running": sr[:sl.size], "queue_running": qr[:ql.size], "queue_max_priority": mp[:ql.size],
+                "global_running": int(gr[0])}

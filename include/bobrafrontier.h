@@ -469,6 +469,41 @@ int bf_eval_compact(bf_ctx* ctx, const bf_batch* batch, bf_compact_out* out);
 int bf_resident_tick_compact(bf_ctx* ctx, uint32_t handle, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs,
                              uint32_t flags, uint32_t max_iterations, bf_compact_out* out, bf_counts* counts);
 
+/* ------------------------------------------------------------------ device groups (SURVEY.md row e)
+ * The reference is ONE operator process (cmd/main.go:220, StoryRunReconciler storyrun_controller.go:216), so the
+ * multi-GPU path must be reachable from one process through this ABI: a group owns one ctx per device and an NCCL
+ * communicator over them (ncclCommInitAll; libnccl.so.2 is loaded at bf_group_create, the library itself does not
+ * link it).  StoryRuns are independent, so a batch shards into contiguous blocks of ceil(N / G) runs with NO
+ * data-path collective; the one exchange of a pass is an ncclAllGather of each shard's 32-byte counts block, which
+ * gives every shard the global totals and the offsets of its compacted lists.  Topologies live where their runs
+ * are: put them through the shard's own ctx (bf_group_ctx + bf_topology_put_many; slot ids are per shard) or
+ * replicate a shared set on every device with bf_group_topology_put_many (same slot ids everywhere).
+ * Collective failures come back as BF_ENCCL with the NCCL text in bf_group_last_error.                            */
+typedef struct bf_group bf_group;
+
+int bf_group_create(bf_group** out, const int32_t* devices, uint32_t n_devices, const bf_config* cfg /* device field ignored; may be NULL */);
+void bf_group_destroy(bf_group* g);
+uint32_t bf_group_size(const bf_group* g);
+bf_ctx* bf_group_ctx(bf_group* g, uint32_t shard);
+const char* bf_group_last_error(const bf_group* g);
+/* Runs [*first, *first + *count) of an n_runs batch belong to `shard`.                                            */
+int bf_group_shard_range(const bf_group* g, uint32_t n_runs, uint32_t shard, uint32_t* first, uint32_t* count);
+/* The same topologies on every device; fails with BF_ETOPO if the shards' slot tables have diverged (mixing
+ * replicated and per-shard uploads is allowed only when the replicated ones come first).                          */
+int bf_group_topology_put_many(bf_group* g, const bf_topology* topos, uint32_t count, uint32_t* slots_out);
+/* One pass over a HOST batch sharded across the group: every shard runs bf_eval on its block of runs (its own H2D /
+ * kernels / D2H pipeline, all shards concurrently), then the counts are all-gathered on the devices.
+ * shard_counts[n_devices] (may be NULL) receives the gathered per-shard counts, batch->counts the global totals.
+ * BF_EVAL_EXPANSION is not offered here (per-shard lists: call bf_eval on bf_group_ctx).                           */
+int bf_group_eval(bf_group* g, const bf_batch* batch, bf_counts* shard_counts);
+/* bf_schedule for a batch evaluated by the IMMEDIATELY PRECEDING bf_group_eval: every shard counts its own Running
+ * StepRuns and demand, the per-story / per-queue / global totals are all-reduced (sum) and the per-queue highest
+ * effective priority (max) across the shards, then every shard truncates its ready sets against the GLOBAL totals —
+ * the limits and the priority ordering hold across the whole batch, as enforcePriorityOrdering / enforceSchedulingLimits
+ * (dag.go:1801-1946) hold across the cluster.  runs[n_runs] and out->records cover the whole batch; the totals arrays
+ * of `out` receive the global values.                                                                             */
+int bf_group_schedule(bf_group* g, const bf_batch* batch, const bf_sched_run* runs, const bf_sched_tables* tables, bf_sched_out* out);
+
 /* Pinned host memory for batches (cgo: memory with no Go pointers).           */
 int bf_alloc_pinned(bf_ctx* ctx, size_t bytes, void** out);
 int bf_free_pinned(bf_ctx* ctx, void* p);
