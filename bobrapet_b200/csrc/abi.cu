@@ -617,7 +617,7 @@ int compact_arena(bf_ctx* c, size_t incoming) {
 // Enqueue on `s` (after the passes that wrote d_result): compaction kernels, D2H of the summary words, of the event total
 // and of a first slice of the event list sized from the previous pass (the total is only known after the sync).
 int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, uint32_t n_runs, bf_compact_out* out, cudaStream_t s,
-                    uint64_t* first_slice) {
+                    uint64_t* first_slice, bool with_rejected) {
   const uint64_t cap = out->events ? out->events_cap : 0;
   if (int rc = ensure_dev(c, c->d_summary, c->d_summary_cap, n_runs ? n_runs : 1)) return rc;
   if (int rc = ensure_dev(c, c->d_events, c->d_events_cap, cap ? (size_t)cap : 1)) return rc;
@@ -627,20 +627,32 @@ int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, uint
   P.block_sums = c->d_cblock + 1; P.total = c->d_cblock;
   P.n_runs = n_runs; P.words = L.words; P.result_stride = L.result_stride; P.off_ready = L.off_ready; P.off_skip = L.off_skip;
   P.off_fail = L.off_fail; P.off_needs_cond = L.off_needs_cond; P.off_skip_dep = L.off_skip_dep;
+  // the small results (event total, counts, rejected deltas) are written to the pinned block by the last kernel itself:
+  // three fewer latency-bound D2H copies per tick
+  unsigned long long* tail = reinterpret_cast<unsigned long long*>(c->h_counts + 2);   // 6 x u64 in the pinned block
+  P.host_tail = tail; P.counts = c->d_counts; P.rejected = with_rejected ? c->d_rejected : nullptr;
+  if (n_runs == 0) BF_CUDA(c, cudaStreamSynchronize(s));   // the empty case stores to the pinned block from the host
   BF_CUDA(c, bf::launch_compact(P, s));
   c->stats.kernel_launches += n_runs ? 2 : 0;
-  unsigned long long* h_total = reinterpret_cast<unsigned long long*>(c->h_counts + 2);
-  BF_CUDA(c, cudaMemcpyAsync(h_total, c->d_cblock, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  uint64_t guess = c->last_events + c->last_events / 32 + 2048;   // the previous tick's list + 3 %: one copy in the steady state
+  if (guess > cap) guess = cap;
+  if (guess) BF_CUDA(c, cudaMemcpyAsync(out->events, c->d_events, (size_t)guess * sizeof(bf_step_event), cudaMemcpyDeviceToHost, s));
   if (out->summary && n_runs) BF_CUDA(c, cudaMemcpyAsync(out->summary, c->d_summary, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
+  *first_slice = guess;
+  return BF_OK;
+}
+#if 0
   uint64_t guess = c->last_events + c->last_events / 4 + 4096;
   if (guess > cap) guess = cap;
   if (guess) BF_CUDA(c, cudaMemcpyAsync(out->events, c->d_events, (size_t)guess * sizeof(bf_step_event), cudaMemcpyDeviceToHost, s));
   *first_slice = guess;
   return BF_OK;
 }
+#endif
 // after the stream has been synchronised: fetch what the first slice missed
 int compact_finish(bf_ctx* c, bf_compact_out* out, uint64_t first_slice) {
-  const uint64_t total = *reinterpret_cast<const unsigned long long*>(c->h_counts + 2);
+  const unsigned long long* tail = reinterpret_cast<const unsigned long long*>(c->h_counts + 2);
+  const uint64_t total = tail[0];
   const uint64_t cap = out->events ? out->events_cap : 0;
   const uint64_t have = total < cap ? total : cap;
   if (have > first_slice)
@@ -1008,9 +1020,11 @@ static int eval_host(bf_ctx* c, const bf_batch* b, bf_compact_out* co) {
       }
       if (rb && !co) BF_CUDA(c, cudaMemcpyAsync(hr + ro, c->d_result + ro, rb, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
     }
-    BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof hc, cudaMemcpyDeviceToHost, s));
-    if (co)
-      if (int rc = compact_enqueue(c, L, c->d_result, b->n_runs, co, s, &first_slice)) return rc;
+    if (co) {   // counts travel with the compaction's tail block
+      if (int rc = compact_enqueue(c, L, c->d_result, b->n_runs, co, s, &first_slice, false)) return rc;
+    } else {
+      BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof hc, cudaMemcpyDeviceToHost, s));
+    }
     return BF_OK;
   };
   const int body_rc = body();
@@ -1023,6 +1037,7 @@ static int eval_host(bf_ctx* c, const bf_batch* b, bf_compact_out* co) {
   if (body_rc != BF_OK) return body_rc;
   if (e_sync != cudaSuccess) return cuda_fail(c, e_sync, "cudaStreamSynchronize");
   hc = *c->h_counts;
+  if (co) memcpy(&hc, reinterpret_cast<const unsigned long long*>(c->h_counts + 2) + 1, sizeof hc);
   c->stats.last_eval_chunks = chunks;
   c->last_eval_valid = true; c->last_eval_runs = b->n_runs; c->last_eval_layout = L;
   c->last_state = c->d_state; c->last_result = c->d_result;
@@ -1300,10 +1315,12 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
         BF_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(result) + lo * L.result_stride, r->d_result + lo * L.result_stride,
                                    (hi - lo) * L.result_stride, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
     }
-    BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(bf_counts), cudaMemcpyDeviceToHost, s));
-    if (co)
-      if (int rc2 = compact_enqueue(c, L, r->d_result, n_runs, co, s, &first_slice)) return rc2;
-    BF_CUDA(c, cudaMemcpyAsync(h_rej, c->d_rejected, 4, cudaMemcpyDeviceToHost, s));
+    if (co) {   // counts and the rejected-delta counter travel with the compaction's tail block
+      if (int rc2 = compact_enqueue(c, L, r->d_result, n_runs, co, s, &first_slice, true)) return rc2;
+    } else {
+      BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(bf_counts), cudaMemcpyDeviceToHost, s));
+      BF_CUDA(c, cudaMemcpyAsync(h_rej, c->d_rejected, 4, cudaMemcpyDeviceToHost, s));
+    }
     return BF_OK;
   };
   const int rc = body();
@@ -1314,6 +1331,11 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
   }
   if (rc != BF_OK) return rc;
   if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
+  if (co) {
+    const unsigned long long* tail = reinterpret_cast<const unsigned long long*>(c->h_counts + 2);
+    memcpy(c->h_counts, tail + 1, sizeof(bf_counts));
+    *h_rej = (uint32_t)tail[5];
+  }
   if (counts) *counts = *c->h_counts;
   c->stats.last_eval_chunks = chunks;
   c->last_eval_valid = true; c->last_eval_runs = n_runs; c->last_eval_layout = L;

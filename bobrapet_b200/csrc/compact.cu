@@ -9,6 +9,7 @@
 // so the list is bit-exact against the oracle's masks).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/bobrafrontier.h"
 #include "device_record.h"
@@ -99,7 +100,14 @@ __global__ void __launch_bounds__(CB) compact_emit(const CompactParams P) {
   __syncthreads();
   const uint32_t before = inc - c + (warp ? sh[warp - 1] : 0u);
   unsigned long long pos = base_s + before;
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == CB - 1) *P.total = pos + c;  // the batch's event count
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == CB - 1) {
+    *P.total = pos + c;  // the batch's event count
+    if (P.host_tail) {   // posted writes to pinned host memory; visible to the host once the stream has been synchronised
+      P.host_tail[0] = pos + c;
+      for (int k = 0; k < 4; ++k) P.host_tail[1 + k] = P.counts ? P.counts[k] : 0ull;
+      P.host_tail[5] = P.rejected ? (unsigned long long)*P.rejected : 0ull;
+    }
+  }
   if (!alive || c == 0) return;
   for (uint32_t w = 0; w < P.words; ++w) {
     const uint32_t rd = reinterpret_cast<const uint32_t*>(rr + P.off_ready)[w], sk = reinterpret_cast<const uint32_t*>(rr + P.off_skip)[w];
@@ -123,7 +131,10 @@ __global__ void __launch_bounds__(CB) compact_emit(const CompactParams P) {
 
 // scratch: block_sums needs ceil(n / 512) u64
 cudaError_t launch_compact(const CompactParams& P, cudaStream_t stream) {
-  if (P.n_runs == 0) return cudaMemsetAsync(P.total, 0, sizeof(unsigned long long), stream);
+  if (P.n_runs == 0) {
+    if (P.host_tail) memset(P.host_tail, 0, 6 * sizeof(unsigned long long));   // pinned host memory: plain store
+    return cudaMemsetAsync(P.total, 0, sizeof(unsigned long long), stream);
+  }
   const uint32_t nb = (P.n_runs + CB - 1) / CB;
   compact_count<<<nb, CB, 0, stream>>>(P);
   compact_emit<<<nb, CB, 0, stream>>>(P);

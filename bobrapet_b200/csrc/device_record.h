@@ -107,6 +107,11 @@ struct CompactParams {
   unsigned long long cap;
   unsigned long long* block_sums;    // scratch: ceil(n_runs / 512)
   unsigned long long* total;         // out: events of the batch
+  // the pass's small results, written straight to pinned host memory by the last block (no separate small D2H copies):
+  // host_tail[0] = events, [1..4] = bf_counts, [5] = rejected deltas
+  unsigned long long* host_tail;     // device-visible address of the pinned block, or nullptr
+  const unsigned long long* counts;  // device bf_counts of the pass
+  const uint32_t* rejected;          // device counter of rejected deltas, or nullptr
   uint32_t n_runs, words, result_stride, off_ready, off_skip, off_fail, off_needs_cond, off_skip_dep;
 };
 

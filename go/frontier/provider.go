@@ -1,5 +1,9 @@
 package frontier
 
+import (
+	bubuv1alpha1 "github.com/bubustack/bobrapet/api/v1alpha1"
+)
+
 // FrontierProvider is the seam DAGReconciler gets (SOURCE ONLY, see frontier.go).
 //
 // internal/controller/runs/dag.go:1708 today:
@@ -9,23 +13,55 @@ package frontier
 //
 // becomes
 //
-//	if row, ok := r.Frontier.Lookup(srun.UID, srun.ResourceVersion); ok {
-//	    readySteps, skippedSteps, skippedReasons = row.Steps(steps)   // bit i of ready/skip -> &steps[i]
+//	if row, ok := r.Frontier.Lookup(string(srun.UID), srun.ResourceVersion); ok {
+//	    readySteps, skippedSteps, skippedReasons = row.Steps(allStorySteps(story))
 //	} else {
-//	    ... the Go path above (first sight of a run, packer miss, or bf_eval error)
+//	    ... the Go path above (first sight of a run, packer miss, or a bf_eval error)
 //	}
 //
 // Ready bits are LSB-first in list order, so the concurrency limiters' readySteps[:slots] (dag.go:1796-1798)
-// keep working on the slice returned by row.Steps.
+// keep working on the slice returned by Row.Steps.
 type FrontierProvider interface {
 	// Lookup returns the result row computed for this StoryRun at exactly this resourceVersion, if any.
 	Lookup(uid string, resourceVersion string) (Row, bool)
 }
 
-// Row is one StoryRun's result record.
+// Row is one StoryRun's result of the last tick, decoded from the compact events (or from a mask record).
 type Row struct {
-	Summary           uint32
-	Ready, Skip       []uint32 // bit masks, step i = bit i%32 of word i/32
-	SkipDep, NeedCond []uint32
-	PhaseOut          []uint32 // 4 bit planes
+	Summary uint32      // BF_SUM_*: group evaluated, mainDone / mainFailed flags, "some phase changed"
+	Events  []StepEvent // this run's slice of the tick's event list (run-major, so it is contiguous)
+	// FailedDep names, per skipped step, the dependency that failed — "Skipped due to failed dependency: <d>"
+	// (dag.go:2735-2739): the lowest index among the step's needs whose phase is terminal and not Succeeded/Skipped
+	// (the packer fills it from the host copy of the phases; the kernel reports only WHICH steps were skipped for it).
+	FailedDep map[uint16]string
+}
+
+const (
+	evtReady   = 0x1 // BF_EVT_READY
+	evtSkip    = 0x2 // BF_EVT_SKIP
+	evtSkipDep = 0x10
+)
+
+// Steps turns the row back into the three results of findReadySteps (dag.go:2631-2641) over `steps` =
+// allStorySteps(story) — index i of the packed topology is &steps[i].
+func (r Row) Steps(steps []bubuv1alpha1.Step) (ready, skipped []*bubuv1alpha1.Step, reasons map[string]string) {
+	reasons = map[string]string{}
+	for _, e := range r.Events {
+		if int(e.Step) >= len(steps) {
+			continue
+		}
+		st := &steps[e.Step]
+		switch {
+		case e.Kind&evtReady != 0:
+			ready = append(ready, st)
+		case e.Kind&evtSkip != 0:
+			skipped = append(skipped, st)
+			if e.Kind&evtSkipDep != 0 || r.FailedDep[e.Step] != "" {
+				reasons[st.Name] = "Skipped due to failed dependency: " + r.FailedDep[e.Step] // dag.go:2736
+			} else {
+				reasons[st.Name] = "Skipped due to 'if' condition" // dag.go:2831
+			}
+		}
+	}
+	return ready, skipped, reasons
 }

@@ -22,7 +22,7 @@ def _device_counts():
     return [g for g in (1, 2, 3, 4, 8) if g <= n]
 
 
-@pytest.fixture(scope="module", params=_device_counts() if True else [1])
+@pytest.fixture(params=_device_counts())
 def group(request):
     g = FrontierGroup(list(range(request.param)))
     yield g
