@@ -10,8 +10,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -622,8 +624,20 @@ int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, uint
   if (int rc = ensure_dev(c, c->d_summary, c->d_summary_cap, n_runs ? n_runs : 1)) return rc;
   if (int rc = ensure_dev(c, c->d_events, c->d_events_cap, cap ? (size_t)cap : 1)) return rc;
   if (int rc = ensure_dev(c, c->d_cblock, c->d_cblock_cap, (size_t)(n_runs + 511) / 512 + 2)) return rc;
+  // Zero-copy results: when the caller's buffers are pinned host memory (bf_alloc_pinned) the kernels write the summary
+  // words and the event list straight into them over PCIe — no D2H copy commands, nothing to size in advance, and the
+  // transfer overlaps the compaction.  Pageable buffers take the device list + copy path.
+  auto host_mapped = [&](const void* p) -> void* {
+    if (!p) return nullptr;
+    if (const char* e = getenv("BF_ZERO_COPY")) if (!strcmp(e, "0")) return nullptr;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+  };
+  bf_step_event* zc_events = cap ? static_cast<bf_step_event*>(host_mapped(out->events)) : nullptr;
+  uint32_t* zc_summary = (out->summary && n_runs) ? static_cast<uint32_t*>(host_mapped(out->summary)) : nullptr;
   bf::CompactParams P{};
-  P.result = d_result; P.summary = c->d_summary; P.events = c->d_events; P.cap = cap;
+  P.result = d_result; P.summary = zc_summary ? zc_summary : c->d_summary; P.events = zc_events ? zc_events : c->d_events; P.cap = cap;
   P.block_sums = c->d_cblock + 1; P.total = c->d_cblock;
   P.n_runs = n_runs; P.words = L.words; P.result_stride = L.result_stride; P.off_ready = L.off_ready; P.off_skip = L.off_skip;
   P.off_fail = L.off_fail; P.off_needs_cond = L.off_needs_cond; P.off_skip_dep = L.off_skip_dep;
@@ -636,8 +650,9 @@ int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, uint
   c->stats.kernel_launches += n_runs ? 2 : 0;
   uint64_t guess = c->last_events + c->last_events / 32 + 2048;   // the previous tick's list + 3 %: one copy in the steady state
   if (guess > cap) guess = cap;
-  if (guess) BF_CUDA(c, cudaMemcpyAsync(out->events, c->d_events, (size_t)guess * sizeof(bf_step_event), cudaMemcpyDeviceToHost, s));
-  if (out->summary && n_runs) BF_CUDA(c, cudaMemcpyAsync(out->summary, c->d_summary, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
+  if (zc_events) guess = cap;                                      // already in the caller's buffer: nothing left to fetch
+  else if (guess) BF_CUDA(c, cudaMemcpyAsync(out->events, c->d_events, (size_t)guess * sizeof(bf_step_event), cudaMemcpyDeviceToHost, s));
+  if (out->summary && n_runs && !zc_summary) BF_CUDA(c, cudaMemcpyAsync(out->summary, c->d_summary, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
   *first_slice = guess;
   return BF_OK;
 }
@@ -668,22 +683,43 @@ int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_
   size_t total = 0;
   std::string why;
   const bool csr_only = force_csr();
-  for (uint32_t i = 0; i < count; ++i) {
-    const int rc = plan_record(topos[i], plans[i], why, host_kahn, csr_only);
-    if (rc != BF_OK) return fail(c, rc, "topology " + std::to_string(i) + ": " + why);
-    total += plans[i].rec_bytes;
-  }
+  // validation (Kahn) and record building are per topology: spread a bulk upload over the host cores
+  const uint32_t n_thr = count >= 512 ? std::min<uint32_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  auto parallel_for = [&](auto&& fn) {
+    if (n_thr == 1) { fn(0u, count); return; }
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < n_thr; ++t)
+      th.emplace_back([&, t] { fn((uint32_t)((uint64_t)count * t / n_thr), (uint32_t)((uint64_t)count * (t + 1) / n_thr)); });
+    for (auto& x : th) x.join();
+  };
+  std::vector<int> rcs(count, BF_OK);
+  std::mutex why_mu;
+  uint32_t first_bad = count;
+  parallel_for([&](uint32_t lo, uint32_t hi) {
+    std::string w;
+    for (uint32_t i = lo; i < hi; ++i) {
+      rcs[i] = plan_record(topos[i], plans[i], w, host_kahn, csr_only);
+      if (rcs[i] != BF_OK) {
+        std::lock_guard<std::mutex> g(why_mu);
+        if (i < first_bad) { first_bad = i; why = w; }
+        return;
+      }
+    }
+  });
+  if (first_bad < count) return fail(c, rcs[first_bad], "topology " + std::to_string(first_bad) + ": " + why);
+  for (uint32_t i = 0; i < count; ++i) total += plans[i].rec_bytes;
   if (c->arena_dead > ((size_t)1 << 20) && c->arena_dead * 2 > c->arena_used)
     if (int rc = compact_arena(c, total)) return rc;
   const size_t base = round_up_sz(c->arena_used, 16);
   if (int rc = grow_arena(c, base + total)) return rc;
   std::vector<uint8_t> staging;
   try { staging.resize(total); } catch (const std::bad_alloc&) { return fail(c, BF_ENOMEM, "host staging allocation failed"); }
+  std::vector<size_t> rec_off(count);
   size_t off = 0;
-  for (uint32_t i = 0; i < count; ++i) {
-    build_record(topos[i], plans[i], staging.data() + off);
-    off += plans[i].rec_bytes;
-  }
+  for (uint32_t i = 0; i < count; ++i) { rec_off[i] = off; off += plans[i].rec_bytes; }
+  parallel_for([&](uint32_t lo, uint32_t hi) {
+    for (uint32_t i = lo; i < hi; ++i) build_record(topos[i], plans[i], staging.data() + rec_off[i]);
+  });
   if (total) BF_CUDA(c, cudaMemcpy(c->arena + base, staging.data(), total, cudaMemcpyHostToDevice));
   off = 0;
   for (uint32_t i = 0; i < count; ++i) {

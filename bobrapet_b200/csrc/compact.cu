@@ -17,6 +17,7 @@
 namespace bf {
 
 constexpr int CB = 512;  // runs per block (one thread per run)
+constexpr uint32_t STAGE_EVENTS = 4096;  // events of a block staged in shared memory (32 KB)
 
 __device__ __forceinline__ uint32_t union_word(const CompactParams& P, const uint8_t* rr, uint32_t w) {
   uint32_t u = reinterpret_cast<const uint32_t*>(rr + P.off_ready)[w] | reinterpret_cast<const uint32_t*>(rr + P.off_skip)[w];
@@ -107,6 +108,37 @@ __global__ void __launch_bounds__(CB) compact_emit(const CompactParams P) {
       for (int k = 0; k < 4; ++k) P.host_tail[1 + k] = P.counts ? P.counts[k] : 0ull;
       P.host_tail[5] = P.rejected ? (unsigned long long)*P.rejected : 0ull;
     }
+  }
+  // Small blocks of the list are staged in shared memory and written out by consecutive threads: the destination may be
+  // PINNED HOST memory (zero-copy results: no D2H copy command at all), where scattered 8-byte stores would each be a
+  // PCIe write of their own; staged, a warp writes 256 contiguous bytes per instruction.
+  __shared__ bf_step_event stage[STAGE_EVENTS];
+  const uint32_t btot = sh[CB / 32 - 1];
+  const bool staged = btot <= STAGE_EVENTS;
+  if (staged) {
+    if (alive && c != 0) {
+      uint32_t at = before;
+      for (uint32_t w = 0; w < P.words; ++w) {
+        const uint32_t rd = reinterpret_cast<const uint32_t*>(rr + P.off_ready)[w], sk = reinterpret_cast<const uint32_t*>(rr + P.off_skip)[w];
+        const uint32_t fl = P.off_fail != BF_OFF_NONE ? reinterpret_cast<const uint32_t*>(rr + P.off_fail)[w] : 0u;
+        const uint32_t nc = P.off_needs_cond != BF_OFF_NONE ? reinterpret_cast<const uint32_t*>(rr + P.off_needs_cond)[w] : 0u;
+        const uint32_t sd = P.off_skip_dep != BF_OFF_NONE ? reinterpret_cast<const uint32_t*>(rr + P.off_skip_dep)[w] : 0u;
+        for (uint32_t u = rd | sk | fl | nc | sd; u; u &= u - 1) {
+          const uint32_t b = __ffs(u) - 1;
+          bf_step_event e;
+          e.run = r;
+          e.step = (uint16_t)(w * 32u + b);
+          e.kind = (uint16_t)(((rd >> b) & 1u) * BF_EVT_READY | ((sk >> b) & 1u) * BF_EVT_SKIP | ((fl >> b) & 1u) * BF_EVT_FAIL |
+                              ((nc >> b) & 1u) * BF_EVT_NEEDS_COND | ((sd >> b) & 1u) * BF_EVT_SKIP_DEP);
+          stage[at++] = e;
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned long long base = base_s;
+    for (uint32_t i = threadIdx.x; i < btot; i += CB)
+      if (base + i < P.cap) P.events[base + i] = stage[i];
+    return;
   }
   if (!alive || c == 0) return;
   for (uint32_t w = 0; w < P.words; ++w) {

@@ -26,10 +26,23 @@ def _check(fr, ts, slots, L, state, flags=0, cap=None, want=None, wcounts=None):
         want, wcounts = PK.evaluate(PK.PackedTopologies(ts, slots), L, state, flags, 0, threads=8)
     wsum, wev = PK.compact_events(L, want)
     cap = len(wev) + 16 if cap is None else cap
+    # pageable buffers: device list + D2H copies; pinned buffers (bf_alloc_pinned): the kernels write the caller's memory directly
     summary, events, n_events, counts = fr.eval_compact(L, state, cap, flags=flags)
     assert n_events == len(wev) and counts == wcounts
     assert np.array_equal(summary, wsum)
     assert np.array_equal(events, wev[:cap])
+    n = state.shape[0]
+    p_sum = fr.alloc_pinned(max(n, 1) * 4).view(np.uint32)
+    p_ev = fr.alloc_pinned(max(cap, 1) * 8).view(fr.EVENT_DTYPE)
+    p_sum[:] = 0xABABABAB
+    try:
+        summary, events, n_events, counts = fr.eval_compact(L, state, cap, flags=flags, summary=p_sum, events=p_ev)
+        assert n_events == len(wev) and counts == wcounts
+        assert np.array_equal(summary, wsum)
+        assert np.array_equal(events, wev[:cap])
+    finally:
+        fr.free_pinned(p_sum.view(np.uint8))
+        fr.free_pinned(p_ev.view(np.uint8))
     return n_events
 
 
