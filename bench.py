@@ -530,19 +530,20 @@ def e2e_legs(g, live, n_runs, S, steps):
             "d2h_bytes_per_step": int(n_runs * Lk.result_stride + 32), "steps": k_e2e,
             "api": "bf_eval (host buffers, synchronous): H2D of every state record + frontier kernel + D2H of every result record"}
     legs = {"full_upload": full}
-    # compact results: (run, step, kind) events + one summary word per run instead of 80-byte mask records
+    # compact results: one head word per run + one 16-bit event per ready / skipped step instead of 80-byte mask records
     ev_cap = int(1.5 * (live.counts0[0] + live.counts0[1])) + 65536
-    h_sum = fr.alloc_pinned(n_runs * 4).view(np.uint32)
-    h_ev = fr.alloc_pinned(ev_cap * 8).view(fr.EVENT_DTYPE)
-    n_ev = [0]
+    h_head = fr.alloc_pinned(n_runs * 4).view(np.uint32)
+    h_ev = fr.alloc_pinned(ev_cap * 2).view(np.uint16)
+    last = [0, 0]
 
     def call_compact(i):
-        n_ev[0] = fr.eval_compact(Lk, hs, ev_cap, summary=h_sum, events=h_ev)[2]
+        r = fr.eval_compact(Lk, hs, ev_cap, head=h_head, events=h_ev)
+        last[0] = r[2]
     try:
         dtc = timed_calls(call_compact)
         legs["full_upload_compact"] = {"value": evals_per_pass * k_e2e / dtc, "unit": UNIT, "h2d_bytes_per_step": int(n_runs * Lk.state_stride),
-                                       "d2h_bytes_per_step": int(n_runs * 4 + n_ev[0] * 8 + 40), "events_per_step": int(n_ev[0]),
-                                       "api": "bf_eval_compact: H2D of every state record + kernels + D2H of summary words and (run, step, kind) events"}
+                                       "d2h_bytes_per_step": int(n_runs * 4 + last[0] * 2 + 56), "events_per_step": int(last[0]),
+                                       "api": "bf_eval_compact: H2D of every state record + kernels + D2H of one head word per run and 16-bit events"}
     except Exception as ex:
         legs["full_upload_compact"] = {"error": str(ex)[:200]}
     # row f2 — the steady-state tick of the operator: the state stays resident on the device, a tick sends only deltas
@@ -566,14 +567,23 @@ def e2e_legs(g, live, n_runs, S, steps):
                                      "h2d_bytes_per_step": int(k_delta * 8), "d2h_bytes_per_step": int(n_runs * Lk.result_stride + 32),
                                      "api": "bf_resident_tick (deltas + pass + mask records, one call): state stays on the device (row f2)"}
 
-        def call_tick_compact(i):
-            n_ev[0] = fr.resident_tick_compact(hres, n_runs, dsets[i % 3], ev_cap, summary=h_sum, events=h_ev)[2]
-        dtk = timed_calls(call_tick_compact)
+        def tick(flags):
+            def call(i):
+                r = fr.resident_tick_compact(hres, n_runs, dsets[i % 3], ev_cap, flags=flags, head=h_head, events=h_ev)
+                last[0], last[1] = r[2], r[4]
+            return call
+        dtk = timed_calls(tick(0))
         e2e = {"value": evals_per_pass * k_e2e / dtk, "unit": UNIT, "h2d_bytes_per_step": int(k_delta * 8),
-               "d2h_bytes_per_step": int(n_runs * 4 + n_ev[0] * 8 + 40), "steps": k_e2e, "change_rate": 0.01,
-               "events_per_step": int(n_ev[0]),
+               "d2h_bytes_per_step": int(n_runs * 4 + last[0] * 2 + 56), "steps": k_e2e, "change_rate": 0.01,
+               "events_per_step": int(last[0]), "runs_listed_per_step": int(last[1]),
                "api": "bf_resident_tick_compact (host buffers, synchronous): H2D of the tick's deltas (8 B per changed code) + scatter + "
-                      "frontier kernel + on-device compaction + D2H of one summary word per run and one 8-byte event per ready / skipped step"}
+                      "frontier kernel + on-device compaction + D2H of one head word per run and one 16-bit event per ready / skipped step "
+                      "of EVERY run"}
+        dtc2 = timed_calls(tick(A.EVAL_CHANGED_ONLY))
+        legs["incremental_changed_only"] = {
+            "value": evals_per_pass * k_e2e / dtc2, "unit": UNIT, "change_rate": 0.01, "h2d_bytes_per_step": int(k_delta * 8),
+            "d2h_bytes_per_step": int(n_runs * 4 + last[0] * 2 + 56), "events_per_step": int(last[0]), "runs_listed_per_step": int(last[1]),
+            "api": "bf_resident_tick_compact with BF_EVAL_CHANGED_ONLY: events only for the runs whose result differs from the previous tick's"}
         fr.resident_destroy(hres)
         for d in dsets:
             fr.free_pinned(d.view(np.uint8))
@@ -585,7 +595,7 @@ def e2e_legs(g, live, n_runs, S, steps):
     e2e["topology_put_ms"] = live.topology_put_ms
     e2e["topology_put_note"] = ("bf_topology_put_many of this rank's %d topologies (%.0f MB of records), once per Story generation, "
                                 "outside the per-tick figure" % (n_runs, live.fr.stats()["arena_used_bytes"] / 3e6))
-    fr.free_pinned(h_sum.view(np.uint8))
+    fr.free_pinned(h_head.view(np.uint8))
     fr.free_pinned(h_ev.view(np.uint8))
     fr.free_pinned(hs.reshape(-1))
     fr.free_pinned(hr.reshape(-1))

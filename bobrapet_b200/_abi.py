@@ -100,12 +100,12 @@ class Stats(C.Structure):
 EVT_READY, EVT_SKIP, EVT_FAIL, EVT_NEEDS_COND, EVT_SKIP_DEP = 0x1, 0x2, 0x4, 0x8, 0x10  # BF_EVT_*
 
 
-class StepEvent(C.Structure):
-    _fields_ = [("run", C.c_uint32), ("step", C.c_uint16), ("kind", C.c_uint16)]
+HEAD_SUMMARY_MASK, HEAD_DEAD, HEAD_LISTED, HEAD_COUNT_SHIFT = 0x7FFF, 0x7FFF, 0x8000, 16  # BF_HEAD_*
+EVAL_CHANGED_ONLY = 0x10
 
 
 class CompactOut(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("summary", C.c_void_p), ("events", C.c_void_p),
+    _fields_ = [("struct_size", C.c_uint32), ("n_listed", C.c_uint32), ("head", C.c_void_p), ("events", C.c_void_p),
                 ("events_cap", C.c_uint64), ("n_events", C.c_uint64)]
 
 

@@ -47,7 +47,10 @@ struct Resident {  // a device-resident batch (row f2)
   bf_layout L{};
   uint32_t cap = 0;
   uint8_t* d_state = nullptr;
-  uint8_t* d_result = nullptr;
+  uint8_t* d_result = nullptr;       // records of the last pass
+  uint8_t* d_result_prev = nullptr;  // records of the pass before (changed-only compaction); allocated on first use
+  bool prev_valid = false;           // d_result holds a pass over the current device state lineage
+  uint32_t prev_runs = 0;            // ... over this many runs
 };
 
 struct TopoMeta {
@@ -95,9 +98,9 @@ struct bf_ctx {
   bf_counts* h_counts = nullptr;  // pinned landing zone for the counts block (a pageable target would make the copy synchronous)
   bf_expansion* d_exp = nullptr; size_t d_exp_cap = 0;
   // compact results (bf_eval_compact / bf_resident_tick_compact)
-  uint32_t* d_summary = nullptr; size_t d_summary_cap = 0;
-  bf_step_event* d_events = nullptr; size_t d_events_cap = 0;
-  unsigned long long* d_cblock = nullptr; size_t d_cblock_cap = 0;   // [0] = total, [1..] = per-block sums
+  uint32_t* d_head = nullptr; size_t d_head_cap = 0;
+  uint16_t* d_events = nullptr; size_t d_events_cap = 0;
+  unsigned long long* d_cblock = nullptr; size_t d_cblock_cap = 0;   // [0] = events, [1] = listed runs, [2..] = per-block sums
   uint64_t last_events = 0;                                          // events of the previous compact pass (sizes the first D2H)
   // scratch shared by both entry points
   uint32_t* d_exp_counts = nullptr; size_t d_exp_counts_cap = 0;
@@ -615,55 +618,44 @@ int compact_arena(bf_ctx* c, size_t incoming) {
   return BF_OK;
 }
 
-// ---- compact results: masks -> events on the device, then the two small D2H copies ----
-// Enqueue on `s` (after the passes that wrote d_result): compaction kernels, D2H of the summary words, of the event total
-// and of a first slice of the event list sized from the previous pass (the total is only known after the sync).
-int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, uint32_t n_runs, bf_compact_out* out, cudaStream_t s,
-                    uint64_t* first_slice, bool with_rejected) {
+// ---- compact results: masks -> heads + 16-bit events on the device, then two small D2H copies ----
+// Enqueue on `s` (after the passes that wrote d_result): compaction kernels, D2H of the head words and of a first slice of
+// the event list sized from the previous pass (the exact length is only known after the sync; it arrives, with the counts,
+// in the pinned tail block the last kernel writes itself).
+uint32_t result_tail_of(const bf_layout& L) {
+  uint32_t tail = (uint32_t)sizeof(bf_result_header);
+  auto upd = [&](uint32_t off, uint32_t len) { if (off != BF_OFF_NONE && off + len > tail) tail = off + len; };
+  upd(L.off_ready, L.words * 4); upd(L.off_skip, L.words * 4); upd(L.off_fail, L.words * 4);
+  upd(L.off_needs_cond, L.words * 4); upd(L.off_skip_dep, L.words * 4); upd(L.off_phase_out, L.words * 16);
+  return tail;
+}
+
+int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, const uint8_t* d_prev, uint32_t n_runs, bf_compact_out* out,
+                    cudaStream_t s, uint64_t* first_slice, bool with_rejected) {
   const uint64_t cap = out->events ? out->events_cap : 0;
-  if (int rc = ensure_dev(c, c->d_summary, c->d_summary_cap, n_runs ? n_runs : 1)) return rc;
+  if (int rc = ensure_dev(c, c->d_head, c->d_head_cap, n_runs ? n_runs : 1)) return rc;
   if (int rc = ensure_dev(c, c->d_events, c->d_events_cap, cap ? (size_t)cap : 1)) return rc;
-  if (int rc = ensure_dev(c, c->d_cblock, c->d_cblock_cap, (size_t)(n_runs + 511) / 512 + 2)) return rc;
-  // Zero-copy results: when the caller's buffers are pinned host memory (bf_alloc_pinned) the kernels write the summary
-  // words and the event list straight into them over PCIe — no D2H copy commands, nothing to size in advance, and the
-  // transfer overlaps the compaction.  Pageable buffers take the device list + copy path.
-  auto host_mapped = [&](const void* p) -> void* {
-    if (!p) return nullptr;
-    if (const char* e = getenv("BF_ZERO_COPY")) if (!strcmp(e, "0")) return nullptr;
-    cudaPointerAttributes a{};
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
-  };
-  bf_step_event* zc_events = cap ? static_cast<bf_step_event*>(host_mapped(out->events)) : nullptr;
-  uint32_t* zc_summary = (out->summary && n_runs) ? static_cast<uint32_t*>(host_mapped(out->summary)) : nullptr;
+  if (int rc = ensure_dev(c, c->d_cblock, c->d_cblock_cap, (size_t)(n_runs + 511) / 512 + 4)) return rc;
   bf::CompactParams P{};
-  P.result = d_result; P.summary = zc_summary ? zc_summary : c->d_summary; P.events = zc_events ? zc_events : c->d_events; P.cap = cap;
-  P.block_sums = c->d_cblock + 1; P.total = c->d_cblock;
-  P.n_runs = n_runs; P.words = L.words; P.result_stride = L.result_stride; P.off_ready = L.off_ready; P.off_skip = L.off_skip;
+  P.result = d_result; P.prev_result = d_prev; P.head = c->d_head; P.events = c->d_events; P.cap = cap;
+  P.block_sums = c->d_cblock + 2; P.total = c->d_cblock;
+  P.n_runs = n_runs; P.words = L.words; P.result_stride = L.result_stride; P.result_tail = result_tail_of(L);
+  P.off_ready = L.off_ready; P.off_skip = L.off_skip;
   P.off_fail = L.off_fail; P.off_needs_cond = L.off_needs_cond; P.off_skip_dep = L.off_skip_dep;
-  // the small results (event total, counts, rejected deltas) are written to the pinned block by the last kernel itself:
-  // three fewer latency-bound D2H copies per tick
-  unsigned long long* tail = reinterpret_cast<unsigned long long*>(c->h_counts + 2);   // 6 x u64 in the pinned block
+  // the small results (event total, counts, rejected deltas, listed runs) are written to the pinned block by the last kernel
+  // itself: no latency-bound small D2H copies
+  unsigned long long* tail = reinterpret_cast<unsigned long long*>(c->h_counts + 2);   // 7 x u64 in the pinned block
   P.host_tail = tail; P.counts = c->d_counts; P.rejected = with_rejected ? c->d_rejected : nullptr;
   if (n_runs == 0) BF_CUDA(c, cudaStreamSynchronize(s));   // the empty case stores to the pinned block from the host
   BF_CUDA(c, bf::launch_compact(P, s));
   c->stats.kernel_launches += n_runs ? 2 : 0;
-  uint64_t guess = c->last_events + c->last_events / 32 + 2048;   // the previous tick's list + 3 %: one copy in the steady state
+  uint64_t guess = c->last_events + c->last_events / 32 + 4096;   // the previous tick's list + 3 %: one copy in the steady state
   if (guess > cap) guess = cap;
-  if (zc_events) guess = cap;                                      // already in the caller's buffer: nothing left to fetch
-  else if (guess) BF_CUDA(c, cudaMemcpyAsync(out->events, c->d_events, (size_t)guess * sizeof(bf_step_event), cudaMemcpyDeviceToHost, s));
-  if (out->summary && n_runs && !zc_summary) BF_CUDA(c, cudaMemcpyAsync(out->summary, c->d_summary, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
+  if (guess) BF_CUDA(c, cudaMemcpyAsync(out->events, c->d_events, (size_t)guess * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+  if (out->head && n_runs) BF_CUDA(c, cudaMemcpyAsync(out->head, c->d_head, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
   *first_slice = guess;
   return BF_OK;
 }
-#if 0
-  uint64_t guess = c->last_events + c->last_events / 4 + 4096;
-  if (guess > cap) guess = cap;
-  if (guess) BF_CUDA(c, cudaMemcpyAsync(out->events, c->d_events, (size_t)guess * sizeof(bf_step_event), cudaMemcpyDeviceToHost, s));
-  *first_slice = guess;
-  return BF_OK;
-}
-#endif
 // after the stream has been synchronised: fetch what the first slice missed
 int compact_finish(bf_ctx* c, bf_compact_out* out, uint64_t first_slice) {
   const unsigned long long* tail = reinterpret_cast<const unsigned long long*>(c->h_counts + 2);
@@ -671,9 +663,10 @@ int compact_finish(bf_ctx* c, bf_compact_out* out, uint64_t first_slice) {
   const uint64_t cap = out->events ? out->events_cap : 0;
   const uint64_t have = total < cap ? total : cap;
   if (have > first_slice)
-    BF_CUDA(c, cudaMemcpy(out->events + first_slice, c->d_events + first_slice, (size_t)(have - first_slice) * sizeof(bf_step_event),
+    BF_CUDA(c, cudaMemcpy(out->events + first_slice, c->d_events + first_slice, (size_t)(have - first_slice) * sizeof(uint16_t),
                           cudaMemcpyDeviceToHost));
   out->n_events = total;
+  out->n_listed = (uint32_t)tail[6];
   c->last_events = total;
   return BF_OK;
 }
@@ -809,8 +802,8 @@ void bf_destroy(bf_ctx* c) {
   cudaFreeHost(c->h_counts);
   cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
   cudaFree(c->d_defer); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums); cudaFree(c->d_sched); cudaFree(c->d_deltas); cudaFree(c->d_rejected);
-  cudaFree(c->d_summary); cudaFree(c->d_events); cudaFree(c->d_cblock);
-  for (Resident& r : c->resident) { cudaFree(r.d_state); cudaFree(r.d_result); }
+  cudaFree(c->d_head); cudaFree(c->d_events); cudaFree(c->d_cblock);
+  for (Resident& r : c->resident) { cudaFree(r.d_state); cudaFree(r.d_result); cudaFree(r.d_result_prev); }
   delete c;
 }
 
@@ -1057,7 +1050,7 @@ static int eval_host(bf_ctx* c, const bf_batch* b, bf_compact_out* co) {
       if (rb && !co) BF_CUDA(c, cudaMemcpyAsync(hr + ro, c->d_result + ro, rb, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
     }
     if (co) {   // counts travel with the compaction's tail block
-      if (int rc = compact_enqueue(c, L, c->d_result, b->n_runs, co, s, &first_slice, false)) return rc;
+      if (int rc = compact_enqueue(c, L, c->d_result, nullptr, b->n_runs, co, s, &first_slice, false)) return rc;
     } else {
       BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof hc, cudaMemcpyDeviceToHost, s));
     }
@@ -1237,7 +1230,7 @@ int bf_resident_destroy(bf_ctx* c, uint32_t h) {
   BF_CUDA(c, cudaSetDevice(c->device));
   cudaStreamSynchronize(c->stream);
   if (c->last_state == r->d_state) c->last_eval_valid = false;
-  cudaFree(r->d_state); cudaFree(r->d_result);
+  cudaFree(r->d_state); cudaFree(r->d_result); cudaFree(r->d_result_prev);
   *r = Resident();
   return BF_OK;
 }
@@ -1251,6 +1244,7 @@ int bf_resident_upload(bf_ctx* c, uint32_t h, uint32_t first, uint32_t n, const 
   if (n == 0) return BF_OK;
   BF_CUDA(c, cudaSetDevice(c->device));
   if (c->last_state == r->d_state) c->last_eval_valid = false;   // the evaluated snapshot is gone: bf_schedule must follow a new pass
+  r->prev_valid = false;                                          // full records arrived: the next changed-only tick lists every run
   BF_CUDA(c, cudaMemcpyAsync(r->d_state + (size_t)first * r->L.state_stride, records, (size_t)n * r->L.state_stride, cudaMemcpyHostToDevice, c->stream));
   BF_CUDA(c, cudaStreamSynchronize(c->stream));
   return BF_OK;
@@ -1321,6 +1315,17 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
   cudaStream_t s = c->stream;
   const bf_layout& L = r->L;
   const size_t rbytes = (size_t)n_runs * L.result_stride;
+  const bool changed_only = co && (flags & BF_EVAL_CHANGED_ONLY);
+  flags &= ~(uint32_t)BF_EVAL_CHANGED_ONLY;
+  const uint8_t* d_prev = nullptr;
+  if (changed_only) {   // this pass writes the other buffer; the one it leaves behind is what "changed" is measured against
+    if (!r->d_result_prev) {
+      cudaError_t e = cudaMalloc(&r->d_result_prev, (size_t)r->cap * L.result_stride);
+      if (e != cudaSuccess) return fail(c, BF_ENOMEM, std::string("resident batch (second result buffer): ") + cudaGetErrorString(e));
+    }
+    std::swap(r->d_result, r->d_result_prev);
+    if (r->prev_valid && r->prev_runs == n_runs) d_prev = r->d_result_prev;
+  }
   uint32_t chunks = 1;
   uint64_t first_slice = 0;
   if (!co && rbytes >= (2u << 20)) {
@@ -1352,7 +1357,7 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
                                    (hi - lo) * L.result_stride, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
     }
     if (co) {   // counts and the rejected-delta counter travel with the compaction's tail block
-      if (int rc2 = compact_enqueue(c, L, r->d_result, n_runs, co, s, &first_slice, true)) return rc2;
+      if (int rc2 = compact_enqueue(c, L, r->d_result, d_prev, n_runs, co, s, &first_slice, true)) return rc2;
     } else {
       BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(bf_counts), cudaMemcpyDeviceToHost, s));
       BF_CUDA(c, cudaMemcpyAsync(h_rej, c->d_rejected, 4, cudaMemcpyDeviceToHost, s));
@@ -1365,8 +1370,10 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
     const cudaError_t e2 = cudaStreamSynchronize(c->s_out);
     if (es == cudaSuccess) es = e2;
   }
+  r->prev_valid = false;
   if (rc != BF_OK) return rc;
   if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
+  r->prev_valid = true; r->prev_runs = n_runs;
   if (co) {
     const unsigned long long* tail = reinterpret_cast<const unsigned long long*>(c->h_counts + 2);
     memcpy(c->h_counts, tail + 1, sizeof(bf_counts));

@@ -99,20 +99,21 @@ struct KParams {
   uint32_t slot_groups;
 };
 
-// compact.cu: result records -> (run, step, kind) events + one summary word per run
+// compact.cu: result records -> one head word per run + 16-bit (step | kind << 10) events
 struct CompactParams {
   const uint8_t* result;
-  uint32_t* summary;                 // [n_runs] or nullptr
-  bf_step_event* events;             // [cap]
+  const uint8_t* prev_result;        // previous tick's records (changed-only mode) or nullptr: every run is listed
+  uint32_t* head;                    // [n_runs]
+  uint16_t* events;                  // [cap]
   unsigned long long cap;
   unsigned long long* block_sums;    // scratch: ceil(n_runs / 512)
-  unsigned long long* total;         // out: events of the batch
+  unsigned long long* total;         // out: [0] events of the batch, [1] listed runs
   // the pass's small results, written straight to pinned host memory by the last block (no separate small D2H copies):
-  // host_tail[0] = events, [1..4] = bf_counts, [5] = rejected deltas
+  // host_tail[0] = events, [1..4] = bf_counts, [5] = rejected deltas, [6] = listed runs
   unsigned long long* host_tail;     // device-visible address of the pinned block, or nullptr
   const unsigned long long* counts;  // device bf_counts of the pass
   const uint32_t* rejected;          // device counter of rejected deltas, or nullptr
-  uint32_t n_runs, words, result_stride, off_ready, off_skip, off_fail, off_needs_cond, off_skip_dep;
+  uint32_t n_runs, words, result_stride, result_tail, off_ready, off_skip, off_fail, off_needs_cond, off_skip_dep;
 };
 
 // resident.cu (row f2)

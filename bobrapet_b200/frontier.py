@@ -157,42 +157,41 @@ class Frontier:
 
 
 
-    # -- compact results: (run, step, kind) events + one summary word per run instead of mask records
-    EVENT_DTYPE = np.dtype([("run", "<u4"), ("step", "<u2"), ("kind", "<u2")])
-
-    def _compact_out(self, n_runs: int, events_cap: int, summary, events):
-        if summary is None:
-            summary = np.zeros(max(n_runs, 1), dtype=np.uint32)
+    # -- compact results: one head word per run + 16-bit (step | kind << 10) events instead of mask records
+    def _compact_out(self, n_runs: int, events_cap: int, head, events):
+        if head is None:
+            head = np.zeros(max(n_runs, 1), dtype=np.uint32)
         if events is None:
-            events = np.zeros(max(events_cap, 1), dtype=self.EVENT_DTYPE)
-        assert events.dtype == self.EVENT_DTYPE and events.flags["C_CONTIGUOUS"] and events.shape[0] >= events_cap
-        co = A.CompactOut(struct_size=C.sizeof(A.CompactOut), summary=summary.ctypes.data, events=events.ctypes.data,
+            events = np.zeros(max(events_cap, 1), dtype=np.uint16)
+        assert head.dtype == np.uint32 and head.flags["C_CONTIGUOUS"] and head.shape[0] >= n_runs
+        assert events.dtype == np.uint16 and events.flags["C_CONTIGUOUS"] and events.shape[0] >= events_cap
+        co = A.CompactOut(struct_size=C.sizeof(A.CompactOut), head=head.ctypes.data, events=events.ctypes.data,
                           events_cap=events_cap, n_events=0)
-        return co, summary, events
+        return co, head, events
 
     def eval_compact(self, L: A.Layout, state: np.ndarray, events_cap: int, flags: int = 0, max_iterations: int = 0,
-                     summary: Optional[np.ndarray] = None, events: Optional[np.ndarray] = None):
-        """bf_eval_compact -> (summary [n] uint32, events[:min(n_events, cap)], n_events, counts)"""
+                     head: Optional[np.ndarray] = None, events: Optional[np.ndarray] = None):
+        """bf_eval_compact -> (head [n] uint32, events[:min(n_events, cap)] uint16, n_events, counts)"""
         n = int(state.shape[0])
         assert state.dtype == np.uint8 and state.flags["C_CONTIGUOUS"] and state.shape[1] == L.state_stride
-        co, summary, events = self._compact_out(n, events_cap, summary, events)
+        co, head, events = self._compact_out(n, events_cap, head, events)
         counts = A.Counts()
         b = A.Batch(struct_size=C.sizeof(A.Batch), n_runs=n, flags=flags, max_iterations=max_iterations, layout=L,
                     state=state.ctypes.data, result=None, expansion=None, expansion_cap=0, counts=C.addressof(counts))
         self._check(self._lib.bf_eval_compact(self._ctx, C.byref(b), C.byref(co)), "bf_eval_compact")
         cdict = {"ready": counts.ready, "skip": counts.skip, "expansion": counts.expansion, "evals": counts.evals}
-        return summary[:n], events[:min(int(co.n_events), events_cap)], int(co.n_events), cdict
+        return head[:n], events[:min(int(co.n_events), events_cap)], int(co.n_events), cdict
 
     def resident_tick_compact(self, handle: int, n_runs: int, deltas: np.ndarray, events_cap: int, flags: int = 0,
-                              max_iterations: int = 0, summary: Optional[np.ndarray] = None, events: Optional[np.ndarray] = None):
-        """bf_resident_tick_compact -> (summary, events, n_events, counts)"""
+                              max_iterations: int = 0, head: Optional[np.ndarray] = None, events: Optional[np.ndarray] = None):
+        """bf_resident_tick_compact -> (head, events, n_events, counts, n_listed); flags may carry A.EVAL_CHANGED_ONLY"""
         assert deltas.dtype == self.DELTA_DTYPE and deltas.flags["C_CONTIGUOUS"]
-        co, summary, events = self._compact_out(n_runs, events_cap, summary, events)
+        co, head, events = self._compact_out(n_runs, events_cap, head, events)
         counts = A.Counts()
         self._check(self._lib.bf_resident_tick_compact(self._ctx, handle, deltas.ctypes.data, deltas.shape[0], n_runs, flags,
                                                        max_iterations, C.byref(co), C.byref(counts)), "bf_resident_tick_compact")
         cdict = {"ready": counts.ready, "skip": counts.skip, "expansion": counts.expansion, "evals": counts.evals}
-        return summary[:n_runs], events[:min(int(co.n_events), events_cap)], int(co.n_events), cdict
+        return head[:n_runs], events[:min(int(co.n_events), events_cap)], int(co.n_events), cdict, int(co.n_listed)
 
     # -- resident batches: device-side state, delta uploads (row f2)
     DELTA_DTYPE = np.dtype([("run", "<u4"), ("index", "<u2"), ("field", "u1"), ("code", "u1")])

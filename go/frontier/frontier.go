@@ -154,24 +154,27 @@ func (c *Ctx) Eval(b *Batch, flags uint32) (Counts, error) {
 	return k, c.err(rc)
 }
 
-// StepEvent mirrors bf_step_event: one (run, step) with its BF_EVT_* bits.
-type StepEvent struct {
-	Run  uint32
-	Step uint16
-	Kind uint16
-}
+// Compact results: head[r] = low 15 summary bits | listed << 15 | event count << 16 (BF_HEAD_*), events = one uint16 per
+// ready / skipped / failed step, step | kind << 10 (BF_EVT_*), run-major in batch order and step-ascending inside a run —
+// the order of findReadySteps' lists.  Run r's events are the next head[r]>>16 entries.
+const (
+	HeadSummaryMask = 0x7FFF
+	HeadListed      = 0x8000
+	HeadCountShift  = 16
+	EvalChangedOnly = 0x10 // BF_EVAL_CHANGED_ONLY: list only the runs whose result differs from the previous tick's
+)
 
-// EvalCompact is Eval with the results as lists: summary[r] = BF_SUM_* word of run r, events = every (run, step)
-// that is ready / skipped / failed, run-major and step-ascending (the order of findReadySteps' lists).
-func (c *Ctx) EvalCompact(b *Batch, flags uint32, summary []uint32, events []StepEvent) (n uint64, k Counts, err error) {
-	var ev *C.bf_step_event
+// EvalCompact is Eval with the results as lists.
+func (c *Ctx) EvalCompact(b *Batch, flags uint32, head []uint32, events []uint16) (nEvents uint64, nListed uint32, k Counts, err error) {
+	var ev *C.uint16_t
 	if len(events) > 0 {
-		ev = (*C.bf_step_event)(unsafe.Pointer(&events[0]))
+		ev = (*C.uint16_t)(unsafe.Pointer(&events[0]))
 	}
 	var ne C.uint64_t
-	rc := C.bfgo_eval_compact(c.p, &b.Layout, C.uint32_t(b.N), C.uint32_t(flags), 0, b.State, u32p(summary), ev, C.uint64_t(len(events)),
-		&ne, (*C.bf_counts)(unsafe.Pointer(&k)))
-	return uint64(ne), k, c.err(rc)
+	var nl C.uint32_t
+	rc := C.bfgo_eval_compact(c.p, &b.Layout, C.uint32_t(b.N), C.uint32_t(flags), 0, b.State, u32p(head), ev, C.uint64_t(len(events)),
+		&ne, &nl, (*C.bf_counts)(unsafe.Pointer(&k)))
+	return uint64(ne), uint32(nl), k, c.err(rc)
 }
 
 // SchedRun mirrors bf_sched_run (32 bytes, no pointers).
@@ -269,21 +272,22 @@ func (r *Resident) Upload(first, n uint32, records unsafe.Pointer) error {
 }
 
 // Tick is the steady-state reconcile tick: the deltas syncStateFromStepRuns (dag.go:965-1009) produced go up, the
-// pass runs over the resident state, and the ready / skipped steps come back as events.
-func (r *Resident) Tick(deltas []Delta, n, flags uint32, summary []uint32, events []StepEvent) (uint64, Counts, error) {
+// pass runs over the resident state, and the ready / skipped steps come back as lists; with EvalChangedOnly only the
+// runs whose result changed since the previous tick are listed (the batcher keeps every run's last Row).
+func (r *Resident) Tick(deltas []Delta, n, flags uint32, head []uint32, events []uint16) (nEvents uint64, nListed uint32, k Counts, err error) {
 	var dp *C.bf_delta
 	if len(deltas) > 0 {
 		dp = (*C.bf_delta)(unsafe.Pointer(&deltas[0]))
 	}
-	var ev *C.bf_step_event
+	var ev *C.uint16_t
 	if len(events) > 0 {
-		ev = (*C.bf_step_event)(unsafe.Pointer(&events[0]))
+		ev = (*C.uint16_t)(unsafe.Pointer(&events[0]))
 	}
 	var ne C.uint64_t
-	var k Counts
-	rc := C.bfgo_resident_tick_compact(r.c.p, r.handle, dp, C.uint32_t(len(deltas)), C.uint32_t(n), C.uint32_t(flags), 0, u32p(summary), ev,
-		C.uint64_t(len(events)), &ne, (*C.bf_counts)(unsafe.Pointer(&k)))
-	return uint64(ne), k, r.c.err(rc)
+	var nl C.uint32_t
+	rc := C.bfgo_resident_tick_compact(r.c.p, r.handle, dp, C.uint32_t(len(deltas)), C.uint32_t(n), C.uint32_t(flags), 0, u32p(head), ev,
+		C.uint64_t(len(events)), &ne, &nl, (*C.bf_counts)(unsafe.Pointer(&k)))
+	return uint64(ne), uint32(nl), k, r.c.err(rc)
 }
 
 // Group is one operator process driving several GPUs (bf_group_*): contiguous blocks of runs per device, one NCCL

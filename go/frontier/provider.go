@@ -26,10 +26,10 @@ type FrontierProvider interface {
 	Lookup(uid string, resourceVersion string) (Row, bool)
 }
 
-// Row is one StoryRun's result of the last tick, decoded from the compact events (or from a mask record).
+// Row is one StoryRun's result of the last tick that listed it, decoded from the compact lists.
 type Row struct {
-	Summary uint32      // BF_SUM_*: group evaluated, mainDone / mainFailed flags, "some phase changed"
-	Events  []StepEvent // this run's slice of the tick's event list (run-major, so it is contiguous)
+	Summary uint32   // low 15 bits of BF_SUM_*: group evaluated, mainDone / mainFailed flags, "some phase changed"
+	Events  []uint16 // this run's slice of the tick's event list: step | kind << 10
 	// FailedDep names, per skipped step, the dependency that failed — "Skipped due to failed dependency: <d>"
 	// (dag.go:2735-2739): the lowest index among the step's needs whose phase is terminal and not Succeeded/Skipped
 	// (the packer fills it from the host copy of the phases; the kernel reports only WHICH steps were skipped for it).
@@ -42,22 +42,36 @@ const (
 	evtSkipDep = 0x10
 )
 
+// Rows walks one tick's lists: run r's events are the next head[r]>>16 entries; only listed runs are handed to `set`
+// (with BF_EVAL_CHANGED_ONLY the cache keeps the previous Row of every other run).
+func Rows(head []uint32, events []uint16, set func(run uint32, row Row)) {
+	pos := 0
+	for r, h := range head {
+		n := int(h >> HeadCountShift)
+		if h&HeadListed != 0 {
+			set(uint32(r), Row{Summary: h & HeadSummaryMask, Events: events[pos : pos+n]})
+		}
+		pos += n
+	}
+}
+
 // Steps turns the row back into the three results of findReadySteps (dag.go:2631-2641) over `steps` =
 // allStorySteps(story) — index i of the packed topology is &steps[i].
 func (r Row) Steps(steps []bubuv1alpha1.Step) (ready, skipped []*bubuv1alpha1.Step, reasons map[string]string) {
 	reasons = map[string]string{}
 	for _, e := range r.Events {
-		if int(e.Step) >= len(steps) {
+		step, kind := e&0x3FF, e>>10
+		if int(step) >= len(steps) {
 			continue
 		}
-		st := &steps[e.Step]
+		st := &steps[step]
 		switch {
-		case e.Kind&evtReady != 0:
+		case kind&evtReady != 0:
 			ready = append(ready, st)
-		case e.Kind&evtSkip != 0:
+		case kind&evtSkip != 0:
 			skipped = append(skipped, st)
-			if e.Kind&evtSkipDep != 0 || r.FailedDep[e.Step] != "" {
-				reasons[st.Name] = "Skipped due to failed dependency: " + r.FailedDep[e.Step] // dag.go:2736
+			if kind&evtSkipDep != 0 || r.FailedDep[step] != "" {
+				reasons[st.Name] = "Skipped due to failed dependency: " + r.FailedDep[step] // dag.go:2736
 			} else {
 				reasons[st.Name] = "Skipped due to 'if' condition" // dag.go:2831
 			}

@@ -51,31 +51,33 @@ static inline int bfgo_eval(bf_ctx* c, const bf_layout* L, uint32_t n_runs, uint
   return bf_eval(c, &b);
 }
 
-static inline void bfgo_compact(bf_compact_out* co, uint32_t* summary, bf_step_event* events, uint64_t events_cap) {
+static inline void bfgo_compact(bf_compact_out* co, uint32_t* head, uint16_t* events, uint64_t events_cap) {
   memset(co, 0, sizeof *co);
   co->struct_size = (uint32_t)sizeof *co;
-  co->summary = summary; co->events = events; co->events_cap = events_cap;
+  co->head = head; co->events = events; co->events_cap = events_cap;
 }
 
 static inline int bfgo_eval_compact(bf_ctx* c, const bf_layout* L, uint32_t n_runs, uint32_t flags, uint32_t max_iterations,
-                                    const void* state, uint32_t* summary, bf_step_event* events, uint64_t events_cap,
-                                    uint64_t* n_events, bf_counts* counts) {
+                                    const void* state, uint32_t* head, uint16_t* events, uint64_t events_cap,
+                                    uint64_t* n_events, uint32_t* n_listed, bf_counts* counts) {
   bf_batch b;
   bf_compact_out co;
   bfgo_batch(&b, L, n_runs, flags, max_iterations, state, NULL, counts);
-  bfgo_compact(&co, summary, events, events_cap);
+  bfgo_compact(&co, head, events, events_cap);
   const int rc = bf_eval_compact(c, &b, &co);
   *n_events = co.n_events;
+  *n_listed = co.n_listed;
   return rc;
 }
 
 static inline int bfgo_resident_tick_compact(bf_ctx* c, uint32_t handle, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs,
-                                             uint32_t flags, uint32_t max_iterations, uint32_t* summary, bf_step_event* events,
-                                             uint64_t events_cap, uint64_t* n_events, bf_counts* counts) {
+                                             uint32_t flags, uint32_t max_iterations, uint32_t* head, uint16_t* events,
+                                             uint64_t events_cap, uint64_t* n_events, uint32_t* n_listed, bf_counts* counts) {
   bf_compact_out co;
-  bfgo_compact(&co, summary, events, events_cap);
+  bfgo_compact(&co, head, events, events_cap);
   const int rc = bf_resident_tick_compact(c, handle, deltas, n_deltas, n_runs, flags, max_iterations, &co, counts);
   *n_events = co.n_events;
+  *n_listed = co.n_listed;
   return rc;
 }
 

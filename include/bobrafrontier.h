@@ -436,35 +436,47 @@ int bf_resident_download(bf_ctx* ctx, uint32_t handle, uint32_t first_run, uint3
 
 /* ------------------------------------------------------------------ compact results
  * What the consumer of a pass needs (findAndLaunchReadySteps, dag.go:1735-1775) is two short LISTS per run — the
- * ready steps to hand to StepExecutor.Execute and the skipped steps to mark — plus the run's summary word, not 80+
- * bytes of masks per run.  The compact entry points turn the result masks into events ON THE DEVICE and ship only
- * those: one 8-byte event per (run, step) that has any result bit set, run-major and step-ascending (the order of
- * the reference's lists), and one summary word per run.  At BASELINE configs[2] that is ~2.9 MB per pass instead
- * of 8 MB.  The dense records stay on the device (bf_schedule may follow).                                        */
+ * ready steps to hand to StepExecutor.Execute and the skipped steps to mark — plus the run's summary flags, not 80+
+ * bytes of masks per run.  The compact entry points turn the result masks into lists ON THE DEVICE and ship only
+ * those:
+ *   head[r]   one u32 per run: low 15 bits = low bits of the run's BF_SUM_* word (group, done / failed flags,
+ *             PHASE_CHANGED; 0x7FFF = dead topology slot), bit 15 = the run's events are in this call's list,
+ *             high 16 bits = how many.  The fixpoint iteration count of the summary word is not carried.
+ *   events[]  one u16 per (run, step) that has any result bit set: step | kind << 10, run-major in batch order and
+ *             step-ascending inside a run (the order of the reference's lists); run r's events are the next
+ *             head[r] >> 16 entries.
+ * At BASELINE configs[2] that is 0.4 MB + ~0.6 MB per pass instead of 8 MB of mask records.  The dense records stay
+ * on the device (bf_schedule may follow).
+ * BF_EVAL_CHANGED_ONLY (resident ticks): only runs whose result record differs from the PREVIOUS tick's carry
+ * BF_HEAD_LISTED and events — the batcher keeps the last row of every run anyway, so a steady-state
+ * tick returns O(changes) in both directions.  The first tick after bf_resident_create / _upload lists every run.   */
 #define BF_EVT_READY 0x1u      /* step is in `ready`                                                            */
 #define BF_EVT_SKIP 0x2u       /* step is in `skip`  (failed dependency or `if` false)                          */
 #define BF_EVT_FAIL 0x4u       /* step is in `fail`        (only when the layout has BF_F_OUT_FAIL)              */
 #define BF_EVT_NEEDS_COND 0x8u /* step is in `needs_cond`  (only with BF_F_OUT_NEEDS_COND)                       */
 #define BF_EVT_SKIP_DEP 0x10u  /* step is in `skip_dep`    (only with BF_F_OUT_SKIP_DEP)                         */
-typedef struct bf_step_event { /* 8 B */
-  uint32_t run;                /* index in the batch                                                            */
-  uint16_t step;
-  uint16_t kind;               /* BF_EVT_* bits                                                                 */
-} bf_step_event;
+#define BF_EVENT_STEP(e) ((uint32_t)(e) & 0x3FFu)
+#define BF_EVENT_KIND(e) ((uint32_t)(e) >> 10)
+#define BF_HEAD_SUMMARY_MASK 0x7FFFu
+#define BF_HEAD_DEAD 0x7FFFu   /* low bits of a run whose topology slot is dead: no events                       */
+#define BF_HEAD_LISTED 0x8000u
+#define BF_HEAD_COUNT_SHIFT 16
+#define BF_EVAL_CHANGED_ONLY 0x10u /* flag of bf_resident_tick_compact                                           */
 
 typedef struct bf_compact_out {
   uint32_t struct_size;
-  uint32_t reserved;
-  uint32_t* summary;           /* [n_runs] BF_SUM_* word of every run (0xFFFFFFFF = dead topology slot); may be NULL */
-  bf_step_event* events;       /* [events_cap]                                                                   */
+  uint32_t n_listed;           /* out: runs that carry BF_HEAD_LISTED                                            */
+  uint32_t* head;              /* [n_runs]                                                                       */
+  uint16_t* events;            /* [events_cap]                                                                   */
   uint64_t events_cap;
-  uint64_t n_events;           /* out: events the pass produced; when > events_cap only the first events_cap were written */
+  uint64_t n_events;           /* out: events the pass produced; when > events_cap only the first events_cap were written
+                                  (heads always carry the true counts)                                           */
 } bf_compact_out;
 
-/* bf_eval with compact results: H2D(state) -> kernels -> D2H(summary words + events).  batch->result is ignored
- * (may be NULL); expansion as for bf_eval.  Host buffers, synchronous.                                           */
+/* bf_eval with compact results: H2D(state) -> kernels -> D2H(heads + events).  batch->result is ignored
+ * (may be NULL).  Host buffers, synchronous.                                                                     */
 int bf_eval_compact(bf_ctx* ctx, const bf_batch* batch, bf_compact_out* out);
-/* bf_resident_tick with compact results: H2D(deltas) -> scatter -> pass -> D2H(summary words + events).  This is the
+/* bf_resident_tick with compact results: H2D(deltas) -> scatter -> pass -> D2H(heads + events).  This is the
  * steady-state tick of the operator: both directions are proportional to what changed.                           */
 int bf_resident_tick_compact(bf_ctx* ctx, uint32_t handle, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs,
                              uint32_t flags, uint32_t max_iterations, bf_compact_out* out, bf_counts* counts);

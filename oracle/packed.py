@@ -111,23 +111,28 @@ def evaluate(pt: PackedTopologies, L, state: np.ndarray, flags: int = 0, max_ite
     return result, {"ready": counts.ready, "skip": counts.skip, "expansion": counts.expansion, "evals": counts.evals}
 
 
-def compact_events(L, result: np.ndarray):
+def compact_events(L, result: np.ndarray, prev: np.ndarray = None):
     """The compact form of oracle result records (the checker of bf_eval_compact / bf_resident_tick_compact):
-    -> (summary [N] uint32, events structured array (run, step, kind) run-major / step-ascending).
-    kind bits: 1 ready, 2 skip, 4 fail, 8 needs_cond, 16 skip_dep (BF_EVT_*); dead slots (summary 0xFFFFFFFF) have none."""
+    -> (head [N] uint32, events uint16 (step | kind << 10), run-major / step-ascending, n_listed).
+    head = low 15 summary bits (0x7FFF for a dead slot) | listed << 15 | event count << 16; kind bits: 1 ready, 2 skip, 4 fail,
+    8 needs_cond, 16 skip_dep (BF_EVT_*).  With `prev` (the previous tick's records) only runs whose record differs are listed."""
     n = result.shape[0]
     W = L.words
     summary = np.ascontiguousarray(result[:, 0:4]).view("<u4").reshape(n).copy()
+    dead = summary == 0xFFFFFFFF
     kind = np.zeros((n, W * 32), dtype=np.uint16)
     for bit, off in ((1, L.off_ready), (2, L.off_skip), (4, L.off_fail), (8, L.off_needs_cond), (16, L.off_skip_dep)):
         if off != 0xFFFFFFFF:
             m = np.unpackbits(np.ascontiguousarray(result[:, off:off + 4 * W]), axis=1, bitorder="little")
             kind |= m.astype(np.uint16) * np.uint16(bit)
-    kind[summary == 0xFFFFFFFF] = 0
+    kind[dead] = 0
+    listed = np.ones(n, dtype=bool) if prev is None else (result != prev).any(axis=1)
+    kind[~listed] = 0
+    count = (kind != 0).sum(axis=1).astype(np.uint32)
+    head = np.where(dead, 0x7FFF, summary & 0x7FFF).astype(np.uint32) | (listed.astype(np.uint32) << 15) | (count << 16)
     run, step = np.nonzero(kind)
-    ev = np.zeros(run.shape[0], dtype=np.dtype([("run", "<u4"), ("step", "<u2"), ("kind", "<u2")]))
-    ev["run"], ev["step"], ev["kind"] = run, step, kind[run, step]
-    return summary, ev
+    ev = (step.astype(np.uint16) | (kind[run, step] << 10)).astype(np.uint16)
+    return head, ev, int(listed.sum())
 
 
 def expand(pt: PackedTopologies, L, state: np.ndarray, result: np.ndarray, cap: int):

@@ -83,18 +83,20 @@ int main(void) {
   CHECK((h5->summary & BF_SUM_GROUP_MASK) == BF_GROUP_DONE && (h5->summary & BF_SUM_MAIN_FAILED) && (h5->summary & BF_SUM_PHASE_CHANGED));
   CHECK(counts.ready == 3 && counts.skip == 1 && counts.evals == 3 * N);
 
-  /* ---- EvalCompact: the same pass as lists ---- */
-  uint32_t summary[N];
-  bf_step_event events[16];
+  /* ---- EvalCompact: the same pass as lists (head word per run + 16-bit events) ---- */
+  uint32_t head[N], n_listed = 0;
+  uint16_t events[16];
   uint64_t n_events = 0;
   bf_counts c2;
-  CHECK(bfgo_eval_compact(ctx, &L, N, 0, 0, state, summary, events, 16, &n_events, &c2) == BF_OK);
-  CHECK(n_events == 4 && memcmp(&c2, &counts, sizeof counts) == 0);
-  CHECK(events[0].run == 0 && events[0].step == 0 && events[0].kind == BF_EVT_READY);
-  CHECK(events[1].run == 2 && events[1].step == 1 && events[1].kind == BF_EVT_READY);
-  CHECK(events[2].run == 3 && events[2].step == 2 && events[2].kind == BF_EVT_READY);
-  CHECK(events[3].run == 4 && events[3].step == 1 && events[3].kind == (BF_EVT_SKIP | BF_EVT_SKIP_DEP));
-  CHECK(summary[5] == h5->summary);
+  CHECK(bfgo_eval_compact(ctx, &L, N, 0, 0, state, head, events, 16, &n_events, &n_listed, &c2) == BF_OK);
+  CHECK(n_events == 4 && n_listed == N && memcmp(&c2, &counts, sizeof counts) == 0);
+  const uint32_t want_count[N] = {1, 0, 1, 1, 1, 0};
+  for (uint32_t r = 0; r < N; ++r) CHECK((head[r] >> BF_HEAD_COUNT_SHIFT) == want_count[r] && (head[r] & BF_HEAD_LISTED));
+  CHECK(BF_EVENT_STEP(events[0]) == 0 && BF_EVENT_KIND(events[0]) == BF_EVT_READY);                        /* run 0: A ready */
+  CHECK(BF_EVENT_STEP(events[1]) == 1 && BF_EVENT_KIND(events[1]) == BF_EVT_READY);                        /* run 2: B ready */
+  CHECK(BF_EVENT_STEP(events[2]) == 2 && BF_EVENT_KIND(events[2]) == BF_EVT_READY);                        /* run 3: C ready */
+  CHECK(BF_EVENT_STEP(events[3]) == 1 && BF_EVENT_KIND(events[3]) == (BF_EVT_SKIP | BF_EVT_SKIP_DEP));     /* run 4: B skipped */
+  CHECK((head[5] & BF_HEAD_SUMMARY_MASK) == (h5->summary & BF_HEAD_SUMMARY_MASK));
 
   /* ---- Schedule: story 0 has limit 2 and already 1 Running StepRun in the batch (run 1's A) => one slot for three ready steps */
   CHECK(bfgo_eval(ctx, &L, N, 0, 0, state, result, &counts) == BF_OK);
@@ -140,8 +142,12 @@ int main(void) {
   CHECK(bf_resident_upload(ctx, handle, 0, N, state) == BF_OK);
   bf_delta d;
   d.run = 0; d.index = 0; d.field = BF_DELTA_PHASE; d.code = BF_PHASE_SUCCEEDED;
-  CHECK(bfgo_resident_tick_compact(ctx, handle, &d, 1, N, 0, 0, summary, events, 16, &n_events, &c2) == BF_OK);
-  CHECK(n_events == 4 && events[0].run == 0 && events[0].step == 1 && events[0].kind == BF_EVT_READY);
+  CHECK(bfgo_resident_tick_compact(ctx, handle, &d, 1, N, 0, 0, head, events, 16, &n_events, &n_listed, &c2) == BF_OK);
+  CHECK(n_events == 4 && n_listed == N && BF_EVENT_STEP(events[0]) == 1 && BF_EVENT_KIND(events[0]) == BF_EVT_READY);
+  /* a changed-only tick with one more delta (B of run 0 -> Succeeded => C ready): only run 0 is listed */
+  d.index = 1;
+  CHECK(bfgo_resident_tick_compact(ctx, handle, &d, 1, N, BF_EVAL_CHANGED_ONLY, 0, head, events, 16, &n_events, &n_listed, &c2) == BF_OK);
+  CHECK(n_listed == 1 && n_events == 1 && (head[0] & BF_HEAD_LISTED) && !(head[2] & BF_HEAD_LISTED) && BF_EVENT_STEP(events[0]) == 2);
   CHECK(bf_resident_destroy(ctx, handle) == BF_OK);
 
   /* ---- error behaviour: a bad struct size is BF_EINVAL with text, nothing aborts ---- */

@@ -1,5 +1,6 @@
-"""Compact results (bf_eval_compact / bf_resident_tick_compact): the (run, step, kind) event list and the per-run summary
-words must be exactly what the oracle's mask records say, in run-major / step-ascending order."""
+"""Compact results (bf_eval_compact / bf_resident_tick_compact): the per-run head words and the 16-bit (step | kind << 10) event
+list must be exactly what the oracle's mask records say, in run-major / step-ascending order; in changed-only mode exactly the
+runs whose record differs from the previous tick's are listed, and replaying the ticks rebuilds every run's row."""
 import numpy as np
 import pytest
 
@@ -24,24 +25,22 @@ def fr():
 def _check(fr, ts, slots, L, state, flags=0, cap=None, want=None, wcounts=None):
     if want is None:
         want, wcounts = PK.evaluate(PK.PackedTopologies(ts, slots), L, state, flags, 0, threads=8)
-    wsum, wev = PK.compact_events(L, want)
+    whead, wev, wlisted = PK.compact_events(L, want)
     cap = len(wev) + 16 if cap is None else cap
-    # pageable buffers: device list + D2H copies; pinned buffers (bf_alloc_pinned): the kernels write the caller's memory directly
-    summary, events, n_events, counts = fr.eval_compact(L, state, cap, flags=flags)
+    head, events, n_events, counts = fr.eval_compact(L, state, cap, flags=flags)
     assert n_events == len(wev) and counts == wcounts
-    assert np.array_equal(summary, wsum)
+    assert np.array_equal(head, whead)
     assert np.array_equal(events, wev[:cap])
+    # pinned caller buffers (what the batcher uses)
     n = state.shape[0]
-    p_sum = fr.alloc_pinned(max(n, 1) * 4).view(np.uint32)
-    p_ev = fr.alloc_pinned(max(cap, 1) * 8).view(fr.EVENT_DTYPE)
-    p_sum[:] = 0xABABABAB
+    p_head = fr.alloc_pinned(max(n, 1) * 4).view(np.uint32)
+    p_ev = fr.alloc_pinned(max(cap, 1) * 2).view(np.uint16)
+    p_head[:] = 0xABABABAB
     try:
-        summary, events, n_events, counts = fr.eval_compact(L, state, cap, flags=flags, summary=p_sum, events=p_ev)
-        assert n_events == len(wev) and counts == wcounts
-        assert np.array_equal(summary, wsum)
-        assert np.array_equal(events, wev[:cap])
+        head, events, n_events, counts = fr.eval_compact(L, state, cap, flags=flags, head=p_head, events=p_ev)
+        assert n_events == len(wev) and counts == wcounts and np.array_equal(head, whead) and np.array_equal(events, wev[:cap])
     finally:
-        fr.free_pinned(p_sum.view(np.uint8))
+        fr.free_pinned(p_head.view(np.uint8))
         fr.free_pinned(p_ev.view(np.uint8))
     return n_events
 
@@ -89,28 +88,54 @@ def test_compact_capacity_smaller_than_the_list_and_dead_slot(fr):
     _check(fr, ts, slots, L, state, want=want, wcounts=wcounts)          # and a larger list after a tiny one (the first D2H slice is a guess)
 
 
-def test_resident_tick_compact(fr):
+def test_resident_tick_compact_and_changed_only(fr):
     n, S = 6007, 256
     ts = synth.topologies(4, 0, n, S)
     slots = fr.put_topologies(ts)
     L = make_layout(S, 0, ALL)
     state = synth.state(4, 0, n, L, slots, ts)
+    pt = PK.PackedTopologies(ts, slots)
     h = fr.resident_create(L, n)
     try:
         fr.resident_upload(h, 0, state)
         rng = np.random.default_rng(3)
-        for tick in range(3):
-            k = 500
+        prev = None
+        rows = {}      # the batcher's cache: run -> (head low bits, events), rebuilt from changed-only ticks
+        for tick in range(6):
+            k = [500, 40, 0, 3000, 1, 500][tick]
             flat = rng.choice(n * S, size=k, replace=False)
             d = np.zeros(k, dtype=fr.DELTA_DTYPE)
             d["run"], d["index"], d["field"] = flat // S, flat % S, A.DELTA_PHASE
             d["code"] = rng.choice([0, 2, 3, 3, 4, 13], size=k)
-            summary, events, n_events, counts = fr.resident_tick_compact(h, n, d, 200000)
+            changed_only = tick >= 2
+            head, events, n_events, counts, n_listed = fr.resident_tick_compact(
+                h, n, d, 200000, flags=(A.EVAL_CHANGED_ONLY if changed_only else 0))
             cur = fr.resident_download(h, 0, n, L.state_stride)
-            want, wcounts = PK.evaluate(PK.PackedTopologies(ts, slots), L, cur, 0, 0, threads=8)
-            wsum, wev = PK.compact_events(L, want)
-            assert n_events == len(wev) and counts == wcounts and np.array_equal(summary, wsum) and np.array_equal(events, wev)
-            assert not np.array_equal(cur, state)
-            state = cur
+            want, wcounts = PK.evaluate(pt, L, cur, 0, 0, threads=8)
+            # the first changed-only tick follows full ticks whose records are still on the device: it may already be sparse
+            whead, wev, wlisted = PK.compact_events(L, want, prev if changed_only else None)
+            assert counts == wcounts and n_events == len(wev) and n_listed == wlisted
+            assert np.array_equal(head, whead) and np.array_equal(events, wev)
+            if changed_only and k <= 40:
+                assert n_listed <= max(4 * k, 1) and n_listed < n // 10      # O(changes), not O(runs)
+            # replay into the cache and compare with the full compact form of this tick
+            pos = 0
+            for r in np.nonzero(head & A.HEAD_LISTED)[0]:
+                c = int(head[r]) >> A.HEAD_COUNT_SHIFT
+                rows[int(r)] = (int(head[r]) & A.HEAD_SUMMARY_MASK, events[pos:pos + c].copy())
+                pos += c
+            assert pos == n_events
+            fhead, fev, _ = PK.compact_events(L, want)
+            pos = 0
+            for r in range(n):
+                c = int(fhead[r]) >> A.HEAD_COUNT_SHIFT
+                assert rows[r][0] == int(fhead[r]) & A.HEAD_SUMMARY_MASK and np.array_equal(rows[r][1], fev[pos:pos + c]), (tick, r)
+                pos += c
+            prev = want
+        # new full records for some runs: the next changed-only tick lists every run again
+        fr.resident_upload(h, 10, cur[10:20])
+        head, events, n_events, counts, n_listed = fr.resident_tick_compact(h, n, np.zeros(0, dtype=fr.DELTA_DTYPE), 200000,
+                                                                             flags=A.EVAL_CHANGED_ONLY)
+        assert n_listed == n
     finally:
         fr.resident_destroy(h)

@@ -29,21 +29,21 @@ def test_eight_concurrent_callers_get_their_own_results():
             slots = f.put_topologies(ts)
             state = synth.state(4, 100000 * w, n, L, slots, ts)
             want, wc = PK.evaluate(PK.PackedTopologies(ts, slots), L, state, threads=4)
-            wsum, wev = PK.compact_events(L, want)
-            jobs.append((state, want, wc, wsum, wev))
+            whead, wev, _ = PK.compact_events(L, want)
+            jobs.append((state, want, wc, whead, wev))
         reps = 12
         errors = []
 
         def worker(w):
-            state, want, wc, wsum, wev = jobs[w]
+            state, want, wc, whead, wev = jobs[w]
             try:
                 for i in range(reps):
                     if i % 2:
                         got, gc = f.eval(L, state)
                         assert np.array_equal(got, want) and gc == wc
                     else:
-                        summary, events, n_events, gc = f.eval_compact(L, state, len(wev) + 8)
-                        assert n_events == len(wev) and np.array_equal(summary, wsum) and np.array_equal(events, wev) and gc == wc
+                        head, events, n_events, gc = f.eval_compact(L, state, len(wev) + 8)
+                        assert n_events == len(wev) and np.array_equal(head, whead) and np.array_equal(events, wev) and gc == wc
             except Exception as e:  # noqa: BLE001
                 errors.append((w, repr(e)[:300]))
 

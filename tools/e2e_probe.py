@@ -21,9 +21,9 @@ h = fr.resident_create(L, n)
 fr.resident_upload(h, 0, state)
 rng = np.random.default_rng(1)
 hr = fr.alloc_pinned(n * L.result_stride).reshape(n, L.result_stride)
-h_sum = fr.alloc_pinned(n * 4).view(np.uint32)
+h_head = fr.alloc_pinned(n * 4).view(np.uint32)
 cap = 600000
-h_ev = fr.alloc_pinned(cap * 8).view(fr.EVENT_DTYPE)
+h_ev = fr.alloc_pinned(cap * 2).view(np.uint16)
 
 
 def deltas(rate):
@@ -52,10 +52,21 @@ for rate in (0.01, 0.004, 0.001):
 
     def tick():
         i[0] += 1
-        return fr.resident_tick_compact(h, n, ds[i[0] % 3], cap, summary=h_sum, events=h_ev)
+        return fr.resident_tick_compact(h, n, ds[i[0] % 3], cap, head=h_head, events=h_ev)
     timeit("tick_compact, %.1f%% deltas (%d)" % (100 * rate, ds[0].shape[0]), tick)
-timeit("tick_compact, no deltas", lambda: fr.resident_tick_compact(h, n, empty, cap, summary=h_sum, events=h_ev))
-timeit("tick_compact, no deltas, events_cap 0", lambda: fr.resident_tick_compact(h, n, empty, 0, summary=h_sum, events=h_ev))
+ds1 = [deltas(0.01) for _ in range(3)]
+j = [0]
+
+
+def tick_changed():
+    j[0] += 1
+    return fr.resident_tick_compact(h, n, ds1[j[0] % 3], cap, flags=A.EVAL_CHANGED_ONLY, head=h_head, events=h_ev)
+
+
+timeit("tick_compact changed-only, 1% deltas", tick_changed)
+print("   listed runs / events of the last changed-only tick:", tick_changed()[4], tick_changed()[2])
+timeit("tick_compact, no deltas", lambda: fr.resident_tick_compact(h, n, empty, cap, head=h_head, events=h_ev))
+timeit("tick_compact, no deltas, events_cap 0", lambda: fr.resident_tick_compact(h, n, empty, 0, head=h_head, events=h_ev))
 timeit("tick dense (mask records), no deltas", lambda: fr.resident_tick(h, L, n, empty, hr))
 ds = [deltas(0.01) for _ in range(3)]
 timeit("tick dense, 1% deltas", lambda: fr.resident_tick(h, L, n, ds[0], hr))
