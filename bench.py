@@ -286,7 +286,10 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
     from bobrapet_b200.sharding import CountExchange, global_offsets
     args, dev, world, rank = g.args, g.dev, g.world, g.rank
     S = CFG_S[cfg]
-    fr = Frontier(g.local_rank)
+    # N > 1: one SM is left out of the persistent grid so that the NCCL all-gather of a pass runs beside the next pass
+    # instead of queueing behind it (BF_CFG_RESERVE_SMS); BF_BENCH_RESERVE_SMS overrides
+    reserve = int(os.environ.get("BF_BENCH_RESERVE_SMS", "1" if world > 1 else "0"))
+    fr = Frontier(g.local_rank, reserve_sms=reserve)
     run_lo = rank * n_runs
     fields = A.F_COND | A.F_DECISION if cfg in (4, 5) else 0
     n_topo = args.shared or n_runs
@@ -474,7 +477,8 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
                                                "exposed_us": exposed_us, "kernel_ms_max_rank": k_ms},
         "launch": {"grid": st_stats["last_grid"], "block": st_stats["last_block"], "smem": st_stats["last_smem_bytes"],
                    "stages": st_stats["last_stages"], "kernel": st_stats["last_kernel"], "runs_per_trip": st_stats["last_runs_per_trip"],
-                   "mode": ("cuda-graph x%d passes, %d replays per region" % (U, steps // U)) if graph is not None else "eager"},
+                   "mode": ("cuda-graph x%d passes, %d replays per region" % (U, steps // U)) if graph is not None else "eager",
+                   "reserved_sms": reserve},
         "parity_check": parity,
         "counts_last_pass": {"ready": counts_host[0], "skip": counts_host[1], "expansion": counts_host[2], "evals": counts_host[3]},
         "global_counts_last_pass": (offsets["total"] if offsets else None),
@@ -624,6 +628,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_MAX_CTAS", "1")   # the collective is 32 bytes per rank: one CTA, so that one reserved SM holds it
         dist.init_process_group("nccl", device_id=dev)
     synth.set_threads(max(1, min(32, len(os.sched_getaffinity(0)) // max(1, min(world, 8)))))
     if args.ncu:

@@ -65,7 +65,7 @@ struct TopoMeta {
 
 struct bf_ctx {
   int device = 0;
-  int sm_count = 0;
+  int sm_count = 0;                    // SMs the frontier kernels spread over (device SMs minus the reserved ones)
   cudaStream_t stream = nullptr;
   // bf_eval pipeline: H2D copies, kernels and D2H copies of consecutive run chunks overlap on three streams
   static constexpr uint32_t kMaxChunks = 32;
@@ -772,6 +772,7 @@ int bf_create(bf_ctx** out, const bf_config* cfg) {
   if (!c) return BF_ENOMEM;
   c->device = dev;
   c->sm_count = prop.multiProcessorCount;
+  if (cfg && (cfg->flags & 0xFFu) && (int)(cfg->flags & 0xFFu) < c->sm_count) c->sm_count -= (int)(cfg->flags & 0xFFu);   // BF_CFG_RESERVE_SMS
   c->stats.sm_count = (uint32_t)prop.multiProcessorCount;
   if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&c->d_counts, sizeof(bf_counts)) != cudaSuccess ||

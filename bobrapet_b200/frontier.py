@@ -62,14 +62,15 @@ class TopologySet:
 
 
 class Frontier:
-    def __init__(self, device: int = 0, arena_bytes: int = 0, _borrowed_ctx=None):
+    def __init__(self, device: int = 0, arena_bytes: int = 0, _borrowed_ctx=None, reserve_sms: int = 0):
         self._lib = A.load()
         self._owned = _borrowed_ctx is None
         if _borrowed_ctx is not None:       # a shard's ctx owned by a FrontierGroup
             self._ctx = C.c_void_p(_borrowed_ctx)
             return
         self._ctx = C.c_void_p()
-        cfg = A.Config(struct_size=C.sizeof(A.Config), device=device, arena_bytes=arena_bytes, max_topologies=0, flags=0)
+        cfg = A.Config(struct_size=C.sizeof(A.Config), device=device, arena_bytes=arena_bytes, max_topologies=0,
+                       flags=(reserve_sms & 0xFF))   # BF_CFG_RESERVE_SMS: SMs left to other streams' kernels (the count all-gather)
         rc = self._lib.bf_create(C.byref(self._ctx), C.byref(cfg))
         if rc != A.BF_OK:
             self._ctx = None

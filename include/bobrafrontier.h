@@ -259,8 +259,12 @@ typedef struct bf_config {
   int32_t device;          /* CUDA ordinal; one ctx drives one GPU (one process per GPU) */
   uint64_t arena_bytes;    /* initial topology arena in HBM (grows on demand); 0 = default */
   uint32_t max_topologies; /* initial slot table size; 0 = default                       */
-  uint32_t flags;
+  uint32_t flags;          /* BF_CFG_*                                                   */
 } bf_config;
+/* The frontier kernels are persistent (one CTA per SM holding nearly all of its shared memory), so a kernel of ANOTHER
+ * stream — the NCCL all-gather of the counts — finds no SM until a pass ends and queues behind it.  Leaving k SMs out of
+ * the grid (k = flags & 0xFF) lets the collective run beside the next pass; it costs k / 148 of the pass.                */
+#define BF_CFG_RESERVE_SMS(k) ((uint32_t)(k) & 0xFFu)
 
 uint32_t bf_abi_version(void);
 const char* bf_strerror(int status);
