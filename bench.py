@@ -350,14 +350,20 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
     gathered = [exch.new_buffer() for _ in range(ROT)]
     work_stream = g.work_stream
 
+    # Consecutive passes work on different batches (ROT disjoint input / result / counts sets), so each pass is submitted with
+    # BF_EVAL_COUNTS_SET | BF_EVAL_PIPELINED: no counter fill between passes, and the start-up of pass k + 1 overlaps the tail
+    # of pass k (programmatic dependent launch).  BF_BENCH_PIPELINE=0 submits plain passes (fill + kernel, fully serialised).
+    pipe_flags = (A.EVAL_COUNTS_SET | A.EVAL_PIPELINED) if (os.environ.get("BF_BENCH_PIPELINE", "1") != "0" and ROT >= 2) else 0
+
     def one_pass(s, st_, with_gather=True):
         Lk, d_state, d_result, d_counts, _, d_exp, exp_cap = sets[s]
-        d_counts.zero_()
+        if not pipe_flags:
+            d_counts.zero_()
         if exp_cap:
             fr.eval_device(Lk, n_runs, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), st_.cuda_stream,
-                           flags=A.EVAL_EXPANSION, expansion_ptr=d_exp.data_ptr(), expansion_cap=exp_cap)
+                           flags=A.EVAL_EXPANSION | pipe_flags, expansion_ptr=d_exp.data_ptr(), expansion_cap=exp_cap)
         else:
-            fr.eval_device(Lk, n_runs, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), st_.cuda_stream)
+            fr.eval_device(Lk, n_runs, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), st_.cuda_stream, flags=pipe_flags)
         if world > 1 and with_gather:
             # the path's one collective: all-gather of the per-shard counts, overlapped with the next pass
             exch.gather(d_counts, gathered[s], st_)
@@ -477,7 +483,11 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
                                                "exposed_us": exposed_us, "kernel_ms_max_rank": k_ms},
         "launch": {"grid": st_stats["last_grid"], "block": st_stats["last_block"], "smem": st_stats["last_smem_bytes"],
                    "stages": st_stats["last_stages"], "kernel": st_stats["last_kernel"], "runs_per_trip": st_stats["last_runs_per_trip"],
-                   "mode": ("cuda-graph x%d passes, %d replays per region" % (U, steps // U)) if graph is not None else "eager",
+                   "mode": (("cuda-graph x%d passes, %d replays per region" % (U, steps // U)) if graph is not None else "eager") +
+                           ("; passes over the %d rotating batches submitted with BF_EVAL_COUNTS_SET | BF_EVAL_PIPELINED (no fill between "
+                            "passes; the start-up of pass k+1 overlaps the tail of pass k where the pass is the packed-lanes kernel alone)" % ROT
+                            if pipe_flags else "; plain passes (counter fill + kernel, serialised)"),
+                   "pipelined": bool(pipe_flags),
                    "reserved_sms": reserve},
         "parity_check": parity,
         "counts_last_pass": {"ready": counts_host[0], "skip": counts_host[1], "expansion": counts_host[2], "evals": counts_host[3]},

@@ -102,6 +102,7 @@ EVT_READY, EVT_SKIP, EVT_FAIL, EVT_NEEDS_COND, EVT_SKIP_DEP = 0x1, 0x2, 0x4, 0x8
 
 HEAD_SUMMARY_MASK, HEAD_DEAD, HEAD_LISTED, HEAD_COUNT_SHIFT = 0x7FFF, 0x7FFF, 0x8000, 16  # BF_HEAD_*
 EVAL_CHANGED_ONLY = 0x10
+EVAL_COUNTS_SET, EVAL_PIPELINED = 0x20, 0x40
 
 
 class CompactOut(C.Structure):

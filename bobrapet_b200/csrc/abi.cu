@@ -95,6 +95,7 @@ struct bf_ctx {
   uint8_t* d_state = nullptr; size_t d_state_cap = 0;
   uint8_t* d_result = nullptr; size_t d_result_cap = 0;
   unsigned long long* d_counts = nullptr;
+  unsigned long long* d_acc = nullptr;   // BF_EVAL_COUNTS_SET scratch of the packed-lanes kernel (device_record.h), zero between launches
   bf_counts* h_counts = nullptr;  // pinned landing zone for the counts block (a pageable target would make the copy synchronous)
   bf_expansion* d_exp = nullptr; size_t d_exp_cap = 0;
   // compact results (bf_eval_compact / bf_resident_tick_compact)
@@ -170,15 +171,21 @@ int ensure_dev(bf_ctx* c, T*& p, size_t& cap, size_t need_elems) {
 }
 
 // ---- record building -----------------------------------------------------------------------
-// BF_TOPO_FORMAT=csr keeps every topology in CSR form (A/B timing and the parity tests of that path); read per upload
-static bool force_csr() { const char* e = getenv("BF_TOPO_FORMAT"); return e && !strcmp(e, "csr"); }
+// BF_TOPO_FORMAT=csr keeps every topology in CSR form, =ell16 keeps the fixed-width rows at u16 entries (A/B timing and
+// the parity tests of those paths); read per upload.  0 = default (best format), 1 = CSR only, 2 = no byte entries
+static int forced_format() {
+  const char* e = getenv("BF_TOPO_FORMAT");
+  if (e && !strcmp(e, "csr")) return 1;
+  if (e && !strcmp(e, "ell16")) return 2;
+  return 0;
+}
 
 struct RecPlan {
   uint32_t off_col, off_planes, off_par, off_allow, rec_bytes, W, child_nibbles, ell, max_deg;
   std::vector<uint32_t> child_first, allow_off;
 };
 
-int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_kahn = true, bool csr_only = false) {
+int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_kahn = true, int forced = 0) {
   if (t.n_steps == 0 || t.n_steps > BF_MAX_STEPS) { why = "n_steps out of range (1..1024)"; return BF_ETOPO; }
   if (t.n_edges > BF_MAX_EDGES) { why = "n_edges exceeds 65535"; return BF_ETOPO; }
   if (!t.row_ptr || !t.step_flags || (t.n_edges && !t.col_idx)) { why = "null topology array"; return BF_EINVAL; }
@@ -244,17 +251,21 @@ int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_ka
   p.ell = 0;
   p.W = (S + 31) / 32;
   const uint32_t ell_rows = 32 * p.W;   // a row for every step of every word, so the walk fetches without a bounds test
-  if (K && 2 * K * ell_rows <= csr_bytes && !csr_only) p.ell = K;
+  if (K && forced != 1) {
+    // byte entries (device_record.h): every step index of a topology of at most 256 steps fits a byte
+    if (ell_rows <= 256 && forced != 2 && K * ell_rows + 4 * p.W <= csr_bytes) p.ell = K | bf::ELL_BYTE;
+    else if (2 * K * ell_rows <= csr_bytes) p.ell = K;
+  }
   if (p.ell) {
     p.off_col = off;
-    off += 2 * p.ell * ell_rows;
+    off += bf::ell_row_bytes(p.ell) * ell_rows;
   } else {
     off += round_up(2 * (S + 1), 16);
     p.off_col = off;
     off += round_up(2 * E + 8, 16);
   }
   p.off_planes = off;
-  off += round_up(bf::PL_COUNT * p.W * 4, 16);
+  off += round_up(bf::plane_count(p.ell) * p.W * 4, 16);
   p.off_par = off;
   off += t.n_parallel * (uint32_t)sizeof(bf::ParDesc);
   p.off_allow = off;
@@ -276,7 +287,18 @@ void build_record(const bf_topology& t, const RecPlan& p, uint8_t* rec) {
   h.max_deg = (uint16_t)(p.max_deg > 0xFFFF ? 0xFFFF : p.max_deg);
   h.child_nibbles = (uint16_t)p.child_nibbles;
   h.off_col = (uint16_t)p.off_col; h.ell = (uint16_t)p.ell; h.off_planes = p.off_planes; h.off_par = p.off_par; h.rec_bytes = p.rec_bytes;
-  if (p.ell) {
+  if (p.ell & bf::ELL_BYTE) {
+    // byte entries: a short row repeats its first entry, a row without needs holds its own index and is flagged NODEP
+    // (as are the rows past S); the planes are zeroed above and filled below
+    uint8_t* col = rec + p.off_col;
+    uint32_t* nodep = reinterpret_cast<uint32_t*>(rec + p.off_planes) + bf::PL_NODEP * W;
+    const uint32_t K = bf::ell_k(p.ell);
+    for (uint32_t i = 0; i < 32 * W; ++i) {
+      const uint32_t e0 = i < S ? t.row_ptr[i] : 0, n = i < S ? t.row_ptr[i + 1] - e0 : 0;
+      if (n == 0) nodep[i >> 5] |= 1u << (i & 31u);
+      for (uint32_t k = 0; k < K; ++k) col[i * K + k] = (uint8_t)(n == 0 ? i : t.col_idx[e0 + (k < n ? k : 0)]);
+    }
+  } else if (p.ell) {
     uint16_t* col = reinterpret_cast<uint16_t*>(rec + p.off_col);
     const uint16_t pad = (uint16_t)(32 * W);  // the status byte just past the last step word: always "satisfied"
     for (uint32_t i = 0; i < S; ++i) {
@@ -525,6 +547,15 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   }
   const uint32_t g_smem = 128 + g_wpb * (g_st * P.stage_bytes + work_general + 64);
 
+  // BF_EVAL_COUNTS_SET: the packed-lanes kernel alone publishes the totals itself (last CTA out); every other shape of a pass
+  // (two tiers, the general kernel, expansion counts, an empty batch) zeroes the block first and adds as usual
+  const bool counts_set = (b.flags & BF_EVAL_COUNTS_SET) && P.counts != nullptr;
+  const bool counts_in_kernel = counts_set && pack && !two_tier && !want_exp && b.n_runs != 0;
+  if (counts_set && !counts_in_kernel) BF_CUDA(c, cudaMemsetAsync(P.counts, 0, sizeof(bf_counts), stream));
+  P.acc = counts_in_kernel ? c->d_acc : nullptr;
+  // BF_EVAL_PIPELINED applies to a pass that is the packed-lanes kernel alone and touches the counts only behind its wait
+  if (!(pack && !two_tier && !want_exp && b.n_runs != 0 && (counts_in_kernel || P.counts == nullptr))) P.flags &= ~BF_EVAL_PIPELINED;
+
   uint32_t grid = 0, smem = 0;
   if (pack) {
     P.wq = wq; P.wq_log2 = lg; P.warps_per_block = nw; P.slot_groups = ng; P.stages = 1;
@@ -675,7 +706,7 @@ int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_
   std::vector<RecPlan> plans(count);
   size_t total = 0;
   std::string why;
-  const bool csr_only = force_csr();
+  const int forced = forced_format();
   // validation (Kahn) and record building are per topology: spread a bulk upload over the host cores
   const uint32_t n_thr = count >= 512 ? std::min<uint32_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
   auto parallel_for = [&](auto&& fn) {
@@ -691,7 +722,7 @@ int put_many_locked(bf_ctx* c, const bf_topology* topos, uint32_t count, uint32_
   parallel_for([&](uint32_t lo, uint32_t hi) {
     std::string w;
     for (uint32_t i = lo; i < hi; ++i) {
-      rcs[i] = plan_record(topos[i], plans[i], w, host_kahn, csr_only);
+      rcs[i] = plan_record(topos[i], plans[i], w, host_kahn, forced);
       if (rcs[i] != BF_OK) {
         std::lock_guard<std::mutex> g(why_mu);
         if (i < first_bad) { first_bad = i; why = w; }
@@ -776,6 +807,7 @@ int bf_create(bf_ctx** out, const bf_config* cfg) {
   c->stats.sm_count = (uint32_t)prop.multiProcessorCount;
   if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&c->d_counts, sizeof(bf_counts)) != cudaSuccess ||
+      cudaMalloc(&c->d_acc, 64) != cudaSuccess || cudaMemset(c->d_acc, 0, 64) != cudaSuccess ||
       cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 4 * sizeof(bf_counts), cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
     bf_destroy(c);  // releases whatever was created
@@ -801,7 +833,7 @@ void bf_destroy(bf_ctx* c) {
     if (c->ev_k[k]) cudaEventDestroy(c->ev_k[k]);
   }
   cudaFreeHost(c->h_counts);
-  cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts);
+  cudaFree(c->arena); cudaFree(c->slots_dev); cudaFree(c->d_state); cudaFree(c->d_result); cudaFree(c->d_counts); cudaFree(c->d_acc);
   cudaFree(c->d_defer); cudaFree(c->d_exp); cudaFree(c->d_exp_counts); cudaFree(c->d_offsets); cudaFree(c->d_block_sums); cudaFree(c->d_sched); cudaFree(c->d_deltas); cudaFree(c->d_rejected);
   cudaFree(c->d_head); cudaFree(c->d_events); cudaFree(c->d_cblock);
   for (Resident& r : c->resident) { cudaFree(r.d_state); cudaFree(r.d_result); cudaFree(r.d_result_prev); }

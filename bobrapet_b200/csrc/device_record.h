@@ -11,21 +11,30 @@
 //   +off_col      col_idx   u16[E]            dependency step indices, then >= 4 zero entries, pad 16
 //
 //   fixed-width rows (ell = K in {2, 4}; taken when no step has more than K needs and S*K entries are not
-//   larger than the CSR block they replace): row_ptr is implicit (row i starts at entry i*K)
+//   larger than the CSR block they replace; S > 256): row_ptr is implicit (row i starts at entry i*K)
 //   +32 = off_col col_idx   u16[32*W][K]      the needs of step i, unused entries (and the rows past S) = PAD
 //                                             PAD = 32*W: the status byte just past the last step word, always 0
 //                                             ("satisfied, not failed"), so a padded entry never changes a verdict
 //
-//   both
-//   +off_planes   planes    u32[8][W]         static step flags, BIT-SLICED (W = ceil(S/32)):
+//   fixed-width rows with BYTE entries (ell = 0x100 | K; taken for every topology of at most 256 steps that qualifies
+//   for fixed-width rows): a step index fits a byte, so the adjacency is HALF the size again
+//   +32 = off_col col_idx   u8[32*W][K]       the needs of step i; a row shorter than K repeats its first entry (the OR
+//                                             over a row's status bytes is idempotent); there is no PAD index (32*W = 256
+//                                             does not fit a byte at S = 256), so a row WITHOUT needs holds its own index
+//                                             and its step is flagged in a ninth static plane, NODEP: flagged steps never
+//                                             enter the walk, their dependencies are trivially met
+//
+//   all
+//   +off_planes   planes    u32[8 or 9][W]    static step flags, BIT-SLICED (W = ceil(S/32)):
 //                                             t0,t1,t2 (type), AF, TS, HAS_IF, G1 (comp), G2 (finally)
-//                                             = S bytes, same size as the canonical u8 step_flags[S]
+//                                             = S bytes, same size as the canonical u8 step_flags[S];
+//                                             byte-entry rows: + NODEP
 //   +off_par      ParDesc[P] (16 B each) followed by the branch allowFailure bit words
 //
 // Canonical ("algorithmic") bytes per topology, SURVEY.md section 8(d):
 //   2*(S+1) + 2*E + S  (u16 CSR + u8 flags).  The CSR record adds the header and the 16-byte paddings
 //   (~1.5% at cfg3); the fixed-width record drops row_ptr, so it is SMALLER than the canonical figure
-//   (cfg3: 2 336 B against 2 798 B).
+//   (cfg3: 2 336 B with u16 entries, 1 344 B with byte entries, against 2 798 B).
 #pragma once
 #include <stdint.h>
 
@@ -39,14 +48,18 @@ struct TopoHeader {
   uint16_t n_main, n_comp, n_final;
   uint16_t child_nibbles;  // total child nibbles of all descs
   uint16_t off_col;    // byte offset of col_idx
-  uint16_t ell;        // 0 = CSR (row_ptr at +32), K = 2 / 4: fixed-width rows of K entries, no row_ptr
+  uint16_t ell;        // 0 = CSR (row_ptr at +32), K = 2 / 4: fixed-width rows of K u16 entries, no row_ptr; 0x100 | K: byte entries
   uint32_t off_planes;
   uint32_t off_par;
   uint32_t rec_bytes;  // multiple of 16
 };
 static_assert(sizeof(TopoHeader) == 32, "TopoHeader must be 32 bytes");
 
-enum Plane { PL_T0 = 0, PL_T1, PL_T2, PL_AF, PL_TS, PL_HASIF, PL_G1, PL_G2, PL_COUNT };
+enum Plane { PL_T0 = 0, PL_T1, PL_T2, PL_AF, PL_TS, PL_HASIF, PL_G1, PL_G2, PL_COUNT, PL_NODEP = PL_COUNT };
+constexpr uint32_t ELL_BYTE = 0x100u;                                                   // TopoHeader::ell flag: byte entries
+__host__ __device__ inline uint32_t ell_k(uint32_t ell) { return ell & 0xFFu; }                      // entries per row
+__host__ __device__ inline uint32_t ell_row_bytes(uint32_t ell) { return (ell & ELL_BYTE) ? (ell & 0xFFu) : 2u * ell; }
+__host__ __device__ inline uint32_t plane_count(uint32_t ell) { return (ell & ELL_BYTE) ? PL_COUNT + 1u : PL_COUNT; }
 
 struct ParDesc {
   uint16_t step;
@@ -69,6 +82,8 @@ struct KParams {
   uint8_t* result;
   const Slot* slots;
   unsigned long long* counts;   // bf_counts (4 x u64) or nullptr
+  unsigned long long* acc;      // BF_EVAL_COUNTS_SET, packed-lanes kernel alone: ctx scratch {4 totals, CTA ticket}; the last CTA
+                                // out copies the totals to `counts` and clears the scratch (nullptr: add to `counts`)
   uint32_t* exp_counts;         // [n_runs] compact per-run expansion counts or nullptr
   // two-tier dispatch: the packed-lanes kernel appends the runs it cannot take (topologies with
   // parallel steps) to defer_list; the general kernel then runs over run_list[0..*run_list_count)

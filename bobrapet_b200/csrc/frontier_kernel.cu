@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
 
     // ---------------- planes of word `lane`: dynamic codes (state record) + static flags (topology) ----------------
     const bool act = lane < Wt;
-    uint32_t t0 = 0, t1 = 0, t2 = 0, AF = 0, TS = 0, HASIF = 0, G1 = 0, G2 = 0, VALID = 0;
+    uint32_t t0 = 0, t1 = 0, t2 = 0, AF = 0, TS = 0, HASIF = 0, G1 = 0, G2 = 0, VALID = 0, NODEP = 0;
     uint32_t c0 = 0, c1 = 0, d0 = 0, d1 = 0;
     uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     if (act) {
@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
       AF = lds_u32(sp + PL_AF * ps);
       if (CD) TS = lds_u32(sp + PL_TS * ps);
       if (XO) HASIF = lds_u32(sp + PL_HASIF * ps);
+      if (ell & ELL_BYTE) NODEP = lds_u32(sp + PL_NODEP * ps);   // byte-entry rows: steps without needs stay out of the walk
       G1 = lds_u32(sp + PL_G1 * ps); G2 = lds_u32(sp + PL_G2 * ps);
       VALID = bmsk_clamp(0u, S - lane * 32u);  // the word's steps below S (width clamps at 32)
       const uint32_t pw = sr_a + P.off_phase + lane * 4u, ds = Wmax * 4u;  // dynamic planes: stride of the layout
@@ -350,7 +351,9 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         const uint32_t SAT = COMPL | (realtime ? plut<BF_LUT_RT_SAT>(p0, p1, p2, p3) : 0u) | (allow_failed ? TERM : 0u);
         const uint32_t U = ~SAT;
         const uint32_t FD = skip_on_failed ? (TERM & ~SAT) : 0u;
-        const uint32_t CAND = GSEL & ~COMPL & ~RUNQ & ~TERM;
+        const uint32_t CAND0 = GSEL & ~COMPL & ~RUNQ & ~TERM;
+        const uint32_t FREE = CAND0 & NODEP;   // candidates without needs: met by definition (byte-entry rows only)
+        const uint32_t CAND = CAND0 & ~NODEP;  // the candidates whose rows are walked
         // ------------- stage C: masks -> one status byte per step (bit0 unmet, bit1 failed-dep) -------------
         __syncwarp();
         uint32_t m0 = 0;
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         constexpr int WK = OCC2 ? 2 : 4;
         if (skip_on_failed) walk_words_fmt<WK, true>(fmt, lane, CAND, rp_a, col_a, st_a, met_w, fd_w);  // warp-uniform dispatch
         else walk_words_fmt<WK, false>(fmt, lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
+        met_w |= FREE;
         uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
         if (CD) {
           ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
@@ -399,6 +403,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
                 fixup_item(lane, __shfl_sync(FULL, CAND, j), j, ell, rp_a, col_a, st_a, mfail_a, fclass, mb, fb);
                 if (lane == j) { met_w = mb; fd_w = fb; }
               }
+              met_w |= FREE;
               const uint32_t nf = met_w & c0 & c1;
               const bool same = !__any_sync(FULL, nf != fail_w);
               fail_w = nf;

@@ -13,13 +13,21 @@
 //
 // Data movement: the CTA (one per SM, persistent) owns a ring of NG slot groups in shared memory, each holding the R
 // state records (adjacent in HBM: ONE bulk copy) and R topology records (one bulk copy each) of a group, guarded by
-// one mbarrier per slot group.  The ring is shared by all warps of the CTA: the warp that finishes group t re-arms
-// the slot group it just read with the copies of group t + NG, which another warp will consume — so the number of
-// groups in flight adapts by itself (a warp waiting at a barrier IS a group in flight), and a CTA keeps 16 warps fed
-// from 17 slot groups where a private double-buffered ring per warp would allow only 8 warps.  The chain run ->
-// slot id -> slot entry is prefetched 32 (group, run) pairs at a time, one pair per lane, and the lanes that own the
-// pairs of a group issue its copies from their own registers.  A dead / oversized slot is marked by a zero header
-// written before the arrive, a run deferred to the general kernel by an all-ones header word.
+// one mbarrier per slot group.  The ring is shared by all warps of the CTA: groups are consumed in ticket order (a free
+// warp draws the CTA's next group from a shared counter), and the warp that finishes group t re-arms the slot group it
+// just read with the copies of group t + NG, which whichever warp draws that ticket will consume — so the number of
+// groups in flight adapts by itself (a warp waiting at a barrier IS a group in flight), and a CTA keeps 24 warps fed
+// from 33 slot groups where a private double-buffered ring per warp would allow only 16 warps.  The chain run ->
+// slot id -> slot entry of group t + NG is fetched by the R lanes that own its runs while the warp works on group t
+// (first link before the barrier wait, second after it), and those lanes issue the copies from their own registers.
+// A dead / oversized slot is marked by a zero header written before the arrive, a run deferred to the general kernel by
+// an all-ones header word.
+//
+// Start-up and tail: a cold CTA needs three dependent DRAM round trips (slot id, slot entry, bulk copy: ~3.6 - 6.6 us
+// measured with tools/trace_probe.py) before its first group can be evaluated, and the CTAs of a grid finish 4 - 5 us
+// apart.  BF_EVAL_PIPELINED (a caller's promise that consecutive passes are independent) launches the pass as a
+// programmatic dependent of the preceding kernel: its CTAs take the SMs that kernel has already left, so start-up,
+// launch gap and tail overlap (cfg3: 45.8 -> 40.1 us per pass); griddepcontrol.wait sits in front of the counters.
 //
 // All shared-memory traffic goes through 32-bit shared-window addresses.  Integer only; no tensor cores.
 #include "kernel_common.cuh"
@@ -32,7 +40,13 @@ extern __shared__ __align__(128) uint8_t smem_p[];
 #define WALK_K 4   // (run, word) items walked at once: independent load chains per warp (measured: 2: 50.9 us, 3: 50.0, 4: 49.5)
 #endif
 #ifndef PACK_MAX_WARPS
-#define PACK_MAX_WARPS 16   // warps per CTA the kernel is compiled for (registers: 65536 / (32 * PACK_MAX_WARPS) per thread)
+#define PACK_MAX_WARPS 24   // warps per CTA the kernel is compiled for (registers: 65536 / (32 * PACK_MAX_WARPS) per thread = 80).
+#endif                      // Measured at cfg3 with byte-entry rows (ring of 33 slot groups): 16: 48.2 us, 20: 47.1, 24: 45.6, 28: 47.9, 32: 49.4
+
+#ifdef PACK_TRACE   // timeline probe (tools/trace_probe.py, lib_ab builds only): per launch and CTA {start, first group landed, last group done, end}
+__device__ unsigned long long g_trace[8][160][4];
+__device__ unsigned int g_launch;
+DI unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #endif
 
 // ---- stage D over the (run, word) items of a group.
@@ -64,10 +78,10 @@ DI void walk_items_k(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t lg, 
     const uint32_t cw = __shfl_sync(FULL, CAND, L[k]);
     const uint32_t g = L[k] >> lg, i = (L[k] & wmask) * 32u + lane;
     c[k] = (cw >> lane) & 1u;
-    if (FMT == FMT_ELL4 || FMT == FMT_ELL2) {
+    if (fmt_traits<FMT>::fixed) {
       st[k] = C.st0 + g * C.st_stride;
-      p[k] = C.col0 + g * C.topo_buf + i * (FMT == FMT_ELL4 ? 8u : 4u);   // rows exist for every step of the word (device_record.h)
-      n[k] = (uint32_t)FMT;
+      p[k] = C.col0 + g * C.topo_buf + i * fmt_traits<FMT>::row_bytes;   // rows exist for every step of the word (device_record.h)
+      n[k] = (uint32_t)(FMT & 0xFF);
     } else {
       const uint4 t = lds_v4(C.tab_a + g * 16u);
       st[k] = t.z;
@@ -111,7 +125,9 @@ DI void walk_items_any(uint32_t lane, uint32_t CAND, uint32_t lg, const WalkCtx&
     const int fmt = fmt_of(meta >> 16, meta & 0xFFFFu);  // warp-uniform
     uint32_t one = todo & (0u - todo);
     todo ^= one;
-    if (fmt == FMT_ELL4) walk_items_k<1, FMT_ELL4, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
+    if (fmt == FMT_ELL4B) walk_items_k<1, FMT_ELL4B, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
+    else if (fmt == FMT_ELL2B) walk_items_k<1, FMT_ELL2B, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
+    else if (fmt == FMT_ELL4) walk_items_k<1, FMT_ELL4, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
     else if (fmt == FMT_CSR4) walk_items_k<1, FMT_CSR4, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
     else if (fmt == FMT_ELL2) walk_items_k<1, FMT_ELL2, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
     else walk_items_k<1, FMT_CSRL, NEED_FD>(lane, CAND, one, lg, C, met_w, fd_w);
@@ -121,6 +137,9 @@ DI void walk_items_any(uint32_t lane, uint32_t CAND, uint32_t lg, const WalkCtx&
 // CD: cond and/or decision codes present   XO: any of fail/needs_cond/skip_dep/phase_out requested
 template <bool CD, bool XO>
 __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(const KParams P) {
+  // BF_EVAL_PIPELINED: let the next kernel of the stream (launched as a programmatic dependent) take the SMs this grid leaves
+  // as its CTAs run out of groups; a no-op otherwise
+  if (P.flags & BF_EVAL_PIPELINED) asm volatile("griddepcontrol.launch_dependents;");
   const uint32_t lane = pin(threadIdx.x & 31u);  // pinned: otherwise rematerialised from S2R inside the loop
   const uint32_t warp = __shfl_sync(FULL, threadIdx.x >> 5, 0);  // through a shuffle: the compiler then treats it as warp-uniform
   const uint32_t NW = P.warps_per_block, NG = P.slot_groups;
@@ -128,6 +147,11 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
   const uint32_t g = pin(lane >> lg), w = pin(lane & (Wq - 1u));
   const uint32_t gmask = (Wq == 32u ? FULL : ((1u << Wq) - 1u)) << (g << lg);
 
+#ifdef PACK_TRACE
+  const unsigned long long tr_start = gtime();
+  const unsigned int tr_launch = *((volatile unsigned int*)&g_launch) & 7u;
+  unsigned long long tr_first = 0, tr_last = 0;
+#endif
   // ---- shared memory carve-up: [block counters 128 B][mbarriers, one per slot group][NG slot groups][warp scratch]
   // slot group: R state records (contiguous, as in HBM) then R topology buffers of topo_buf_bytes each.
   // The mbarriers sit in one block AWAY from the TMA destinations (a barrier next to a record tail cost 9 %).
@@ -145,7 +169,7 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
   const uint32_t st0_a = scratch_a + 128u;
   const uint32_t tab_a = st0_a + R * st_stride;
 
-  if (threadIdx.x < 4) blk_counts[threadIdx.x] = 0ull;
+  if (threadIdx.x < 5) blk_counts[threadIdx.x] = 0ull;   // four counters + the group ticket
   if (threadIdx.x < NG) {
     mbar_init(bars + 8u * threadIdx.x, R);
     sts_u32(armed_a + 4u * threadIdx.x, 0u);
@@ -158,41 +182,38 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
   const uint32_t N = P.n_runs;
   const uint32_t n_groups = (N + R - 1) >> (5 - lg);
   const uint32_t T = blockIdx.x < n_groups ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  // Issue schedule: group t < NG is issued in the prologue by warp t % NW; group t >= NG by the warp that consumed
-  // t - NG (it frees that slot group).  So warp `warp` issues, in order, q = 0, 1, ..:
-  //   t_of(q) = warp + q * NW                      while that is < NG   (n_pro of them)
-  //           = warp + (q - n_pro) * NW + NG        afterwards
-  const uint32_t n_pro = warp < NG ? (NG - warp + NW - 1) / NW : 0;
-  auto t_of = [&](uint32_t q) -> uint32_t { return q < n_pro ? warp + q * NW : warp + (q - n_pro) * NW + NG; };
+  // Schedule: groups are CONSUMED in ticket order — a warp that is free takes the next group of the CTA from a shared
+  // counter (a static t -> warp map left the warps with one group more than the others running alone at the end: 8 against
+  // 7.04 groups per warp at the headline size).  Group t lives in slot group t % NG, use number t / NG; groups t < NG are
+  // issued in the prologue (by warp t % NW), group t >= NG by the warp that consumed t - NG and thereby freed the slot.
+  const uint32_t n_pro = warp < NG ? (NG - warp + NW - 1) / NW : 0;   // my prologue issues: t = warp + q * NW < NG
 
-  // ---- producer side: lane l holds (issue index q0 + l / R, run l % R) of the current batch of GB = 32 / R issues
-  const uint32_t GB = 32u >> (5 - lg);        // = Wq: issues per prefetch batch
-  const uint32_t lq = lane >> (5 - lg), lr = lane & (R - 1u);   // my pair inside the batch: issue lq, run lr
-  uint32_t nq = 0;                            // next issue index (lane-uniform)
-  uint32_t nx_sid = 0xFFFFFFFFu, nx_run = 0xFFFFFFFFu;
-  uint32_t pf_run = 0xFFFFFFFFu, pf_lo = 0, pf_hi = 0, pf_bytes = 0, pf_meta = 0;
-  auto load_sids = [&](uint32_t q0) {
-    const uint32_t t = t_of(q0 + lq);
-    nx_sid = 0xFFFFFFFFu; nx_run = 0xFFFFFFFFu;
-    if (t < T) {
+  // ---- producer side: the chain run -> slot id -> slot entry of a group is fetched by the R lanes that own its runs.
+  // Prologue: lane l holds (issue q0 + l / R, run l % R) of a batch of GB = 32 / R issues; steady state: the lanes of
+  // issue 0 (lq == 0) hold the group my warp will issue when it is done with the current one.
+  const uint32_t GB = 32u >> (5 - lg);        // = Wq: issues per prologue batch
+  const uint32_t lq = lane >> (5 - lg), lr = lane & (R - 1u);   // my pair inside a batch: issue lq, run lr
+  uint32_t pf_sid = 0xFFFFFFFFu, pf_run = 0xFFFFFFFFu, pf_lo = 0, pf_hi = 0, pf_bytes = 0, pf_meta = 0;
+  auto load_sid = [&](uint32_t t, bool mine) {   // first link: my run's topology slot id (the head word of its state record)
+    pf_sid = 0xFFFFFFFFu; pf_run = 0xFFFFFFFFu;
+    if (mine && t < T) {
       const uint32_t r = ((blockIdx.x + t * gridDim.x) << (5 - lg)) + lr;
       if (r < N) {
-        nx_run = r;
-        nx_sid = __ldg(reinterpret_cast<const uint32_t*>(P.state + (size_t)r * P.state_stride));
+        pf_run = r;
+        pf_sid = __ldg(reinterpret_cast<const uint32_t*>(P.state + (size_t)r * P.state_stride));
       }
     }
   };
-  auto load_ents = [&]() {
-    pf_run = nx_run; pf_lo = 0; pf_hi = 0; pf_bytes = 0; pf_meta = 0;
-    if (nx_sid < P.n_slots) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.slots + nx_sid));
+  auto load_ent = [&]() {                        // second link: the slot entry (address, bytes, meta)
+    pf_lo = 0; pf_hi = 0; pf_bytes = 0; pf_meta = 0;
+    if (pf_sid < P.n_slots) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.slots + pf_sid));
       pf_lo = v.x; pf_hi = v.y; pf_bytes = v.z; pf_meta = v.w;
     }
   };
-  // issue the copies of issue index nq into slot group `sg`, which thereby starts its use number `use`
-  auto issue = [&](uint32_t sg, uint32_t use) {
-    const uint32_t t = t_of(nq);
-    if (t < T && lq == (nq & (GB - 1u))) {   // the R lanes that own this group's runs
+  // issue the copies of group t into slot group `sg`, which thereby starts its use number `use`; `mine`: my lane owns a run of it
+  auto issue = [&](uint32_t t, uint32_t sg, uint32_t use, bool mine) {
+    if (t < T && mine) {
       const uint32_t buf = groups_a + sg * group_bytes;
       const uint32_t bar = bars + 8u * sg;
       const uint32_t tb = buf + R * P.state_stride + lr * P.topo_buf_bytes;   // my run's topology buffer
@@ -210,15 +231,15 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
       if (lr == 0) bulk_g2s(buf, P.state + (size_t)first * P.state_stride, sbytes, bar);
       if (ok) bulk_g2s(tb, reinterpret_cast<const void*>((uint64_t)pf_lo | ((uint64_t)pf_hi << 32)), pf_bytes, bar);
     }
-    ++nq;
-    if ((nq & (GB - 1u)) == 0u) load_ents();                               // consumed from the next issue on
-    if ((nq & (GB - 1u)) == (GB >> 1)) load_sids((nq & ~(GB - 1u)) + GB);  // half a batch ahead (GB = 1: after load_ents)
   };
-  if (T != 0) {
-    load_sids(0);
-    load_ents();
-    if (GB == 1u) load_sids(1);  // R = 32 (S <= 32): a batch is one issue, keep one batch of slot ids ahead
-    for (uint32_t q = 0; q < n_pro; ++q) issue(warp + q * NW, 0u);  // slot group of t < NG is t itself
+  for (uint32_t q0 = 0; q0 < n_pro; q0 += GB) {      // prologue: GB of my issues at a time (both links of all of them in flight together)
+    const bool in_pro = q0 + lq < n_pro;
+    load_sid(warp + (q0 + lq) * NW, in_pro);
+    load_ent();
+    for (uint32_t k = 0; k < GB && q0 + k < n_pro; ++k) {
+      const uint32_t t = warp + (q0 + k) * NW;       // < NG: its slot group is t itself, use 0
+      issue(t, t, 0u, lq == k);
+    }
   }
 
   const uint32_t Wmax = P.words;
@@ -226,16 +247,23 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
   const bool has_dec = CD && P.off_decision != BF_OFF_NONE;
   uint32_t lane_ready = 0, lane_skip = 0, lane_evals = 0;  // per-lane running totals, reduced once at the end
 
-  uint32_t sg = warp, use = 0;  // slot group / use number of my next group (t = warp < NW <= NG)
-  for (uint32_t t = warp; t < T; t += NW) {
-    const uint32_t cur_sg = sg, cur_use = use;
+  // the next group to consume: a CTA-wide ticket counter behind the four block counters (smem_p + 32)
+  for (;;) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(reinterpret_cast<uint32_t*>(smem_p + 32), 1u);
+    t = __shfl_sync(FULL, t, 0);
+    if (t >= T) break;
+    const uint32_t cur_sg = t % NG, cur_use = t / NG;
+    load_sid(t + NG, lq == 0);   // first link of the group I shall issue into this slot group when I am done with it
     // The slot group is shared between warps: its use `cur_use` is armed by the warp that consumed the previous use.
     // A parity wait alone cannot tell "use u - 1 still pending" from "use u complete" (the parity then names the phase
     // before), so first wait until the arming warp has published use u; from then on the barrier is in phase u.
     while ((int32_t)(lds_poll_u32(armed_a + 4u * cur_sg) - (cur_use + 1u)) < 0) __nanosleep(32);
     mbar_wait(bars + 8u * cur_sg, cur_use & 1u);
-    sg += NW;
-    while (sg >= NG) { sg -= NG; ++use; }
+    load_ent();                  // second link (the slot id has arrived while I waited); consumed by issue() below
+#ifdef PACK_TRACE
+    if (t == 0) tr_first = gtime();
+#endif
 
     const uint32_t gid = blockIdx.x + t * gridDim.x;
     const uint32_t r = (gid << (5 - lg)) + g;                 // my run
@@ -258,7 +286,7 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
 
     // ---------------- planes of my word ----------------
     const bool act = w < Wt;
-    uint32_t AF = 0, TS = 0, HASIF = 0, G1 = 0, G2 = 0, VALID = 0, SYNC_T = 0;
+    uint32_t AF = 0, TS = 0, HASIF = 0, G1 = 0, G2 = 0, VALID = 0, SYNC_T = 0, NODEP = 0;
     uint32_t c0 = 0, c1 = 0, d0 = 0, d1 = 0;
     uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
     if (act) {
@@ -266,6 +294,7 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
       AF = lds_u32(sp + PL_AF * ps);
       G1 = lds_u32(sp + PL_G1 * ps); G2 = lds_u32(sp + PL_G2 * ps);
       if (XO) HASIF = lds_u32(sp + PL_HASIF * ps);
+      if (ell & ELL_BYTE) NODEP = lds_u32(sp + PL_NODEP * ps);   // byte-entry rows: steps without needs stay out of the walk
       VALID = bmsk_clamp(0u, S - w * 32u);
       const uint32_t pw = sr_a + P.off_phase + w * 4u, ds = Wmax * 4u;  // dynamic planes: stride of the layout
       p0 = lds_u32(pw); p1 = lds_u32(pw + ds); p2 = lds_u32(pw + 2u * ds); p3 = lds_u32(pw + 3u * ds);
@@ -378,7 +407,9 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
     const uint32_t SAT = COMPL | (realtime ? plut<BF_LUT_RT_SAT>(p0, p1, p2, p3) : 0u) | (allow_failed ? TERM : 0u);
     const uint32_t U = VALID & ~SAT;   // & VALID: bytes past the last step (the PAD byte of a narrower run) read "satisfied"
     const uint32_t FD = skip_on_failed ? (TERM & ~SAT) : 0u;
-    const uint32_t CAND = evaluate ? (GSEL & ~COMPL & ~RUNQ & ~TERM) : 0u;
+    const uint32_t CAND0 = evaluate ? (GSEL & ~COMPL & ~RUNQ & ~TERM) : 0u;
+    const uint32_t FREE = CAND0 & NODEP;   // candidates without needs: met by definition (byte-entry rows only)
+    const uint32_t CAND = CAND0 & ~NODEP;  // the candidates whose rows are walked
     // ------------- stage C: one status byte per step (bit0 unmet, bit1 failed-dep), all R runs -------------
     const bool any_fd = __any_sync(FULL, skip_on_failed);              // some run of the group has a failed-dependency class
     const int my_fmt = fmt_of(ell, max_deg);
@@ -409,6 +440,12 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
     if (mixed) {
       if (any_fd) walk_items_any<true>(lane, CAND, lg, wctx, met_w, fd_w);
       else walk_items_any<false>(lane, CAND, lg, wctx, met_w, fd_w);
+    } else if (fmt0 == FMT_ELL4B) {
+      if (any_fd) walk_items<FMT_ELL4B, true>(lane, CAND, lg, wctx, met_w, fd_w);
+      else walk_items<FMT_ELL4B, false>(lane, CAND, lg, wctx, met_w, fd_w);
+    } else if (fmt0 == FMT_ELL2B) {
+      if (any_fd) walk_items<FMT_ELL2B, true>(lane, CAND, lg, wctx, met_w, fd_w);
+      else walk_items<FMT_ELL2B, false>(lane, CAND, lg, wctx, met_w, fd_w);
     } else if (fmt0 == FMT_ELL4) {
       if (any_fd) walk_items<FMT_ELL4, true>(lane, CAND, lg, wctx, met_w, fd_w);
       else walk_items<FMT_ELL4, false>(lane, CAND, lg, wctx, met_w, fd_w);
@@ -422,6 +459,7 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
       if (any_fd) walk_items<FMT_CSRL, true>(lane, CAND, lg, wctx, met_w, fd_w);
       else walk_items<FMT_CSRL, false>(lane, CAND, lg, wctx, met_w, fd_w);
     }
+    met_w |= FREE;
     uint32_t ready_w = met_w, skipc_w = 0, fail_w = 0;
     if (CD) {
       ready_w = met_w & ~c0 & ~c1;   // BF_COND_PASS
@@ -444,6 +482,7 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
                        __shfl_sync(FULL, fclass, L), mb, fb);
             if (lane == L) { met_w = mb; fd_w = fb; }
           }
+          met_w |= FREE;
           const uint32_t nf = met_w & c0 & c1;
           const bool same = !__any_sync(FULL, nf != fail_w);
           fail_w = nf;
@@ -489,20 +528,59 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
     lane_evals += (w == 0 && live) ? S : 0u;
 
     __syncwarp();  // every lane is done with this slot group's buffers
-    issue(cur_sg, cur_use + 1u);  // re-arm it with group t + NG (consumed by whichever warp owns that t)
+    issue(t + NG, cur_sg, cur_use + 1u, lq == 0);  // re-arm it with group t + NG (consumed by whichever warp draws that ticket)
+#ifdef PACK_TRACE
+    if (t == 0 && lane == 0 && blockIdx.x < 160) g_trace[tr_launch][blockIdx.x][1] = tr_first;
+    tr_last = gtime();
+#endif
   }
+#ifdef PACK_TRACE
+  if (lane == 0 && blockIdx.x < 160) atomicMax(&g_trace[tr_launch][blockIdx.x][2], tr_last);
+#endif
 
+  // ---- BF_EVAL_PIPELINED: this grid may have started before the preceding kernel of the stream ended (it reads and writes
+  // nothing of that kernel's); from here on it touches the counts and then completes, so that kernel must be complete.
+  if (P.flags & BF_EVAL_PIPELINED) asm volatile("griddepcontrol.wait;" ::: "memory");
   // ---- counters: lane -> warp (redux) -> block (shared atomics) -> one global atomic per block ----
   if (P.counts) {
     const uint32_t wr = redux_add(lane_ready), ws = redux_add(lane_skip), we = redux_add(lane_evals);
-    if (lane == 0 && warp < T) {
+    if (lane == 0) {
       atomicAdd(&blk_counts[0], (unsigned long long)wr);
       atomicAdd(&blk_counts[1], (unsigned long long)ws);
       atomicAdd(&blk_counts[3], (unsigned long long)we);
     }
     __syncthreads();
-    if (threadIdx.x < 4 && blk_counts[threadIdx.x] != 0ull) atomicAdd(&P.counts[threadIdx.x], blk_counts[threadIdx.x]);
+    if (P.acc == nullptr) {
+      if (threadIdx.x < 4 && blk_counts[threadIdx.x] != 0ull) atomicAdd(&P.counts[threadIdx.x], blk_counts[threadIdx.x]);
+    } else {
+      // BF_EVAL_COUNTS_SET: totals gathered in the ctx scratch; the last CTA out writes them to `counts` and clears the scratch
+      // for the next launch (launches that touch the scratch are ordered: stream order, or the wait above)
+      if (threadIdx.x < 4 && blk_counts[threadIdx.x] != 0ull) atomicAdd(&P.acc[threadIdx.x], blk_counts[threadIdx.x]);
+      __threadfence();
+      __syncthreads();
+      volatile unsigned int* last_out = reinterpret_cast<volatile unsigned int*>(smem_p + 40);   // free word of the counter block
+      if (threadIdx.x == 0) *last_out = atomicAdd(reinterpret_cast<unsigned int*>(&P.acc[4]), 1u) == gridDim.x - 1u;
+      __syncthreads();
+      if (*last_out) {
+        __threadfence();
+        if (threadIdx.x < 4) P.counts[threadIdx.x] = atomicExch(&P.acc[threadIdx.x], 0ull);
+        if (threadIdx.x == 4) P.acc[4] = 0ull;
+      }
+    }
   }
+#ifdef PACK_TRACE
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < 160) {
+    g_trace[tr_launch][blockIdx.x][0] = tr_start;
+    g_trace[tr_launch][blockIdx.x][3] = gtime();
+    __threadfence();
+    if (atomicAdd(reinterpret_cast<unsigned int*>(&g_trace[tr_launch][159][0]), 1u) == gridDim.x - 1) {   // last CTA out
+      *reinterpret_cast<unsigned int*>(&g_trace[tr_launch][159][0]) = 0u;
+      atomicAdd(&g_launch, 1u);
+      for (int b = 0; b < 160; ++b) g_trace[(tr_launch + 1) & 7u][b][2] = 0ull;   // next launch's atomicMax cells
+    }
+  }
+#endif
 }
 
 typedef void (*PackFn)(const KParams);
@@ -515,6 +593,13 @@ static PackFn pick_pack(const KParams& P) {
 }
 
 uint32_t frontier_pack_max_warps() { return PACK_MAX_WARPS; }
+#ifdef PACK_TRACE
+extern "C" int bf_debug_pack_trace(unsigned long long* out, unsigned int* launch) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)) != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(launch, g_launch, sizeof(unsigned int)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 cudaError_t launch_frontier_pack(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream) {
   PackFn fn = pick_pack(P);
@@ -531,6 +616,15 @@ cudaError_t launch_frontier_pack(const KParams& P, uint32_t grid, uint32_t smem_
     if (dev >= 0 && dev < 8)
       for (int i = 0; i < 4; ++i)
         if (configured[dev][i] == nullptr) { configured[dev][i] = fn; break; }
+  }
+  if (P.flags & BF_EVAL_PIPELINED) {   // programmatic dependent launch: may start while the preceding kernel drains
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(P.warps_per_block * 32); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fn, P);
   }
   fn<<<grid, P.warps_per_block * 32, smem_bytes, stream>>>(P);
   return cudaGetLastError();

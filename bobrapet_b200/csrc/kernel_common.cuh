@@ -130,15 +130,21 @@ DI uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 //              masked with the row length)
 //   FMT_CSRL   CSR with longer rows: the same plus a tail loop
 //   FMT_ELL2 / FMT_ELL4   fixed-width rows of 2 / 4 entries, unused entries = PAD: no row_ptr, no mask
-enum : int { FMT_CSR4 = 0, FMT_CSRL = 1, FMT_ELL2 = 2, FMT_ELL4 = 4 };
+//   FMT_ELL2B / FMT_ELL4B the same with BYTE entries (S <= 256): a row is ONE 16- / 32-bit load; short rows repeat their
+//              first entry, rows without needs are kept out of the walk by the NODEP plane (device_record.h)
+enum : int { FMT_CSR4 = 0, FMT_CSRL = 1, FMT_ELL2 = 2, FMT_ELL4 = 4, FMT_ELL2B = 0x102, FMT_ELL4B = 0x104 };
+template <int FMT> struct fmt_traits {
+  static constexpr bool byte_rows = (FMT & 0x100) != 0;
+  static constexpr bool fixed = FMT >= 2;
+  static constexpr uint32_t row_bytes = byte_rows ? (uint32_t)(FMT & 0xFF) : 2u * (uint32_t)(FMT & 0xFF);  // fixed formats
+};
 
 DI int fmt_of(uint32_t ell, uint32_t max_deg) { return ell ? (int)ell : (max_deg > 4 ? FMT_CSRL : FMT_CSR4); }
 
 // phase 1 of an item: where the row of step `i` starts (shared address) and, for CSR, its length
 template <int FMT>
 DI void row_locate(bool cand, uint32_t i, uint32_t rp_addr, uint32_t col_addr, uint32_t& p, uint32_t& n) {
-  if (FMT == FMT_ELL4) { p = col_addr + i * 8u; n = 4u; }        // rows exist for every step of the word (padded to 32*W)
-  else if (FMT == FMT_ELL2) { p = col_addr + i * 4u; n = 2u; }
+  if (fmt_traits<FMT>::fixed) { p = col_addr + i * fmt_traits<FMT>::row_bytes; n = (uint32_t)(FMT & 0xFF); }  // rows exist for every step of the word (padded to 32*W)
   else {
     uint32_t e0 = 0;
     n = 0;
@@ -149,15 +155,25 @@ DI void row_locate(bool cand, uint32_t i, uint32_t rp_addr, uint32_t col_addr, u
 // phase 2: the first entries of the row (may run past a short CSR row: valid indices, masked in phase 3)
 template <int FMT>
 DI void row_fetch(uint32_t p, uint32_t (&x)[4]) {
+  if (FMT == FMT_ELL4B) {
+    const uint32_t r = lds_u32(p);
+    x[0] = r & 0xFFu; x[1] = (r >> 8) & 0xFFu; x[2] = (r >> 16) & 0xFFu; x[3] = r >> 24;
+    return;
+  }
+  if (FMT == FMT_ELL2B) {
+    const uint32_t r = lds_u16(p);
+    x[0] = r & 0xFFu; x[1] = r >> 8;
+    return;
+  }
   x[0] = lds_u16(p); x[1] = lds_u16(p + 2u);
   if (FMT != FMT_ELL2) { x[2] = lds_u16(p + 4u); x[3] = lds_u16(p + 6u); }
 }
 // phase 3: OR of the status bytes of the row's dependencies (CSR: one byte lane per entry, masked by the row length)
 template <int FMT>
 DI uint32_t row_status(uint32_t p, uint32_t n, const uint32_t (&x)[4], uint32_t st_addr) {
-  if (FMT == FMT_ELL2) return lds_u8(st_addr + x[0]) | lds_u8(st_addr + x[1]);
+  if (FMT == FMT_ELL2 || FMT == FMT_ELL2B) return lds_u8(st_addr + x[0]) | lds_u8(st_addr + x[1]);
   const uint32_t s0 = lds_u8(st_addr + x[0]), s1 = lds_u8(st_addr + x[1]), s2 = lds_u8(st_addr + x[2]), s3 = lds_u8(st_addr + x[3]);
-  if (FMT == FMT_ELL4) return s0 | s1 | s2 | s3;
+  if (FMT == FMT_ELL4 || FMT == FMT_ELL4B) return s0 | s1 | s2 | s3;
   uint32_t w = (((s3 * 256u + s2) * 256u + s1) * 256u + s0) & bmsk_clamp(0u, n * 8u);
   if (FMT == FMT_CSRL)
     for (uint32_t q = 4; q < n; ++q) w |= lds_u8(st_addr + lds_u16(p + q * 2u));
@@ -225,7 +241,9 @@ DI void walk_words(uint32_t lane, uint32_t CAND, uint32_t rp_addr, uint32_t col_
 template <int KMAX, bool NEED_FD>
 DI void walk_words_fmt(int fmt, uint32_t lane, uint32_t CAND, uint32_t rp_addr, uint32_t col_addr, uint32_t st_addr,
                        uint32_t& met_w, uint32_t& fd_w) {  // fmt is warp-uniform
-  if (fmt == FMT_ELL4) walk_words<KMAX, FMT_ELL4, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
+  if (fmt == FMT_ELL4B) walk_words<KMAX, FMT_ELL4B, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
+  else if (fmt == FMT_ELL4) walk_words<KMAX, FMT_ELL4, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
+  else if (fmt == FMT_ELL2B) walk_words<KMAX, FMT_ELL2B, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
   else if (fmt == FMT_CSR4) walk_words<KMAX, FMT_CSR4, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
   else if (fmt == FMT_ELL2) walk_words<KMAX, FMT_ELL2, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
   else walk_words<KMAX, FMT_CSRL, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
@@ -241,10 +259,11 @@ DI void fixup_item(uint32_t lane, uint32_t candw, uint32_t j, uint32_t ell, uint
   uint32_t acc = 0;
   if (cand) {
     uint32_t p, n;
-    if (ell) { p = col_addr + i * ell * 2u; n = ell; }
+    const uint32_t eb = (ell & ELL_BYTE) ? 1u : 2u;   // bytes per entry (the caller keeps NODEP steps out of candw)
+    if (ell) { n = ell_k(ell); p = col_addr + i * n * eb; }
     else { const uint32_t a = rp_addr + i * 2u; const uint32_t e0 = lds_u16(a); n = lds_u16(a + 2u) - e0; p = col_addr + e0 * 2u; }
     for (uint32_t e = 0; e < n; ++e) {
-      const uint32_t d = lds_u16(p + e * 2u);
+      const uint32_t d = eb == 1u ? lds_u8(p + e) : lds_u16(p + e * 2u);
       uint32_t sb = lds_u8(st_addr + d);
       if (d < i && ((lds_u32(mfail_addr + (d >> 5) * 4u) >> (d & 31u)) & 1u)) sb = failed_class;  // PAD >= i: never
       acc |= sb;

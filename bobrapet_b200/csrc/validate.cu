@@ -30,6 +30,10 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const Slot* sl
   const uint32_t S = th->S, W = th->W, ell = th->ell;  // ell: fixed-width rows, no row_ptr (device_record.h)
   const uint16_t* row_ptr = reinterpret_cast<const uint16_t*>(rec + sizeof(TopoHeader));
   const uint16_t* col = reinterpret_cast<const uint16_t*>(rec + th->off_col);
+  const uint8_t* colb = rec + th->off_col;                                                // byte-entry rows (device_record.h)
+  const bool bytes = (ell & ELL_BYTE) != 0;
+  const uint32_t K = ell_k(ell);
+  const uint32_t* nodep = reinterpret_cast<const uint32_t*>(rec + th->off_planes) + PL_NODEP * W;
   uint32_t* done = done_s[warp];
   for (uint32_t w = lane; w < W; w += 32) done[w] = 0;
   __syncwarp();
@@ -40,9 +44,10 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const Slot* sl
     for (uint32_t i = lane, k = 0; i < S; i += 32, ++k) {
       if ((done[i >> 5] >> (i & 31u)) & 1u) continue;
       bool ok = true;
-      const uint32_t e0 = ell ? i * ell : row_ptr[i], e1 = ell ? e0 + ell : row_ptr[i + 1];
+      uint32_t e0 = ell ? i * K : row_ptr[i], e1 = ell ? e0 + K : row_ptr[i + 1];
+      if (bytes && ((nodep[i >> 5] >> (i & 31u)) & 1u)) e1 = e0;  // a row without needs holds its own index
       for (uint32_t e = e0; e < e1 && ok; ++e) {
-        const uint32_t d = col[e];
+        const uint32_t d = bytes ? colb[e] : col[e];
         if (d >= S) continue;  // unused entry of a fixed-width row
         ok = (done[d >> 5] >> (d & 31u)) & 1u;
       }
@@ -84,6 +89,9 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) closure_kernel(const Slot* slo
   if (start >= S || W > words_out) return;
   const uint16_t* row_ptr = reinterpret_cast<const uint16_t*>(rec + sizeof(TopoHeader));
   const uint16_t* col = reinterpret_cast<const uint16_t*>(rec + th->off_col);
+  const uint8_t* colb = rec + th->off_col;
+  const bool bytes = (ell & ELL_BYTE) != 0;
+  const uint32_t K = ell_k(ell);
   const uint32_t* planes = reinterpret_cast<const uint32_t*>(rec + th->off_planes);
   auto group_of = [&](uint32_t i) -> uint32_t {
     const uint32_t w = i >> 5, b = i & 31u;
@@ -100,9 +108,9 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) closure_kernel(const Slot* slo
     for (uint32_t i = lane; i < S; i += 32) {
       if ((sel[i >> 5] >> (i & 31u)) & 1u) continue;
       if (group_of(i) != g0) continue;
-      const uint32_t e0 = ell ? i * ell : row_ptr[i], e1 = ell ? e0 + ell : row_ptr[i + 1];
+      const uint32_t e0 = ell ? i * K : row_ptr[i], e1 = ell ? e0 + K : row_ptr[i + 1];
       for (uint32_t e = e0; e < e1; ++e) {
-        const uint32_t d = col[e];
+        const uint32_t d = bytes ? colb[e] : col[e];   // (a NODEP row points at its own, unselected, step: no effect)
         if (d < S && ((sel[d >> 5] >> (d & 31u)) & 1u)) {
           atomicOr(&sel[i >> 5], 1u << (i & 31u));
           changed = true;

@@ -224,6 +224,16 @@ typedef struct bf_layout {
                                    launch effects of instantly-completing primitives             */
 #define BF_EVAL_EXPANSION 0x4u  /* emit (run, step, branch) tuples for ready parallel steps      */
 #define BF_EVAL_NO_COUNTS 0x8u  /* skip the global counters                                      */
+/* bf_eval_device only (0x10 is BF_EVAL_CHANGED_ONLY below):                                                          */
+#define BF_EVAL_COUNTS_SET 0x20u /* counts are OVERWRITTEN with this pass's totals (no zeroing by the caller, no memset
+                                   launch between passes: the last CTA out publishes the totals)                      */
+#define BF_EVAL_PIPELINED 0x40u  /* caller's promise: this pass reads nothing the preceding kernel of the stream writes
+                                   and writes nothing it reads or writes (other batch, other result / counts buffers).
+                                   The pass is then launched as a programmatic dependent of that kernel: its CTAs start
+                                   on SMs the previous pass has already left, so its start-up (slot ids -> slot entries
+                                   -> first bulk copies, ~6 us) overlaps the previous pass's tail.  Completion order is
+                                   kept (the pass completes after the preceding kernel).  Needs BF_EVAL_COUNTS_SET or
+                                   BF_EVAL_NO_COUNTS; ignored where it does not apply                               */
 
 typedef struct bf_expansion {
   uint32_t run;    /* index in the batch                      */
@@ -308,8 +318,8 @@ int bf_eval(bf_ctx* ctx, const bf_batch* batch);
 
 /* Asynchronous pass over DEVICE buffers on `stream` (a cudaStream_t): state,
  * result, expansion and counts are device pointers; nothing is synchronised.
- * counts must be zeroed by the caller unless BF_EVAL_NO_COUNTS (the library
- * only adds).                                                                 */
+ * counts must be zeroed by the caller unless BF_EVAL_NO_COUNTS or
+ * BF_EVAL_COUNTS_SET (without them the library only adds).                    */
 int bf_eval_device(bf_ctx* ctx, const bf_batch* batch, void* stream);
 
 /* ------------------------------------------------------------------ limiters

@@ -24,19 +24,20 @@ def fr():
     f.close()
 
 
-@pytest.fixture(params=["pack-ell", "pack-csr", "general-ell", "general-csr"])
+@pytest.fixture(params=["pack-ell", "pack-ell16", "pack-csr", "general-ell", "general-ell16", "general-csr"])
 def kernel(request, monkeypatch):
     """pack = the default: packed lanes (a group of R runs per warp trip, frontier_pack.cu; runs whose topology has
     parallel steps are deferred to the general kernel), general = the one-run-per-warp kernel forced for every run
     (BF_KERNEL=general).  ell / csr = the row format of the topology records: fixed-width rows where they qualify
-    (the default) or CSR only (BF_TOPO_FORMAT=csr, read at upload).  All must equal the oracle."""
+    (the default: byte entries up to 256 steps, u16 entries above), fixed-width rows with u16 entries only
+    (BF_TOPO_FORMAT=ell16) or CSR only (BF_TOPO_FORMAT=csr, read at upload).  All must equal the oracle."""
     k, fmt = request.param.split("-")
     if k == "general":
         monkeypatch.setenv("BF_KERNEL", "general")
     else:
         monkeypatch.delenv("BF_KERNEL", raising=False)
-    if fmt == "csr":
-        monkeypatch.setenv("BF_TOPO_FORMAT", "csr")
+    if fmt in ("csr", "ell16"):
+        monkeypatch.setenv("BF_TOPO_FORMAT", fmt)
     else:
         monkeypatch.delenv("BF_TOPO_FORMAT", raising=False)
     return k
@@ -171,13 +172,13 @@ def test_topology_rejections(fr):
     assert "unknown step dependency" in str(e.value)                          # dag_test.go:206
 
 
-@pytest.mark.parametrize("fmt", ["ell", "csr"])
+@pytest.mark.parametrize("fmt", ["ell", "ell16", "csr"])
 def test_packed_lanes_only_context(monkeypatch, fmt):
     """a ctx whose topologies have no parallel steps runs the packed-lanes kernel alone (4 runs per trip at S=256, 16 at
     S=64: the ring is planned from the largest record a run of the batch's layout can stage, not the ctx-wide largest)"""
     monkeypatch.delenv("BF_KERNEL", raising=False)
-    if fmt == "csr":
-        monkeypatch.setenv("BF_TOPO_FORMAT", "csr")
+    if fmt in ("csr", "ell16"):
+        monkeypatch.setenv("BF_TOPO_FORMAT", fmt)
     else:
         monkeypatch.delenv("BF_TOPO_FORMAT", raising=False)
     f = Frontier(0)
@@ -190,7 +191,8 @@ def test_packed_lanes_only_context(monkeypatch, fmt):
         st = f.stats()
         assert st["last_kernel"] == 1 and st["last_runs_per_trip"] == 4, st
         _, nbytes = f.topology_record(int(slots[0]))
-        assert nbytes == (2336 if fmt == "ell" else 2864), nbytes     # 32 + 256 x 8 + 256 | 32 + 528 + 2048 + 256
+        # 32 + 256 x 4 + 9 x 32 (byte entries + NODEP plane) | 32 + 256 x 8 + 256 | 32 + 528 + 2048 + 256
+        assert nbytes == {"ell": 1344, "ell16": 2336, "csr": 2864}[fmt], nbytes
         ts2 = synth.topologies(2, 0, 777, 64)
         s2 = f.put_topologies(ts2)
         L2 = make_layout(64, 0, A.F_ALL_OUT)
@@ -306,3 +308,30 @@ def test_pipelined_host_eval_matches_oracle(fr, monkeypatch, chunks):
     total = n * (L.state_stride + L.result_stride)
     want_chunks = {0: max(2, (total + (11 << 18)) // (11 << 19)), 1: 1, 5: 5, 32: 32}[chunks]
     assert fr.stats()["last_eval_chunks"] == want_chunks
+
+
+def test_pipelined_passes_counts_set(fr):
+    """BF_EVAL_COUNTS_SET | BF_EVAL_PIPELINED: passes over DIFFERENT batches submitted back to back on one stream (each a
+    programmatic dependent of the one before: its start overlaps the previous pass's tail) give the same records as plain
+    passes, and every counts block holds exactly its own pass's totals although nobody zeroes it."""
+    import torch
+    dev = torch.device("cuda", 0)
+    L = make_layout(256, 0, 0)
+    sets = []
+    for k in range(3):
+        ts = synth.topologies(3, 1000 + 50_000 * k, 20_000 + 17 * k, 256)
+        slots = fr.put_topologies(ts)
+        st = synth.state(3, 1000 + 50_000 * k, ts.S.shape[0], L, slots, ts)
+        want, wc = PK.evaluate(PK.PackedTopologies(ts, slots), L, st, threads=8)
+        sets.append((st.shape[0], torch.from_numpy(st).to(dev), torch.zeros((st.shape[0], L.result_stride), dtype=torch.uint8, device=dev),
+                     torch.full((4,), 123456789, dtype=torch.int64, device=dev), want, wc))
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for rep in range(4):
+            for n, d_state, d_result, d_counts, _, _ in sets:
+                fr.eval_device(L, n, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), s.cuda_stream,
+                               flags=A.EVAL_COUNTS_SET | A.EVAL_PIPELINED)
+    torch.cuda.synchronize()
+    for n, _, d_result, d_counts, want, wc in sets:
+        assert np.array_equal(d_result.cpu().numpy(), want)
+        assert d_counts.cpu().numpy().tolist() == [wc["ready"], wc["skip"], wc["expansion"], wc["evals"]]
