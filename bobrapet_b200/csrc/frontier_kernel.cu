@@ -202,36 +202,90 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
     for (uint32_t it = 0; it < cap; ++it) {
       ++iters;
       // ---------------- stage H: parallel join (dag.go:1131-1198) ----------------
+      // A registered parallel step that is neither absent nor terminal joins when every child is terminal: Failed if a
+      // terminal child neither succeeded / was skipped nor is an allowFailure branch, else Succeeded.  Child phases are
+      // nibbles, eight per word: one lane classifies eight children with the bit-plane tables (SWAR), a sub-warp of SW
+      // lanes covers one descriptor, 32 / SW descriptors per round, and the verdicts reach the lanes that own the parents'
+      // words through two scratch words per step word (the status-byte area is not in use yet at this point).
       if (CH && has_child && nP != 0) {
-        const uint8_t* sr = gptr(sr_a);
-        const uint8_t* tr = gptr(tr_a);
-        const uint64_t registered = *reinterpret_cast<const uint64_t*>(sr + 8);
-        const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + h1.z);
-        const uint8_t* child = sr + P.off_child;
-        for (uint32_t q = 0; q < nP; ++q) {
-          if (!((registered >> q) & 1ull)) continue;
-          const ParDesc d = pd[q];
-          if (d.branches == 0) continue;  // no children to wait for (dag.go:1140-1143)
-          const uint32_t wj = d.step >> 5, wb = d.step & 31u;
-          const uint32_t ph = ((__shfl_sync(FULL, p0, wj) >> wb) & 1u) | (((__shfl_sync(FULL, p1, wj) >> wb) & 1u) << 1) |
-                              (((__shfl_sync(FULL, p2, wj) >> wb) & 1u) << 2) | (((__shfl_sync(FULL, p3, wj) >> wb) & 1u) << 3);
-          if (ph == 0 || ((BF_LUT_TERMINAL >> ph) & 1u)) continue;
-          const uint32_t* allow = reinterpret_cast<const uint32_t*>(tr + d.allow_off);
-          bool all_done = true, any_failed = false;
-          for (uint32_t b = lane; b < d.branches; b += 32) {
-            const uint32_t cph = get_nibble(child, d.child_first + b);
-            const bool done = cph != 0 && ((BF_LUT_TERMINAL >> cph) & 1u);
-            const bool okc = cph == BF_PHASE_SUCCEEDED || cph == BF_PHASE_SKIPPED || ((allow[b >> 5] >> (b & 31u)) & 1u);
-            all_done = all_done && done;
-            any_failed = any_failed || (done && !okc);
-          }
-          all_done = __all_sync(FULL, all_done);
-          any_failed = __any_sync(FULL, any_failed);
-          if (all_done) {
-            marked = true;
-            if (lane == wj) {  // the lane that owns word wj rewrites its planes
-              const uint32_t m = 1u << wb;
-              if (any_failed) pset<BF_PHASE_FAILED>(m, p0, p1, p2, p3); else pset<BF_PHASE_SUCCEEDED>(m, p0, p1, p2, p3);
+        const uint32_t ACTIVE = T_PAR & (p0 | p1 | p2 | p3) & ~plut<BF_LUT_TERMINAL>(p0, p1, p2, p3);
+        if (__any_sync(FULL, ACTIVE != 0)) {
+          const uint32_t pd_a = tr_a + h1.z, child_a = sr_a + P.off_child;
+          const uint32_t reg_lo = lds_u32(sr_a + 8), reg_hi = lds_u32(sr_a + 12);
+          uint32_t mb = 0;
+          for (uint32_t q = lane; q < nP; q += 32) mb = max(mb, lds_u16(pd_a + q * 16u + 2u));
+          mb = __reduce_max_sync(FULL, mb);
+          const uint32_t mw = (mb + 7u) >> 3;   // child words of the widest descriptor
+          if (mw <= 32u) {
+            uint32_t lgs = 0;
+            while ((1u << lgs) < mw) ++lgs;
+            const uint32_t SW = 1u << lgs, DPI = 32u >> lgs, sub = lane >> lgs, wi = lane & (SW - 1u);
+            const uint32_t gm = (SW == 32u ? FULL : ((1u << SW) - 1u)) << (sub << lgs);
+            const uint32_t tS = st_a, tF = st_a + 4u * Wt;
+            __syncwarp();
+            if (act) { sts_u32(tS + lane * 4u, 0u); sts_u32(tF + lane * 4u, 0u); }
+            __syncwarp();
+            for (uint32_t q0 = 0; q0 < nP; q0 += DPI) {
+              const uint32_t q = q0 + sub;
+              bool take = q < nP;
+              uint4 d = make_uint4(0u, 0u, 0u, 0u);
+              if (take) d = lds_v4(pd_a + q * 16u);          // step | branches << 16, child_first, allow_off, -
+              const uint32_t step = d.x & 0xFFFFu, br = d.x >> 16, wj = (step >> 5) & 31u, wb = step & 31u;
+              const uint32_t actw = __shfl_sync(FULL, ACTIVE, wj);
+              take = take && br != 0u && (((q < 32u ? reg_lo >> q : reg_hi >> (q - 32u)) & 1u) != 0u) && (((actw >> wb) & 1u) != 0u);
+              bool nd = false, fl = false;
+              if (take && wi * 8u < br) {
+                const uint32_t cw = lds_u32(child_a + (d.y >> 1) + wi * 4u);   // child_first is a multiple of 8 nibbles
+                const uint32_t vm = 0x11111111u & bmsk_clamp(0u, min(8u, br - wi * 8u) * 4u);
+                uint32_t x0 = cw & 0x11111111u, x1 = (cw >> 1) & 0x11111111u, x2 = (cw >> 2) & 0x11111111u, x3 = (cw >> 3) & 0x11111111u;
+                const uint32_t keep = ~(x0 & x1 & x2 & x3);                     // the reserved code 15 reads as 0
+                x0 &= keep; x1 &= keep; x2 &= keep; x3 &= keep;
+                const uint32_t done = plut<BF_LUT_TERMINAL>(x0, x1, x2, x3);
+                const uint32_t ab = (lds_u32(tr_a + d.z + (wi >> 2) * 4u) >> ((wi & 3u) * 8u)) & 0xFFu;   // allowFailure bits of my 8 branches
+                const uint32_t okc = plut<BF_LUT_COMPLETED0>(x0, x1, x2, x3) | spread4(ab);
+                nd = (vm & ~done) != 0u;
+                fl = (vm & done & ~okc) != 0u;
+              }
+              const uint32_t ndm = __ballot_sync(FULL, nd), flm = __ballot_sync(FULL, fl);
+              if (take && wi == 0u && (ndm & gm) == 0u) red_or_shared(((flm & gm) ? tF : tS) + wj * 4u, 1u << wb);
+            }
+            __syncwarp();
+            uint32_t sS = 0, sF = 0;
+            if (act) { sS = lds_u32(tS + lane * 4u); sF = lds_u32(tF + lane * 4u); }
+            if (__any_sync(FULL, (sS | sF) != 0u)) marked = true;
+            pset<BF_PHASE_SUCCEEDED>(sS, p0, p1, p2, p3);
+            pset<BF_PHASE_FAILED>(sF, p0, p1, p2, p3);
+            __syncwarp();
+          } else {   // more than 256 branches on one step: one descriptor at a time, one child per lane
+            const uint8_t* sr = gptr(sr_a);
+            const uint8_t* tr = gptr(tr_a);
+            const uint64_t registered = *reinterpret_cast<const uint64_t*>(sr + 8);
+            const ParDesc* pd = reinterpret_cast<const ParDesc*>(tr + h1.z);
+            const uint8_t* child = sr + P.off_child;
+            for (uint32_t q = 0; q < nP; ++q) {
+              if (!((registered >> q) & 1ull)) continue;
+              const ParDesc d = pd[q];
+              if (d.branches == 0) continue;  // no children to wait for (dag.go:1140-1143)
+              const uint32_t wj = d.step >> 5, wb = d.step & 31u;
+              if (!((__shfl_sync(FULL, ACTIVE, wj) >> wb) & 1u)) continue;
+              const uint32_t* allow = reinterpret_cast<const uint32_t*>(tr + d.allow_off);
+              bool all_done = true, any_failed = false;
+              for (uint32_t b = lane; b < d.branches; b += 32) {
+                const uint32_t cph = get_nibble(child, d.child_first + b);
+                const bool done = cph != 0 && ((BF_LUT_TERMINAL >> cph) & 1u);
+                const bool okc = cph == BF_PHASE_SUCCEEDED || cph == BF_PHASE_SKIPPED || ((allow[b >> 5] >> (b & 31u)) & 1u);
+                all_done = all_done && done;
+                any_failed = any_failed || (done && !okc);
+              }
+              all_done = __all_sync(FULL, all_done);
+              any_failed = __any_sync(FULL, any_failed);
+              if (all_done) {
+                marked = true;
+                if (lane == wj) {  // the lane that owns word wj rewrites its planes
+                  const uint32_t m = 1u << wb;
+                  if (any_failed) pset<BF_PHASE_FAILED>(m, p0, p1, p2, p3); else pset<BF_PHASE_SUCCEEDED>(m, p0, p1, p2, p3);
+                }
+              }
             }
           }
         }
