@@ -254,6 +254,8 @@ int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_ka
   if (K && forced != 1) {
     // byte entries (device_record.h): every step index of a topology of at most 256 steps fits a byte
     if (ell_rows <= 256 && forced != 2 && K * ell_rows + 4 * p.W <= csr_bytes) p.ell = K | bf::ELL_BYTE;
+    // 10-bit entries: topologies of more than 512 steps (never staged by the packed-lanes kernel) with rows of up to 4 needs
+    else if (K == 4 && p.W > 16 && forced != 2 && 5 * ell_rows + 4 * p.W <= csr_bytes) p.ell = 4 | bf::ELL_PACK10;
     else if (2 * K * ell_rows <= csr_bytes) p.ell = K;
   }
   if (p.ell) {
@@ -287,16 +289,24 @@ void build_record(const bf_topology& t, const RecPlan& p, uint8_t* rec) {
   h.max_deg = (uint16_t)(p.max_deg > 0xFFFF ? 0xFFFF : p.max_deg);
   h.child_nibbles = (uint16_t)p.child_nibbles;
   h.off_col = (uint16_t)p.off_col; h.ell = (uint16_t)p.ell; h.off_planes = p.off_planes; h.off_par = p.off_par; h.rec_bytes = p.rec_bytes;
-  if (p.ell & bf::ELL_BYTE) {
-    // byte entries: a short row repeats its first entry, a row without needs holds its own index and is flagged NODEP
-    // (as are the rows past S); the planes are zeroed above and filled below
+  if (bf::ell_has_nodep(p.ell)) {
+    // byte / 10-bit entries: a short row repeats its first entry, a row without needs holds its own index and is flagged
+    // NODEP (as are the rows past S); the planes are zeroed above and filled below
     uint8_t* col = rec + p.off_col;
+    uint32_t* lo = reinterpret_cast<uint32_t*>(col);
     uint32_t* nodep = reinterpret_cast<uint32_t*>(rec + p.off_planes) + bf::PL_NODEP * W;
     const uint32_t K = bf::ell_k(p.ell);
     for (uint32_t i = 0; i < 32 * W; ++i) {
       const uint32_t e0 = i < S ? t.row_ptr[i] : 0, n = i < S ? t.row_ptr[i + 1] - e0 : 0;
       if (n == 0) nodep[i >> 5] |= 1u << (i & 31u);
-      for (uint32_t k = 0; k < K; ++k) col[i * K + k] = (uint8_t)(n == 0 ? i : t.col_idx[e0 + (k < n ? k : 0)]);
+      uint32_t x[4] = {0, 0, 0, 0};
+      for (uint32_t k = 0; k < K; ++k) x[k] = n == 0 ? i : t.col_idx[e0 + (k < n ? k : 0)];
+      if (p.ell & bf::ELL_PACK10) {
+        lo[i] = x[0] | (x[1] << 10) | (x[2] << 20) | (x[3] << 30);
+        col[128 * W + i] = (uint8_t)(x[3] >> 2);
+      } else {
+        for (uint32_t k = 0; k < K; ++k) col[i * K + k] = (uint8_t)x[k];
+      }
     }
   } else if (p.ell) {
     uint16_t* col = reinterpret_cast<uint16_t*>(rec + p.off_col);
@@ -510,7 +520,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   if (!pack || two_tier) {
     bf::KParams PG = P;
     PG.work_bytes = work_general;
-    const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | (L.fields << 16);
+    const uint32_t variant = (b.flags & BF_EVAL_FIXPOINT) | (P.any_parallel << 8) | ((two_tier ? 1u : 0u) << 9) | (L.fields << 16);
     if (c->plan_wpb == 0 || c->plan_key_stride != L.state_stride || c->plan_key_words != L.words ||
         c->plan_key_rec != batch_rec_bytes || c->plan_key_variant != variant) {
       // Plan: as many resident warps per SM as registers / shared memory allow — the pass is latency/issue bound
@@ -523,8 +533,9 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
       const char* env_b = getenv("BF_BLOCKS_PER_SM");
       for (uint32_t st = 1; st <= 4; ++st) {
         if (env_st && (uint32_t)atoi(env_st) != st) continue;
-        for (uint32_t wpb = 16; wpb >= 1; wpb = (wpb > 4 ? wpb - 4 : wpb - 1)) {
+        for (uint32_t wpb = 24; wpb >= 1; wpb = (wpb > 4 ? wpb - 4 : wpb - 1)) {   // 24 / 20: the 80-register build (frontier_kernel.cu)
           if (env_w && !pack && (uint32_t)atoi(env_w) != wpb) continue;
+          if (wpb > 16 && two_tier) continue;   // the run-list tier exists as the 16-warp build only
           const uint32_t smem_try = 128 + wpb * (st * P.stage_bytes + work_general + 64);
           if (smem_try > budget) continue;
           uint32_t occ2 = 0;

@@ -24,11 +24,17 @@
 //                                             and its step is flagged in a ninth static plane, NODEP: flagged steps never
 //                                             enter the walk, their dependencies are trivially met
 //
+//   fixed-width rows with 10-BIT entries (ell = 0x200 | 4; taken for topologies of more than 512 steps — the ones only the
+//   one-run-per-warp kernel stages — whose rows have at most 4 needs): a step index below 1024 fits 10 bits
+//   +32 = off_col lo        u32[32*W]         entries 0, 1, 2 in bits 0-9, 10-19, 20-29; the low 2 bits of entry 3 in bits 30-31
+//   +32 + 128*W   hi        u8[32*W]          the high 8 bits of entry 3          (5 bytes per row against 8)
+//                                             short rows, rows without needs and NODEP as for byte entries
+//
 //   all
 //   +off_planes   planes    u32[8 or 9][W]    static step flags, BIT-SLICED (W = ceil(S/32)):
 //                                             t0,t1,t2 (type), AF, TS, HAS_IF, G1 (comp), G2 (finally)
 //                                             = S bytes, same size as the canonical u8 step_flags[S];
-//                                             byte-entry rows: + NODEP
+//                                             byte-entry and 10-bit rows: + NODEP
 //   +off_par      ParDesc[P] (16 B each) followed by the branch allowFailure bit words
 //
 // Canonical ("algorithmic") bytes per topology, SURVEY.md section 8(d):
@@ -48,7 +54,7 @@ struct TopoHeader {
   uint16_t n_main, n_comp, n_final;
   uint16_t child_nibbles;  // total child nibbles of all descs
   uint16_t off_col;    // byte offset of col_idx
-  uint16_t ell;        // 0 = CSR (row_ptr at +32), K = 2 / 4: fixed-width rows of K u16 entries, no row_ptr; 0x100 | K: byte entries
+  uint16_t ell;        // 0 = CSR (row_ptr at +32), K = 2 / 4: fixed-width rows of K u16 entries, no row_ptr; 0x100 | K: byte entries; 0x204: 10-bit entries
   uint32_t off_planes;
   uint32_t off_par;
   uint32_t rec_bytes;  // multiple of 16
@@ -57,9 +63,22 @@ static_assert(sizeof(TopoHeader) == 32, "TopoHeader must be 32 bytes");
 
 enum Plane { PL_T0 = 0, PL_T1, PL_T2, PL_AF, PL_TS, PL_HASIF, PL_G1, PL_G2, PL_COUNT, PL_NODEP = PL_COUNT };
 constexpr uint32_t ELL_BYTE = 0x100u;                                                   // TopoHeader::ell flag: byte entries
+constexpr uint32_t ELL_PACK10 = 0x200u;                                                 // TopoHeader::ell flag: 10-bit entries (K = 4)
 __host__ __device__ inline uint32_t ell_k(uint32_t ell) { return ell & 0xFFu; }                      // entries per row
-__host__ __device__ inline uint32_t ell_row_bytes(uint32_t ell) { return (ell & ELL_BYTE) ? (ell & 0xFFu) : 2u * ell; }
-__host__ __device__ inline uint32_t plane_count(uint32_t ell) { return (ell & ELL_BYTE) ? PL_COUNT + 1u : PL_COUNT; }
+__host__ __device__ inline uint32_t ell_row_bytes(uint32_t ell) {
+  return (ell & ELL_PACK10) ? 5u : ((ell & ELL_BYTE) ? (ell & 0xFFu) : 2u * ell);
+}
+__host__ __device__ inline bool ell_has_nodep(uint32_t ell) { return (ell & (ELL_BYTE | ELL_PACK10)) != 0; }
+__host__ __device__ inline uint32_t plane_count(uint32_t ell) { return ell_has_nodep(ell) ? PL_COUNT + 1u : PL_COUNT; }
+// entry e of row i of a fixed-width block at `col` (any of the three entry widths); W = words of the topology
+__host__ __device__ inline uint32_t ell_entry(const uint8_t* col, uint32_t ell, uint32_t W, uint32_t i, uint32_t e) {
+  if (ell & ELL_PACK10) {
+    const uint32_t lo = reinterpret_cast<const uint32_t*>(col)[i];
+    return e < 3u ? (lo >> (10u * e)) & 0x3FFu : (lo >> 30) | ((uint32_t)col[128u * W + i] << 2);
+  }
+  if (ell & ELL_BYTE) return col[i * (ell & 0xFFu) + e];
+  return reinterpret_cast<const uint16_t*>(col)[i * ell + e];
+}
 
 struct ParDesc {
   uint16_t step;

@@ -15,8 +15,8 @@
 // the 32 per-step verdicts of a word straight into one word of the ready / skip bit masks.
 //
 // All shared-memory traffic of the loop uses 32-bit shared-window addresses (ld.shared / st.shared through inline
-// PTX).  The kernel is compiled in variants <CD, CH, FX, XO, LIST, OCC2> (cond/decision codes present, parallel
-// steps present, device fixpoint, extra outputs, run-list tier, build for two resident CTAs per SM) so the common
+// PTX).  The kernel is compiled in variants <CD, CH, FX, XO, LIST, RB> (cond/decision codes present, parallel
+// steps present, device fixpoint, extra outputs, run-list tier, register budget of the build) so the common
 // pass carries no dead work.  Integer only; no tensor cores.  ~3 KB in, 80 B out per run at the BASELINE
 // configuration; 78 % of the measured HBM copy peak there, bounded by instruction issue.
 #include "kernel_common.cuh"
@@ -28,10 +28,13 @@ extern __shared__ __align__(128) uint8_t smem_raw[];
 // CD: cond and/or decision codes present   CH: topologies with `parallel` steps may occur (stage H, expansion count)
 // FX: device-side fixpoint (BF_EVAL_FIXPOINT)   XO: any of fail/needs_cond/skip_dep/phase_out requested
 // LIST: second-tier run over P.run_list (runs deferred by the packed-lanes kernel)
-// OCC2: compiled for two resident 512-thread CTAs per SM (<= 64 registers); chosen by the host plan when the
-//       shared-memory ring of two CTAs fits, otherwise the unconstrained build runs one CTA per SM
-template <bool CD, bool CH, bool FX, bool XO, bool LIST, bool OCC2>
-__global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KParams P) {
+// RB: register budget of the build, chosen by the host plan from what fits shared memory (the pass is bound by per-warp
+//       instruction latency: resident warps first) —
+//       0: one CTA of up to 16 warps per SM (<= 128 registers)
+//       1: two resident CTAs of up to 16 warps (<= 64 registers)
+//       2: one CTA of up to 24 warps (<= 80 registers)
+template <bool CD, bool CH, bool FX, bool XO, bool LIST, int RB>
+__global__ void __launch_bounds__(RB == 2 ? 768 : 512, RB == 1 ? 2 : 1) frontier_kernel(const KParams P) {
   const uint32_t lane = pin(threadIdx.x & 31u);  // pinned: otherwise rematerialised from S2R inside the loop
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t ST = P.stages;
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
       AF = lds_u32(sp + PL_AF * ps);
       if (CD) TS = lds_u32(sp + PL_TS * ps);
       if (XO) HASIF = lds_u32(sp + PL_HASIF * ps);
-      if (ell & ELL_BYTE) NODEP = lds_u32(sp + PL_NODEP * ps);   // byte-entry rows: steps without needs stay out of the walk
+      if (ell_has_nodep(ell)) NODEP = lds_u32(sp + PL_NODEP * ps);   // byte-entry rows: steps without needs stay out of the walk
       G1 = lds_u32(sp + PL_G1 * ps); G2 = lds_u32(sp + PL_G2 * ps);
       VALID = bmsk_clamp(0u, S - lane * 32u);  // the word's steps below S (width clamps at 32)
       const uint32_t pw = sr_a + P.off_phase + lane * 4u, ds = Wmax * 4u;  // dynamic planes: stride of the layout
@@ -196,7 +199,9 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
     uint32_t summary = 0, iters = 0;
     bool marked = false;  // some phase was rewritten (lane-uniform)
     const uint32_t cap = FX ? (P.max_iter ? P.max_iter : S + 1) : 1u;
-    const uint32_t rp_a = tr_a + (uint32_t)sizeof(TopoHeader), col_a = tr_a + (h1.x & 0xFFFFu);  // row_ptr u16[S+1] (CSR only), col_idx
+    const uint32_t col_a = tr_a + (h1.x & 0xFFFFu);   // col_idx / the fixed-width block
+    // row_ptr u16[S+1] (CSR); the walks' row_ptr argument carries the high-byte array of a 10-bit block instead
+    const uint32_t rp_a = (ell & ELL_PACK10) ? col_a + 128u * Wt : tr_a + (uint32_t)sizeof(TopoHeader);
     if (ell && lane == 0) sts_u32(st_a + 32u * Wt, 0u);  // status byte PAD = 32*W: what unused row entries point at
 
     for (uint32_t it = 0; it < cap; ++it) {
@@ -211,28 +216,40 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         const uint32_t ACTIVE = T_PAR & (p0 | p1 | p2 | p3) & ~plut<BF_LUT_TERMINAL>(p0, p1, p2, p3);
         if (__any_sync(FULL, ACTIVE != 0)) {
           const uint32_t pd_a = tr_a + h1.z, child_a = sr_a + P.off_child;
-          const uint32_t reg_lo = lds_u32(sr_a + 8), reg_hi = lds_u32(sr_a + 12);
-          uint32_t mb = 0;
-          for (uint32_t q = lane; q < nP; q += 32) mb = max(mb, lds_u16(pd_a + q * 16u + 2u));
+          // which descriptors join at all: registered, with children, parent neither absent nor terminal (lane q <-> desc q,
+          // second round for descs 32..63), and the widest of them — usually none or a few of the run's descriptors
+          uint32_t take_lo = 0, take_hi = 0, mb = 0;
+          for (uint32_t q0 = 0; q0 < nP; q0 += 32) {
+            const uint32_t q = q0 + lane;
+            const uint32_t sb = q < nP ? lds_u32(pd_a + q * 16u) : 0u;   // step | branches << 16
+            const uint32_t actw = __shfl_sync(FULL, ACTIVE, ((sb & 0xFFFFu) >> 5) & 31u);
+            const uint32_t reg = lds_u32(sr_a + 8u + (q0 >> 3));          // children_registered, 32 descs per word
+            const bool tk = q < nP && (sb >> 16) != 0u && ((reg >> lane) & 1u) != 0u && ((actw >> (sb & 31u)) & 1u) != 0u;
+            const uint32_t m = __ballot_sync(FULL, tk);
+            if (q0 == 0) take_lo = m; else take_hi = m;
+            if (tk) mb = max(mb, sb >> 16);
+          }
           mb = __reduce_max_sync(FULL, mb);
-          const uint32_t mw = (mb + 7u) >> 3;   // child words of the widest descriptor
-          if (mw <= 32u) {
-            uint32_t lgs = 0;
-            while ((1u << lgs) < mw) ++lgs;
+          const uint32_t mw = (mb + 7u) >> 3;   // child words of the widest joining descriptor
+          if ((take_lo | take_hi) == 0u) {
+            // nothing to join in this pass
+          } else if (mw <= 32u) {
+            const uint32_t lgs = mw > 1u ? 32u - (uint32_t)__clz(mw - 1u) : 0u;   // sub-warp of SW = 2^lgs >= mw lanes per descriptor
             const uint32_t SW = 1u << lgs, DPI = 32u >> lgs, sub = lane >> lgs, wi = lane & (SW - 1u);
             const uint32_t gm = (SW == 32u ? FULL : ((1u << SW) - 1u)) << (sub << lgs);
+            const uint32_t dmask = DPI == 32u ? FULL : ((1u << DPI) - 1u);
             const uint32_t tS = st_a, tF = st_a + 4u * Wt;
             __syncwarp();
             if (act) { sts_u32(tS + lane * 4u, 0u); sts_u32(tF + lane * 4u, 0u); }
             __syncwarp();
             for (uint32_t q0 = 0; q0 < nP; q0 += DPI) {
+              const uint32_t tw = q0 < 32u ? take_lo >> q0 : take_hi >> (q0 - 32u);   // DPI divides 32: a round never straddles the words
+              if ((tw & dmask) == 0u) continue;                                       // warp-uniform
               const uint32_t q = q0 + sub;
-              bool take = q < nP;
+              const bool take = (tw >> sub) & 1u;
               uint4 d = make_uint4(0u, 0u, 0u, 0u);
               if (take) d = lds_v4(pd_a + q * 16u);          // step | branches << 16, child_first, allow_off, -
-              const uint32_t step = d.x & 0xFFFFu, br = d.x >> 16, wj = (step >> 5) & 31u, wb = step & 31u;
-              const uint32_t actw = __shfl_sync(FULL, ACTIVE, wj);
-              take = take && br != 0u && (((q < 32u ? reg_lo >> q : reg_hi >> (q - 32u)) & 1u) != 0u) && (((actw >> wb) & 1u) != 0u);
+              const uint32_t step = d.x & 0xFFFFu, br = d.x >> 16, wj = step >> 5, wb = step & 31u;
               bool nd = false, fl = false;
               if (take && wi * 8u < br) {
                 const uint32_t cw = lds_u32(child_a + (d.y >> 1) + wi * 4u);   // child_first is a multiple of 8 nibbles
@@ -432,7 +449,7 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
         uint32_t met_w, fd_w;
         // candidate words per walk group (walk_words, kernel_common.cuh): 2 at two CTAs per SM, 4 where one CTA per
         // SM leaves little else to hide latency
-        constexpr int WK = OCC2 ? 2 : 4;
+        constexpr int WK = RB == 1 ? 2 : 4;
         if (skip_on_failed) walk_words_fmt<WK, true>(fmt, lane, CAND, rp_a, col_a, st_a, met_w, fd_w);  // warp-uniform dispatch
         else walk_words_fmt<WK, false>(fmt, lane, CAND, rp_a, col_a, st_a, met_w, fd_w);
         met_w |= FREE;
@@ -553,33 +570,35 @@ __global__ void __launch_bounds__(512, OCC2 ? 2 : 1) frontier_kernel(const KPara
 
 // ------------------------------------------------------------------ host-side dispatch
 typedef void (*KernelFn)(const KParams);
-template <bool LIST, bool OCC2>
+template <bool LIST, int RB>
 static KernelFn pick_kernel(bool cd, bool ch, bool fx, bool xo) {
   static const KernelFn table[16] = {
-      frontier_kernel<false, false, false, false, LIST, OCC2>, frontier_kernel<false, false, false, true, LIST, OCC2>,
-      frontier_kernel<false, false, true, false, LIST, false>, frontier_kernel<false, false, true, true, LIST, false>,
-      frontier_kernel<false, true, false, false, LIST, OCC2>,  frontier_kernel<false, true, false, true, LIST, OCC2>,
-      frontier_kernel<false, true, true, false, LIST, false>,  frontier_kernel<false, true, true, true, LIST, false>,
-      frontier_kernel<true, false, false, false, LIST, OCC2>,  frontier_kernel<true, false, false, true, LIST, OCC2>,
-      frontier_kernel<true, false, true, false, LIST, false>,  frontier_kernel<true, false, true, true, LIST, false>,
-      frontier_kernel<true, true, false, false, LIST, OCC2>,   frontier_kernel<true, true, false, true, LIST, OCC2>,
-      frontier_kernel<true, true, true, false, LIST, false>,   frontier_kernel<true, true, true, true, LIST, false>,
+      frontier_kernel<false, false, false, false, LIST, RB>, frontier_kernel<false, false, false, true, LIST, RB>,
+      frontier_kernel<false, false, true, false, LIST, 0>,   frontier_kernel<false, false, true, true, LIST, 0>,
+      frontier_kernel<false, true, false, false, LIST, RB>,  frontier_kernel<false, true, false, true, LIST, RB>,
+      frontier_kernel<false, true, true, false, LIST, 0>,    frontier_kernel<false, true, true, true, LIST, 0>,
+      frontier_kernel<true, false, false, false, LIST, RB>,  frontier_kernel<true, false, false, true, LIST, RB>,
+      frontier_kernel<true, false, true, false, LIST, 0>,    frontier_kernel<true, false, true, true, LIST, 0>,
+      frontier_kernel<true, true, false, false, LIST, RB>,   frontier_kernel<true, true, false, true, LIST, RB>,
+      frontier_kernel<true, true, true, false, LIST, 0>,     frontier_kernel<true, true, true, true, LIST, 0>,
   };
   return table[(cd ? 8 : 0) | (ch ? 4 : 0) | (fx ? 2 : 0) | (xo ? 1 : 0)];
 }
 
-static KernelFn kernel_for(const KParams& P, bool occ2) {
+// rb: the build (template parameter RB); the fixpoint and run-list variants exist as RB = 0 only
+static KernelFn kernel_for(const KParams& P, uint32_t rb) {
   const bool cd = P.off_cond != BF_OFF_NONE || P.off_decision != BF_OFF_NONE;
   const bool ch = P.any_parallel != 0;  // join needs the child area; the expansion count needs only the descs
   const bool fx = (P.flags & BF_EVAL_FIXPOINT) != 0;
   const bool xo = P.off_fail != BF_OFF_NONE || P.off_needs_cond != BF_OFF_NONE || P.off_skip_dep != BF_OFF_NONE ||
                   P.off_phase_out != BF_OFF_NONE;
-  if (P.run_list) return pick_kernel<true, false>(cd, ch, fx, xo);   // second tier: a handful of runs
-  return occ2 ? pick_kernel<false, true>(cd, ch, fx, xo) : pick_kernel<false, false>(cd, ch, fx, xo);
+  if (P.run_list) return pick_kernel<true, 0>(cd, ch, fx, xo);   // second tier: a handful of runs
+  if (rb == 2 && !fx) return pick_kernel<false, 2>(cd, ch, fx, xo);
+  return rb == 1 ? pick_kernel<false, 1>(cd, ch, fx, xo) : pick_kernel<false, 0>(cd, ch, fx, xo);
 }
 
 cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream) {
-  KernelFn fn = kernel_for(P, P.occ2 != 0);
+  KernelFn fn = kernel_for(P, P.occ2);
   static KernelFn configured[8][64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -603,13 +622,21 @@ cudaError_t launch_frontier(const KParams& P, uint32_t grid, uint32_t smem_bytes
 int frontier_max_blocks_per_sm(const KParams& P, uint32_t threads, uint32_t smem_bytes, uint32_t* occ2) {
   int n = 0;
   *occ2 = 0;
-  KernelFn fn2 = kernel_for(P, true);
+  if (threads > 512) {   // more than 16 warps per CTA: the 80-register build, one CTA per SM (no fixpoint variants)
+    if (P.flags & BF_EVAL_FIXPOINT) return 0;
+    KernelFn fn3 = kernel_for(P, 2);
+    cudaFuncSetAttribute(fn3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn3, (int)threads, smem_bytes) != cudaSuccess || n < 1) return 0;
+    *occ2 = 2;
+    return 1;
+  }
+  KernelFn fn2 = kernel_for(P, 1);
   cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn2, (int)threads, smem_bytes) == cudaSuccess && n >= 2) {
     *occ2 = 1;
     return n;
   }
-  KernelFn fn = kernel_for(P, false);
+  KernelFn fn = kernel_for(P, 0);
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, (int)threads, smem_bytes) != cudaSuccess) return 1;
   return n;

@@ -89,7 +89,7 @@ DI void walk_items_k(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t lg, 
     }
   }
 #pragma unroll
-  for (int k = 0; k < K; ++k) row_fetch<FMT>(p[k], x[k]);
+  for (int k = 0; k < K; ++k) row_fetch<FMT>(p[k], n[k], x[k]);
 #pragma unroll
   for (int k = 0; k < K; ++k) wv[k] = row_status<FMT>(p[k], n[k], x[k], st[k]);
 #pragma unroll
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
       AF = lds_u32(sp + PL_AF * ps);
       G1 = lds_u32(sp + PL_G1 * ps); G2 = lds_u32(sp + PL_G2 * ps);
       if (XO) HASIF = lds_u32(sp + PL_HASIF * ps);
-      if (ell & ELL_BYTE) NODEP = lds_u32(sp + PL_NODEP * ps);   // byte-entry rows: steps without needs stay out of the walk
+      if (ell_has_nodep(ell)) NODEP = lds_u32(sp + PL_NODEP * ps);   // byte-entry rows: steps without needs stay out of the walk
       VALID = bmsk_clamp(0u, S - w * 32u);
       const uint32_t pw = sr_a + P.off_phase + w * 4u, ds = Wmax * 4u;  // dynamic planes: stride of the layout
       p0 = lds_u32(pw); p1 = lds_u32(pw + ds); p2 = lds_u32(pw + 2u * ds); p3 = lds_u32(pw + 3u * ds);

@@ -133,11 +133,14 @@ DI uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 //   FMT_ELL2 / FMT_ELL4   fixed-width rows of 2 / 4 entries, unused entries = PAD: no row_ptr, no mask
 //   FMT_ELL2B / FMT_ELL4B the same with BYTE entries (S <= 256): a row is ONE 16- / 32-bit load; short rows repeat their
 //              first entry, rows without needs are kept out of the walk by the NODEP plane (device_record.h)
-enum : int { FMT_CSR4 = 0, FMT_CSRL = 1, FMT_ELL2 = 2, FMT_ELL4 = 4, FMT_ELL2B = 0x102, FMT_ELL4B = 0x104 };
+//   FMT_ELL4P  four 10-BIT entries (S > 512, the one-run-per-warp kernel only): one 32-bit load + one byte load per row; the
+//              `rp_addr` argument of the walks carries the address of the block's high-byte array (there is no row_ptr)
+enum : int { FMT_CSR4 = 0, FMT_CSRL = 1, FMT_ELL2 = 2, FMT_ELL4 = 4, FMT_ELL2B = 0x102, FMT_ELL4B = 0x104, FMT_ELL4P = 0x204 };
 template <int FMT> struct fmt_traits {
   static constexpr bool byte_rows = (FMT & 0x100) != 0;
+  static constexpr bool packed10 = (FMT & 0x200) != 0;
   static constexpr bool fixed = FMT >= 2;
-  static constexpr uint32_t row_bytes = byte_rows ? (uint32_t)(FMT & 0xFF) : 2u * (uint32_t)(FMT & 0xFF);  // fixed formats
+  static constexpr uint32_t row_bytes = packed10 ? 4u : (byte_rows ? (uint32_t)(FMT & 0xFF) : 2u * (uint32_t)(FMT & 0xFF));  // fixed formats (10-bit: the lo words)
 };
 
 DI int fmt_of(uint32_t ell, uint32_t max_deg) { return ell ? (int)ell : (max_deg > 4 ? FMT_CSRL : FMT_CSR4); }
@@ -145,7 +148,8 @@ DI int fmt_of(uint32_t ell, uint32_t max_deg) { return ell ? (int)ell : (max_deg
 // phase 1 of an item: where the row of step `i` starts (shared address) and, for CSR, its length
 template <int FMT>
 DI void row_locate(bool cand, uint32_t i, uint32_t rp_addr, uint32_t col_addr, uint32_t& p, uint32_t& n) {
-  if (fmt_traits<FMT>::fixed) { p = col_addr + i * fmt_traits<FMT>::row_bytes; n = (uint32_t)(FMT & 0xFF); }  // rows exist for every step of the word (padded to 32*W)
+  if (fmt_traits<FMT>::packed10) { p = col_addr + i * 4u; n = rp_addr + i; }   // n carries the address of the row's high byte
+  else if (fmt_traits<FMT>::fixed) { p = col_addr + i * fmt_traits<FMT>::row_bytes; n = (uint32_t)(FMT & 0xFF); }  // rows exist for every step of the word (padded to 32*W)
   else {
     uint32_t e0 = 0;
     n = 0;
@@ -155,7 +159,12 @@ DI void row_locate(bool cand, uint32_t i, uint32_t rp_addr, uint32_t col_addr, u
 }
 // phase 2: the first entries of the row (may run past a short CSR row: valid indices, masked in phase 3)
 template <int FMT>
-DI void row_fetch(uint32_t p, uint32_t (&x)[4]) {
+DI void row_fetch(uint32_t p, uint32_t n, uint32_t (&x)[4]) {
+  if (FMT == FMT_ELL4P) {
+    const uint32_t lo = lds_u32(p), hi = lds_u8(n);
+    x[0] = lo & 0x3FFu; x[1] = (lo >> 10) & 0x3FFu; x[2] = (lo >> 20) & 0x3FFu; x[3] = (lo >> 30) | (hi << 2);
+    return;
+  }
   if (FMT == FMT_ELL4B) {
     const uint32_t r = lds_u32(p);
     x[0] = r & 0xFFu; x[1] = (r >> 8) & 0xFFu; x[2] = (r >> 16) & 0xFFu; x[3] = r >> 24;
@@ -174,7 +183,7 @@ template <int FMT>
 DI uint32_t row_status(uint32_t p, uint32_t n, const uint32_t (&x)[4], uint32_t st_addr) {
   if (FMT == FMT_ELL2 || FMT == FMT_ELL2B) return lds_u8(st_addr + x[0]) | lds_u8(st_addr + x[1]);
   const uint32_t s0 = lds_u8(st_addr + x[0]), s1 = lds_u8(st_addr + x[1]), s2 = lds_u8(st_addr + x[2]), s3 = lds_u8(st_addr + x[3]);
-  if (FMT == FMT_ELL4 || FMT == FMT_ELL4B) return s0 | s1 | s2 | s3;
+  if (FMT == FMT_ELL4 || FMT == FMT_ELL4B || FMT == FMT_ELL4P) return s0 | s1 | s2 | s3;
   uint32_t w = (((s3 * 256u + s2) * 256u + s1) * 256u + s0) & bmsk_clamp(0u, n * 8u);
   if (FMT == FMT_CSRL)
     for (uint32_t q = 4; q < n; ++q) w |= lds_u8(st_addr + lds_u16(p + q * 2u));
@@ -200,7 +209,7 @@ DI void walk_group(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t rp_add
     row_locate<FMT>(c[k], j[k] * 32u + lane, rp_addr, col_addr, p[k], n[k]);
   }
 #pragma unroll
-  for (int k = 0; k < K; ++k) row_fetch<FMT>(p[k], x[k]);
+  for (int k = 0; k < K; ++k) row_fetch<FMT>(p[k], n[k], x[k]);
 #pragma unroll
   for (int k = 0; k < K; ++k) w[k] = row_status<FMT>(p[k], n[k], x[k], st_addr);
 #pragma unroll
@@ -242,7 +251,8 @@ DI void walk_words(uint32_t lane, uint32_t CAND, uint32_t rp_addr, uint32_t col_
 template <int KMAX, bool NEED_FD>
 DI void walk_words_fmt(int fmt, uint32_t lane, uint32_t CAND, uint32_t rp_addr, uint32_t col_addr, uint32_t st_addr,
                        uint32_t& met_w, uint32_t& fd_w) {  // fmt is warp-uniform
-  if (fmt == FMT_ELL4B) walk_words<KMAX, FMT_ELL4B, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
+  if (fmt == FMT_ELL4P) walk_words<KMAX, FMT_ELL4P, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
+  else if (fmt == FMT_ELL4B) walk_words<KMAX, FMT_ELL4B, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
   else if (fmt == FMT_ELL4) walk_words<KMAX, FMT_ELL4, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
   else if (fmt == FMT_ELL2B) walk_words<KMAX, FMT_ELL2B, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
   else if (fmt == FMT_CSR4) walk_words<KMAX, FMT_CSR4, NEED_FD>(lane, CAND, rp_addr, col_addr, st_addr, met_w, fd_w);
@@ -261,10 +271,13 @@ DI void fixup_item(uint32_t lane, uint32_t candw, uint32_t j, uint32_t ell, uint
   if (cand) {
     uint32_t p, n;
     const uint32_t eb = (ell & ELL_BYTE) ? 1u : 2u;   // bytes per entry (the caller keeps NODEP steps out of candw)
-    if (ell) { n = ell_k(ell); p = col_addr + i * n * eb; }
+    uint32_t lo10 = 0, hi10 = 0;
+    if (ell & ELL_PACK10) { n = 4u; p = 0; lo10 = lds_u32(col_addr + i * 4u); hi10 = lds_u8(rp_addr + i); }  // rp_addr: the high-byte array
+    else if (ell) { n = ell_k(ell); p = col_addr + i * n * eb; }
     else { const uint32_t a = rp_addr + i * 2u; const uint32_t e0 = lds_u16(a); n = lds_u16(a + 2u) - e0; p = col_addr + e0 * 2u; }
     for (uint32_t e = 0; e < n; ++e) {
-      const uint32_t d = eb == 1u ? lds_u8(p + e) : lds_u16(p + e * 2u);
+      const uint32_t d = (ell & ELL_PACK10) ? (e < 3u ? (lo10 >> (10u * e)) & 0x3FFu : (lo10 >> 30) | (hi10 << 2))
+                                            : (eb == 1u ? lds_u8(p + e) : lds_u16(p + e * 2u));
       uint32_t sb = lds_u8(st_addr + d);
       if (d < i && ((lds_u32(mfail_addr + (d >> 5) * 4u) >> (d & 31u)) & 1u)) sb = failed_class;  // PAD >= i: never
       acc |= sb;

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const Slot* sl
   const uint16_t* row_ptr = reinterpret_cast<const uint16_t*>(rec + sizeof(TopoHeader));
   const uint16_t* col = reinterpret_cast<const uint16_t*>(rec + th->off_col);
   const uint8_t* colb = rec + th->off_col;                                                // byte-entry rows (device_record.h)
-  const bool bytes = (ell & ELL_BYTE) != 0;
+  const bool nodep_fmt = ell_has_nodep(ell);
   const uint32_t K = ell_k(ell);
   const uint32_t* nodep = reinterpret_cast<const uint32_t*>(rec + th->off_planes) + PL_NODEP * W;
   uint32_t* done = done_s[warp];
@@ -45,9 +45,9 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const Slot* sl
       if ((done[i >> 5] >> (i & 31u)) & 1u) continue;
       bool ok = true;
       uint32_t e0 = ell ? i * K : row_ptr[i], e1 = ell ? e0 + K : row_ptr[i + 1];
-      if (bytes && ((nodep[i >> 5] >> (i & 31u)) & 1u)) e1 = e0;  // a row without needs holds its own index
+      if (nodep_fmt && ((nodep[i >> 5] >> (i & 31u)) & 1u)) e1 = e0;  // a row without needs holds its own index
       for (uint32_t e = e0; e < e1 && ok; ++e) {
-        const uint32_t d = bytes ? colb[e] : col[e];
+        const uint32_t d = ell ? ell_entry(colb, ell, W, i, e - e0) : col[e];
         if (d >= S) continue;  // unused entry of a fixed-width row
         ok = (done[d >> 5] >> (d & 31u)) & 1u;
       }
@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) closure_kernel(const Slot* slo
   const uint16_t* row_ptr = reinterpret_cast<const uint16_t*>(rec + sizeof(TopoHeader));
   const uint16_t* col = reinterpret_cast<const uint16_t*>(rec + th->off_col);
   const uint8_t* colb = rec + th->off_col;
-  const bool bytes = (ell & ELL_BYTE) != 0;
   const uint32_t K = ell_k(ell);
   const uint32_t* planes = reinterpret_cast<const uint32_t*>(rec + th->off_planes);
   auto group_of = [&](uint32_t i) -> uint32_t {
@@ -110,7 +109,7 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) closure_kernel(const Slot* slo
       if (group_of(i) != g0) continue;
       const uint32_t e0 = ell ? i * K : row_ptr[i], e1 = ell ? e0 + K : row_ptr[i + 1];
       for (uint32_t e = e0; e < e1; ++e) {
-        const uint32_t d = bytes ? colb[e] : col[e];   // (a NODEP row points at its own, unselected, step: no effect)
+        const uint32_t d = ell ? ell_entry(colb, ell, W, i, e - e0) : col[e];   // (a NODEP row points at its own, unselected, step: no effect)
         if (d < S && ((sel[d >> 5] >> (d & 31u)) & 1u)) {
           atomicOr(&sel[i >> 5], 1u << (i & 31u));
           changed = true;
