@@ -248,19 +248,19 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
   uint32_t lane_ready = 0, lane_skip = 0, lane_evals = 0;  // per-lane running totals, reduced once at the end
 
   // the next group to consume: a CTA-wide ticket counter behind the four block counters (smem_p + 32)
+  const uint32_t ng_magic = (uint32_t)(0x100000000ull / NG) + 1u;   // t / NG = umulhi(t, ng_magic), exact for t < 2^32 / NG
   for (;;) {
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(reinterpret_cast<uint32_t*>(smem_p + 32), 1u);
     t = __shfl_sync(FULL, t, 0);
     if (t >= T) break;
-    const uint32_t cur_sg = t % NG, cur_use = t / NG;
+    const uint32_t cur_use = __umulhi(t, ng_magic), cur_sg = t - cur_use * NG;   // t / NG, t % NG
     load_sid(t + NG, lq == 0);   // first link of the group I shall issue into this slot group when I am done with it
     // The slot group is shared between warps: its use `cur_use` is armed by the warp that consumed the previous use.
     // A parity wait alone cannot tell "use u - 1 still pending" from "use u complete" (the parity then names the phase
     // before), so first wait until the arming warp has published use u; from then on the barrier is in phase u.
     while ((int32_t)(lds_poll_u32(armed_a + 4u * cur_sg) - (cur_use + 1u)) < 0) __nanosleep(32);
     mbar_wait(bars + 8u * cur_sg, cur_use & 1u);
-    load_ent();                  // second link (the slot id has arrived while I waited); consumed by issue() below
 #ifdef PACK_TRACE
     if (t == 0) tr_first = gtime();
 #endif
@@ -434,6 +434,9 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
     const uint32_t my_st = st0_a + g * st_stride;
     if (w == 0) sts_v4(tab_a + g * 16u, col_a, tr_a + (uint32_t)sizeof(TopoHeader), my_st, max_deg | (ell << 16));
     __syncwarp();
+    // second link of the group I shall issue (its slot id, requested when I drew my ticket, has arrived by now — asking for
+    // it right behind the barrier wait stalled every trip for a DRAM round trip); consumed by issue() at the end of the trip
+    load_ent();
     // ------------- stage D: walk the needs rows (dag.go:2711-2733) -------------
     uint32_t met_w, fd_w;
     const WalkCtx wctx{tab_a, grp_a + R * P.state_stride + (uint32_t)sizeof(TopoHeader), P.topo_buf_bytes, st0_a, st_stride};
