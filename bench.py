@@ -473,9 +473,15 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
                     (CFG_NAME[cfg], n_runs, S, ("unique topology per run" if not args.shared else "%d shared topologies" % n_topo), E),
         "value": evals_per_pass * steps / (ms * 1e-3), "ms_per_step": ms / steps, "evals_per_pass": evals_per_pass,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": g.peak, "unit": "GB/s", "frac": achieved / g.peak,
-                     "traffic": traffic, "kernel_ms": region_ms, "kernel_ms_isolated": k_ms,
+                     "traffic": traffic, "traffic_gbs": (traffic / (region_ms * 1e-3) / 1e9) if traffic else None,
+                     "traffic_frac": (traffic / (region_ms * 1e-3) / 1e9 / g.peak) if traffic else None,
+                     "kernel_ms": region_ms, "kernel_ms_isolated": k_ms,
                      "algorithmic_bytes_per_launch": abytes, "peak_source": g.peak_src,
-                     "note": "frac = algorithmic bytes / (region time / launches) / peak; kernel_ms_isolated (event-bracketed single launches, max over ranks) is reported beside it and not used"},
+                     "note": "frac = algorithmic bytes (SURVEY 8(d): canonical u16 CSR + u8 flags + codes) / (region time / launches) / peak. "
+                             "The device adjacency format (fixed-width rows with byte or 10-bit entries, no row_ptr) is SMALLER than the "
+                             "canonical figure, so frac can exceed 1: traffic = DRAM bytes ncu measured for one launch of this kernel "
+                             "(profiles/ncu_traffic.json), traffic_frac = traffic / the same time / peak = the share of the copy peak the kernel "
+                             "really draws. kernel_ms_isolated (event-bracketed single cold launches, max over ranks) is reported beside and not used"},
         "timing": {"region_ms": [float(x) for x in reg], "reps": int(len(reg)), "statistic": "median of the repetitions, each MAX over ranks",
                    "min_ms_per_step": float(np.min(reg)) / steps, "graph_unroll": U if graph is not None else 0,
                    "launches_per_pass": launches_per_pass},

@@ -509,7 +509,16 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
     ng = groups_for(nw);
     if (const char* e = getenv("BF_GROUPS")) { const uint32_t v = (uint32_t)atoi(e); if (v >= nw && v <= ng) ng = v; }
     if (ng < kMinGroups || ng < nw) pack = false;   // records too large for a useful ring: one run per warp instead
-    else pack_smem = 128u + round_up(ng * 12u, 128) + ng * group_bytes + nw * work;
+    else {
+      // a small batch gives a CTA only a few groups: no more warps and slot groups than it will use, so that the CTAs of
+      // consecutive (pipelined) passes fit an SM side by side instead of waiting for each other's shared memory
+      const uint32_t n_groups = (b.n_runs + R - 1) / R;
+      const uint32_t ctas = (uint32_t)c->sm_count < n_groups ? (uint32_t)c->sm_count : (n_groups ? n_groups : 1);
+      const uint32_t t_max = n_groups ? (n_groups + ctas - 1) / ctas : 1;
+      if (nw > t_max) nw = t_max;
+      if (ng > t_max) ng = t_max;
+      pack_smem = 128u + round_up(ng * 12u, 128) + ng * group_bytes + nw * work;
+    }
     P.work_bytes = work;
   }
   const bool two_tier = pack && c->n_with_parallel != 0;
