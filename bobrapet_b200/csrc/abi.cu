@@ -256,7 +256,9 @@ int plan_record(const bf_topology& t, RecPlan& p, std::string& why, bool host_ka
     if (ell_rows <= 256 && forced != 2 && K * ell_rows + 4 * p.W <= csr_bytes) p.ell = K | bf::ELL_BYTE;
     // 10-bit entries: topologies of more than 512 steps (never staged by the packed-lanes kernel) with rows of up to 4 needs
     else if (K == 4 && p.W > 16 && forced != 2 && 5 * ell_rows + 4 * p.W <= csr_bytes) p.ell = 4 | bf::ELL_PACK10;
-    else if (2 * K * ell_rows <= csr_bytes) p.ell = K;
+    // (no u16 rows at 8 words: their PAD index 256 has no status byte — the packed kernel keeps a run's status bytes on a
+    //  256-byte stride there; such a topology has byte entries unless BF_TOPO_FORMAT forbids them, then CSR)
+    else if (2 * K * ell_rows <= csr_bytes && ell_rows != 256) p.ell = K;
   }
   if (p.ell) {
     p.off_col = off;
@@ -499,9 +501,11 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
     if (nw < 1) nw = 1;
     if (nw > bf::frontier_pack_max_warps()) nw = bf::frontier_pack_max_warps();
     const uint32_t group_bytes = R * P.stage_bytes;
-    const uint32_t work = 128u + 1024u + 32u * R;   // fix-up words | status bytes R x (32 Wq + 16) | walk table R x 16
+    // per-warp scratch (frontier_pack.cu): status bytes R x st_stride | fix-up words | walk table R x 16, in units of 256 bytes
+    const uint32_t st_stride = wq == 8 ? 256u : 32u * wq + 16u;
+    const uint32_t work = round_up(R * st_stride + 128u + 16u * R, 256);
     auto groups_for = [&](uint32_t warps) -> uint32_t {   // slot groups that fit beside `warps` scratch areas
-      const uint32_t fixed = 128u + 768u + warps * work;      // 768: mbarriers + armed words of up to 64 groups
+      const uint32_t fixed = 128u + 768u + 256u + warps * work;   // 768: mbarriers + armed words of up to 64 groups; 256: scratch alignment
       const uint32_t n = fixed < budget ? (budget - fixed) / group_bytes : 0;
       return n > 64 ? 64 : n;
     };
@@ -517,7 +521,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
       const uint32_t t_max = n_groups ? (n_groups + ctas - 1) / ctas : 1;
       if (nw > t_max) nw = t_max;
       if (ng > t_max) ng = t_max;
-      pack_smem = 128u + round_up(ng * 12u, 128) + ng * group_bytes + nw * work;
+      pack_smem = 128u + round_up(ng * 12u, 128) + ng * group_bytes + 256u + nw * work;
     }
     P.work_bytes = work;
   }

@@ -63,21 +63,50 @@ struct WalkCtx {
 
 // K items at once (independent load chains); FMT as in kernel_common.cuh — the caller guarantees that every live run
 // of the group has this row format (else it takes walk_items_any).
-template <int K, int FMT, bool NEED_FD>
+// AL (byte-entry rows of four, 8 words per run): the status bytes of a run start on a 256-byte boundary, so the address of a
+// dependency's status byte is ONE byte permute — byte k of the row word over the low byte of the base — instead of an
+// extract and an add.  Fixed-width rows exist for every step of a word, so all 32 lanes fetch and the candidate word (the
+// same in every lane after the shuffle) masks the ballot instead of every lane's predicate.
+template <int K, int FMT, bool NEED_FD, bool AL = false>
 DI void walk_items_k(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t lg, const WalkCtx& C, uint32_t& met_w, uint32_t& fd_w) {
   const uint32_t wmask = (1u << lg) - 1u;
-  uint32_t L[K], p[K], n[K], wv[K], st[K], x[K][4];
+  uint32_t L[K], p[K], n[K], wv[K], st[K], cw[K], x[K][4];
   bool c[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     L[k] = __ffs(todo) - 1;
     todo &= todo - 1;
   }
+  if (AL && FMT == FMT_ELL4B) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      cw[k] = __shfl_sync(FULL, CAND, L[k]);
+      const uint32_t g = L[k] >> 3, i = (L[k] & 7u) * 32u + lane;
+      st[k] = C.st0 + g * 256u;
+      p[k] = C.col0 + g * C.topo_buf + i * 4u;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) n[k] = lds_u32(p[k]);   // the row: four byte entries
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      wv[k] = lds_u8(__byte_perm(n[k], st[k], 0x7650)) | lds_u8(__byte_perm(n[k], st[k], 0x7651)) |
+              lds_u8(__byte_perm(n[k], st[k], 0x7652)) | lds_u8(__byte_perm(n[k], st[k], 0x7653));
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const uint32_t m = __ballot_sync(FULL, (wv[k] & 1u) == 0) & cw[k];
+      if (lane == L[k]) met_w = m;
+      if (NEED_FD) {
+        const uint32_t f = __ballot_sync(FULL, (wv[k] & 2u) != 0) & cw[k];
+        if (lane == L[k]) fd_w = f;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const uint32_t cw = __shfl_sync(FULL, CAND, L[k]);
+    cw[k] = __shfl_sync(FULL, CAND, L[k]);
     const uint32_t g = L[k] >> lg, i = (L[k] & wmask) * 32u + lane;
-    c[k] = (cw >> lane) & 1u;
+    c[k] = (cw[k] >> lane) & 1u;
     if (fmt_traits<FMT>::fixed) {
       st[k] = C.st0 + g * C.st_stride;
       p[k] = C.col0 + g * C.topo_buf + i * fmt_traits<FMT>::row_bytes;   // rows exist for every step of the word (device_record.h)
@@ -94,24 +123,33 @@ DI void walk_items_k(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t lg, 
   for (int k = 0; k < K; ++k) wv[k] = row_status<FMT>(p[k], n[k], x[k], st[k]);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const uint32_t m = __ballot_sync(FULL, c[k] && (wv[k] & 0x01010101u) == 0);
-    if (lane == L[k]) met_w = m;
-    if (NEED_FD) {
-      const uint32_t f = __ballot_sync(FULL, c[k] && (wv[k] & 0x02020202u) != 0);
-      if (lane == L[k]) fd_w = f;
+    if (fmt_traits<FMT>::fixed) {   // every lane holds a real row: mask the ballot with the (lane-uniform) candidate word
+      const uint32_t m = __ballot_sync(FULL, (wv[k] & 0x01010101u) == 0) & cw[k];
+      if (lane == L[k]) met_w = m;
+      if (NEED_FD) {
+        const uint32_t f = __ballot_sync(FULL, (wv[k] & 0x02020202u) != 0) & cw[k];
+        if (lane == L[k]) fd_w = f;
+      }
+    } else {
+      const uint32_t m = __ballot_sync(FULL, c[k] && (wv[k] & 0x01010101u) == 0);
+      if (lane == L[k]) met_w = m;
+      if (NEED_FD) {
+        const uint32_t f = __ballot_sync(FULL, c[k] && (wv[k] & 0x02020202u) != 0);
+        if (lane == L[k]) fd_w = f;
+      }
     }
   }
 }
 
-template <int FMT, bool NEED_FD>
+template <int FMT, bool NEED_FD, bool AL = false>
 DI void walk_items(uint32_t lane, uint32_t CAND, uint32_t lg, const WalkCtx& C, uint32_t& met_w, uint32_t& fd_w) {
   met_w = 0;
   fd_w = 0;
   uint32_t todo = __ballot_sync(FULL, CAND != 0);  // (run, word) pairs with at least one candidate step
-  while (__popc(todo) >= WALK_K) walk_items_k<WALK_K, FMT, NEED_FD>(lane, CAND, todo, lg, C, met_w, fd_w);
+  while (__popc(todo) >= WALK_K) walk_items_k<WALK_K, FMT, NEED_FD, AL>(lane, CAND, todo, lg, C, met_w, fd_w);
   if (WALK_K > 2)
-    if (__popc(todo) >= 2) walk_items_k<2, FMT, NEED_FD>(lane, CAND, todo, lg, C, met_w, fd_w);
-  if (todo) walk_items_k<1, FMT, NEED_FD>(lane, CAND, todo, lg, C, met_w, fd_w);
+    if (__popc(todo) >= 2) walk_items_k<2, FMT, NEED_FD, AL>(lane, CAND, todo, lg, C, met_w, fd_w);
+  if (todo) walk_items_k<1, FMT, NEED_FD, AL>(lane, CAND, todo, lg, C, met_w, fd_w);
 }
 
 // mixed row formats inside one group (rare): one item at a time, format read from the item's table entry
@@ -162,12 +200,15 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
   const uint32_t bars_bytes = (NG * 12u + 127u) & ~127u;
   const uint32_t group_bytes = R * (P.state_stride + P.topo_buf_bytes);
   const uint32_t groups_a = pin(smem_base + 128u + bars_bytes);
-  // scratch (per warp): [fix-up fail words 128 B][status bytes: R x (32*Wq + 16)][walk table: R x 16 B]
-  const uint32_t st_stride = 32u * Wq + 16u;                       // + 16: the PAD byte of a full-width run lives here
-  const uint32_t scratch_a = groups_a + NG * group_bytes + warp * P.work_bytes;
-  const uint32_t mfail_a = scratch_a;
-  const uint32_t st0_a = scratch_a + 128u;
-  const uint32_t tab_a = st0_a + R * st_stride;
+  // scratch (per warp, 256-byte aligned, work_bytes a multiple of 256): [status bytes: R x st_stride][fix-up fail words 128 B]
+  // [walk table: R x 16 B].  st_stride = 32*Wq + 16 (the PAD byte of a full-width run with u16 rows lives in the + 16) except at
+  // Wq = 8, where it is 256 so that every run's status bytes start on a 256-byte boundary (walk_items_k, AL; no topology of
+  // 8 words has u16 fixed-width rows: plan_record, abi.cu)
+  const uint32_t st_stride = Wq == 8u ? 256u : 32u * Wq + 16u;
+  const uint32_t scratch_a = ((groups_a + NG * group_bytes + 255u) & ~255u) + warp * P.work_bytes;
+  const uint32_t st0_a = scratch_a;
+  const uint32_t mfail_a = st0_a + R * st_stride;
+  const uint32_t tab_a = mfail_a + 128u;
 
   if (threadIdx.x < 5) blk_counts[threadIdx.x] = 0ull;   // four counters + the group ticket
   if (threadIdx.x < NG) {
@@ -427,7 +468,7 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
         vx |= bits4_to_bytes(fb & 0xFu) << 1;
         vy |= bits4_to_bytes((fb >> 4) & 0xFu) << 1;
       }
-      sts_v2(st0_a + item * 8u + ((item >> (2u + lg)) << 4), vx, vy);   // run (item >> (2 + lg)) starts at st0 + run * st_stride
+      sts_v2(st0_a + item * 8u + (item >> (2u + lg)) * (st_stride - 32u * Wq), vx, vy);   // run (item >> (2 + lg)) starts at st0 + run * st_stride
     }
     // per-run walk entry: CSR / row bases, status base, longest row and row format
     const uint32_t col_a = tr_a + (h1.x & 0xFFFFu);
@@ -443,6 +484,9 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(c
     if (mixed) {
       if (any_fd) walk_items_any<true>(lane, CAND, lg, wctx, met_w, fd_w);
       else walk_items_any<false>(lane, CAND, lg, wctx, met_w, fd_w);
+    } else if (fmt0 == FMT_ELL4B && Wq == 8u) {   // 129 .. 256 steps: status bytes on 256-byte boundaries
+      if (any_fd) walk_items<FMT_ELL4B, true, true>(lane, CAND, lg, wctx, met_w, fd_w);
+      else walk_items<FMT_ELL4B, false, true>(lane, CAND, lg, wctx, met_w, fd_w);
     } else if (fmt0 == FMT_ELL4B) {
       if (any_fd) walk_items<FMT_ELL4B, true>(lane, CAND, lg, wctx, met_w, fd_w);
       else walk_items<FMT_ELL4B, false>(lane, CAND, lg, wctx, met_w, fd_w);

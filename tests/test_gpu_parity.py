@@ -191,8 +191,9 @@ def test_packed_lanes_only_context(monkeypatch, fmt):
         st = f.stats()
         assert st["last_kernel"] == 1 and st["last_runs_per_trip"] == 4, st
         _, nbytes = f.topology_record(int(slots[0]))
-        # 32 + 256 x 4 + 9 x 32 (byte entries + NODEP plane) | 32 + 256 x 8 + 256 | 32 + 528 + 2048 + 256
-        assert nbytes == {"ell": 1344, "ell16": 2336, "csr": 2864}[fmt], nbytes
+        # 32 + 256 x 4 + 9 x 32 (byte entries + NODEP plane) | 32 + 528 + 2048 + 256 (CSR: a topology of exactly 8 words never
+        # takes u16 fixed-width rows, its PAD index 256 has no status byte in the packed kernel; u16 rows: test_row_formats)
+        assert nbytes == {"ell": 1344, "ell16": 2864, "csr": 2864}[fmt], nbytes
         ts2 = synth.topologies(2, 0, 777, 64)
         s2 = f.put_topologies(ts2)
         L2 = make_layout(64, 0, A.F_ALL_OUT)
@@ -335,3 +336,53 @@ def test_pipelined_passes_counts_set(fr):
     for n, _, d_result, d_counts, want, wc in sets:
         assert np.array_equal(d_result.cpu().numpy(), want)
         assert d_counts.cpu().numpy().tolist() == [wc["ready"], wc["skip"], wc["expansion"], wc["evals"]]
+
+
+@pytest.mark.parametrize("case", ["p10-1024", "p10-mixed", "byte4-256", "byte2-256", "u16x2-800", "csr-1024"])
+def test_row_formats(case):
+    """every device row format on purpose (device_record.h): the record size says which one a topology got; then the records
+    go through both passes (single / fixpoint), the device validation (Kahn peel) and the redrive closure, all against the oracle.
+    Byte / 10-bit rows have no PAD index: short rows repeat an entry, rows without needs are flagged NODEP."""
+    from tests.test_redrive_closure import closure_packed
+    from tests import packing as P
+    smin, smax, deg, fill, par = {"p10-1024": (1024, 1024, 4, 0.9, True), "p10-mixed": (513, 1024, 3, 0.5, True),
+                                  "byte4-256": (256, 256, 4, 0.9, False), "byte2-256": (225, 256, 2, 0.8, False),
+                                  "u16x2-800": (700, 900, 2, 0.9, False), "csr-1024": (1000, 1024, 5, 0.3, True)}[case]
+    rng = np.random.default_rng({"p10-1024": 11, "p10-mixed": 12, "byte4-256": 13, "byte2-256": 14, "u16x2-800": 15, "csr-1024": 16}[case])
+    ts = randgen.random_topologies(rng, 12, smin, smax, max_deg=deg, parallel=par, fill=fill)
+    f = Frontier(0)
+    try:
+        slots = f.put_topologies(ts)
+        R_off = np.concatenate(([0], np.cumsum(ts.S.astype(np.int64) + 1)))
+        E_off = np.concatenate(([0], np.cumsum(ts.E.astype(np.int64))))
+        S_off = np.concatenate(([0], np.cumsum(ts.S.astype(np.int64))))
+        for t in range(ts.count):
+            S, Pn = int(ts.S[t]), int(ts.P[t])
+            W = (S + 31) // 32
+            rp = ts.row_ptr[R_off[t]:R_off[t] + S + 1].astype(np.int64)
+            md = int((rp[1:] - rp[:-1]).max())
+            _, nbytes = f.topology_record(int(slots[t]))
+            br = ts.parallel["branches"][int(ts.P[:t].sum()):int(ts.P[:t].sum()) + Pn].astype(np.int64) if Pn else np.zeros(0, np.int64)
+            par_bytes = 16 * Pn + 4 * int(((br + 31) // 32 + (br == 0)).sum())
+            r16 = lambda x: (x + 15) // 16 * 16  # noqa: E731
+            want = {"p10": 32 + 5 * 32 * W + r16(9 * 4 * W), "byte": 32 + (2 if md <= 2 else 4) * 32 * W + r16(9 * 4 * W),
+                    "u16": 32 + 2 * (2 if md <= 2 else 4) * 32 * W + r16(8 * 4 * W),
+                    "csr": 32 + r16(2 * (S + 1)) + r16(2 * int(ts.E[t]) + 8) + r16(8 * 4 * W)}
+            kind = case.split("-")[0].rstrip("24").replace("u16x", "u16")
+            if kind == "p10" and md <= 2:
+                kind = "u16"      # rows of at most two needs keep u16 pairs (4 bytes per row already)
+            assert nbytes == r16(want[kind] + par_bytes), (case, t, S, md, nbytes, {k: r16(v + par_bytes) for k, v in want.items()})
+        for flags in (0, A.EVAL_FIXPOINT):
+            L, state, _ = randgen.random_state(rng, ts, slots, 1500, ALL, phase_mix="progress")
+            _compare(f, ts, slots, L, state, flags=flags, expansion=par)
+        assert not (f.check_topologies(slots) & 1).any()          # the device Kahn peel reads the same rows
+        for t in range(0, ts.count, 3):
+            S = int(ts.S[t])
+            ps = P.PackedStory(["s%d" % i for i in range(S)], {}, ts.row_ptr[R_off[t]:R_off[t] + S + 1],
+                               ts.col_idx[E_off[t]:E_off[t + 1]], ts.step_flags[S_off[t]:S_off[t] + S])
+            starts = rng.integers(0, S, size=8)
+            got = f.closure([int(slots[t])] * 8, starts, 32)
+            for k, st in enumerate(starts):
+                assert np.array_equal(got[k, :(S + 31) // 32], closure_packed(ps, int(st))), (case, t, st)
+    finally:
+        f.close()
