@@ -120,6 +120,9 @@ struct bf_ctx {
   std::vector<Resident> resident;
   bf_delta* d_deltas = nullptr; size_t d_deltas_cap = 0;
   uint32_t* d_rejected = nullptr;
+  // small device scratch that its consumers leave zeroed (the compaction's tail block reads and clears the rejected-delta
+  // counter and the listed-runs total), so the steady-state tick carries no memset launches; a failed call marks it dirty
+  bool rejected_clean = false, cblock_clean = false;
 
   // cached shared-memory plan (recomputed when the layout or the largest record changes)
   uint32_t plan_key_stride = 0, plan_key_words = 0, plan_key_rec = 0, plan_key_variant = 0xFFFFFFFFu;
@@ -482,6 +485,10 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   // defers the runs whose topology has parallel steps to a device list that the general kernel then takes (second
   // launch; exits at once when the list is empty).  BF_KERNEL=general forces the general kernel (A/B timing).
   const uint32_t budget = 227u * 1024u;
+  // experiment knob (tools/build_variant.sh with -DPACK_MIN_BLOCKS=k -DPACK_MAX_WARPS=24/k): k packed-lanes CTAs per SM, each
+  // with 1/k of the shared memory
+  uint32_t pack_ctas_per_sm = 1;
+  if (const char* e = getenv("BF_PACK_CTAS")) { const uint32_t v = (uint32_t)atoi(e); if (v >= 1 && v <= 4) pack_ctas_per_sm = v; }
   const uint32_t work_general = round_up(4 * L.words, 16) + 32 * L.words + 16;  // fix-up mask words + status bytes + PAD guard
   P.topo_buf_bytes = round_up(batch_rec_bytes, 16);
   P.stage_bytes = L.state_stride + P.topo_buf_bytes;
@@ -506,7 +513,8 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
     const uint32_t work = round_up(R * st_stride + 128u + 16u * R, 256);
     auto groups_for = [&](uint32_t warps) -> uint32_t {   // slot groups that fit beside `warps` scratch areas
       const uint32_t fixed = 128u + 768u + 256u + warps * work;   // 768: mbarriers + armed words of up to 64 groups; 256: scratch alignment
-      const uint32_t n = fixed < budget ? (budget - fixed) / group_bytes : 0;
+      const uint32_t cta_budget = budget / pack_ctas_per_sm - (pack_ctas_per_sm > 1 ? 1024u : 0u);   // (the per-CTA reservation of the driver)
+      const uint32_t n = fixed < cta_budget ? (cta_budget - fixed) / group_bytes : 0;
       return n > 64 ? 64 : n;
     };
     while (nw > 1 && groups_for(nw) < nw) --nw;               // never more warps than slot groups
@@ -517,7 +525,8 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
       // a small batch gives a CTA only a few groups: no more warps and slot groups than it will use, so that the CTAs of
       // consecutive (pipelined) passes fit an SM side by side instead of waiting for each other's shared memory
       const uint32_t n_groups = (b.n_runs + R - 1) / R;
-      const uint32_t ctas = (uint32_t)c->sm_count < n_groups ? (uint32_t)c->sm_count : (n_groups ? n_groups : 1);
+      const uint32_t slots_sm = (uint32_t)c->sm_count * pack_ctas_per_sm;
+      const uint32_t ctas = slots_sm < n_groups ? slots_sm : (n_groups ? n_groups : 1);
       const uint32_t t_max = n_groups ? (n_groups + ctas - 1) / ctas : 1;
       if (nw > t_max) nw = t_max;
       if (ng > t_max) ng = t_max;
@@ -589,7 +598,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
       P.defer_list = c->d_defer + 1;
     }
     const uint32_t n_groups = (b.n_runs + R - 1) / R;
-    grid = (uint32_t)c->sm_count < n_groups ? (uint32_t)c->sm_count : (n_groups ? n_groups : 1);
+    grid = (uint32_t)c->sm_count * pack_ctas_per_sm < n_groups ? (uint32_t)c->sm_count * pack_ctas_per_sm : (n_groups ? n_groups : 1);
     smem = pack_smem;
     if (b.n_runs) {
       if (two_tier) BF_CUDA(c, cudaMemsetAsync(c->d_defer, 0, sizeof(uint32_t), stream));
@@ -690,7 +699,12 @@ int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, cons
   const uint64_t cap = out->events ? out->events_cap : 0;
   if (int rc = ensure_dev(c, c->d_head, c->d_head_cap, n_runs ? n_runs : 1)) return rc;
   if (int rc = ensure_dev(c, c->d_events, c->d_events_cap, cap ? (size_t)cap : 1)) return rc;
-  if (int rc = ensure_dev(c, c->d_cblock, c->d_cblock_cap, (size_t)(n_runs + 511) / 512 + 4)) return rc;
+  {
+    const size_t cap_before = c->d_cblock_cap;
+    if (int rc = ensure_dev(c, c->d_cblock, c->d_cblock_cap, (size_t)(n_runs + 511) / 512 + 4)) return rc;
+    if (c->d_cblock_cap != cap_before) c->cblock_clean = false;
+  }
+  if (!c->cblock_clean) { BF_CUDA(c, cudaMemsetAsync(c->d_cblock, 0, 2 * sizeof(unsigned long long), s)); c->cblock_clean = true; }
   bf::CompactParams P{};
   P.result = d_result; P.prev_result = d_prev; P.head = c->d_head; P.events = c->d_events; P.cap = cap;
   P.block_sums = c->d_cblock + 2; P.total = c->d_cblock;
@@ -702,6 +716,7 @@ int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, cons
   unsigned long long* tail = reinterpret_cast<unsigned long long*>(c->h_counts + 2);   // 7 x u64 in the pinned block
   P.host_tail = tail; P.counts = c->d_counts; P.rejected = with_rejected ? c->d_rejected : nullptr;
   if (n_runs == 0) BF_CUDA(c, cudaStreamSynchronize(s));   // the empty case stores to the pinned block from the host
+  c->cblock_clean = false;   // until the call has gone through (resident_tick_locked / eval_host set it again after the sync)
   BF_CUDA(c, bf::launch_compact(P, s));
   c->stats.kernel_launches += n_runs ? 2 : 0;
   uint64_t guess = c->last_events + c->last_events / 32 + 4096;   // the previous tick's list + 3 %: one copy in the steady state
@@ -1077,6 +1092,7 @@ static int eval_host(bf_ctx* c, const bf_batch* b, bf_compact_out* co) {
   auto body = [&]() -> int {
     BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
     bf_batch db = *b;
+    db.flags &= ~(uint32_t)(BF_EVAL_COUNTS_SET | BF_EVAL_PIPELINED);   // bf_eval_device only: the chunks here add into one block
     if (!want_exp) db.flags &= ~BF_EVAL_EXPANSION;
     const uint8_t* hs = static_cast<const uint8_t*>(b->state);
     uint8_t* hr = static_cast<uint8_t*>(b->result);
@@ -1123,7 +1139,7 @@ static int eval_host(bf_ctx* c, const bf_batch* b, bf_compact_out* co) {
   if (body_rc != BF_OK) return body_rc;
   if (e_sync != cudaSuccess) return cuda_fail(c, e_sync, "cudaStreamSynchronize");
   hc = *c->h_counts;
-  if (co) memcpy(&hc, reinterpret_cast<const unsigned long long*>(c->h_counts + 2) + 1, sizeof hc);
+  if (co) { memcpy(&hc, reinterpret_cast<const unsigned long long*>(c->h_counts + 2) + 1, sizeof hc); c->cblock_clean = true; }
   c->stats.last_eval_chunks = chunks;
   c->last_eval_valid = true; c->last_eval_runs = b->n_runs; c->last_eval_layout = L;
   c->last_state = c->d_state; c->last_result = c->d_result;
@@ -1323,10 +1339,11 @@ int bf_resident_download(bf_ctx* c, uint32_t h, uint32_t first, uint32_t n, void
 // H2D of the deltas + the scatter kernel on the ctx stream, no synchronisation; the rejected counter is read by the caller
 static int resident_apply_async(bf_ctx* c, Resident* r, const bf_delta* deltas, uint32_t n) {
   if (int rc = ensure_dev(c, c->d_deltas, c->d_deltas_cap, n ? n : 1)) return rc;
-  if (!c->d_rejected) BF_CUDA(c, cudaMalloc(&c->d_rejected, 16));
+  if (!c->d_rejected) { BF_CUDA(c, cudaMalloc(&c->d_rejected, 16)); c->rejected_clean = false; }
   cudaStream_t s = c->stream;
-  BF_CUDA(c, cudaMemsetAsync(c->d_rejected, 0, 4, s));
+  if (!c->rejected_clean) { BF_CUDA(c, cudaMemsetAsync(c->d_rejected, 0, 4, s)); c->rejected_clean = true; }
   if (n == 0) return BF_OK;
+  c->rejected_clean = false;   // the scatter kernel may count; whoever reads the counter decides whether it is clean again
   BF_CUDA(c, cudaMemcpyAsync(c->d_deltas, deltas, (size_t)n * sizeof(bf_delta), cudaMemcpyHostToDevice, s));
   bf::DeltaParams P{};
   P.state = r->d_state; P.deltas = c->d_deltas; P.n = n; P.n_runs = r->cap;
@@ -1396,10 +1413,12 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
   uint32_t* h_rej = reinterpret_cast<uint32_t*>(c->h_counts + 1);  // second pinned slot: h_counts is 2 x bf_counts
   auto body = [&]() -> int {
     if (int rc = resident_apply_async(c, r, deltas, n_deltas)) return rc;
-    BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
     bf_batch db{};
     db.struct_size = sizeof(bf_batch);
-    db.flags = flags & ~(uint32_t)BF_EVAL_VALIDATE; db.max_iterations = max_iterations; db.layout = L;
+    db.flags = flags & ~(uint32_t)(BF_EVAL_VALIDATE | BF_EVAL_COUNTS_SET | BF_EVAL_PIPELINED); db.max_iterations = max_iterations; db.layout = L;
+    // one chunk: the pass overwrites the counts block itself (no memset in front of it); several chunks add into a zeroed block
+    if (chunks == 1) db.flags |= BF_EVAL_COUNTS_SET;
+    else BF_CUDA(c, cudaMemsetAsync(c->d_counts, 0, sizeof(bf_counts), s));
     for (uint32_t k = 0; k < chunks; ++k) {
       const size_t lo = (size_t)n_runs * k / chunks, hi = (size_t)n_runs * (k + 1) / chunks;
       db.n_runs = (uint32_t)(hi - lo);
@@ -1432,6 +1451,7 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
   if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
   r->prev_valid = true; r->prev_runs = n_runs;
   if (co) {
+    c->cblock_clean = true; c->rejected_clean = true;   // the compaction's tail block delivered and cleared both
     const unsigned long long* tail = reinterpret_cast<const unsigned long long*>(c->h_counts + 2);
     memcpy(c->h_counts, tail + 1, sizeof(bf_counts));
     *h_rej = (uint32_t)tail[5];

@@ -117,6 +117,10 @@ __global__ void __launch_bounds__(CB) compact_emit(const CompactParams P) {
       P.host_tail[5] = P.rejected ? (unsigned long long)*P.rejected : 0ull;
       P.host_tail[6] = P.total[1];   // complete: every compact_heads block has finished before this kernel started
     }
+    // leave the scratch the way the next tick expects it (no memset launches in the steady state): the listed-runs total
+    // and the rejected-delta counter have been delivered
+    P.total[1] = 0ull;
+    if (P.host_tail && P.rejected) *const_cast<uint32_t*>(P.rejected) = 0u;
   }
   // A block's slice of the list is staged in shared memory and written out by consecutive threads (coalesced 64-byte
   // segments per warp instead of 2-byte scatters); a slice larger than the stage goes out directly.
@@ -143,10 +147,8 @@ __global__ void __launch_bounds__(CB) compact_emit(const CompactParams P) {
     if (base + i < P.cap) P.events[base + i] = stage[i];
 }
 
-// scratch: block_sums needs ceil(n / 512) u64; total[2] is zeroed here
+// scratch: block_sums needs ceil(n / 512) u64; total[2] is zero on entry (the caller zeroes it once, compact_emit leaves it zeroed)
 cudaError_t launch_compact(const CompactParams& P, cudaStream_t stream) {
-  cudaError_t e = cudaMemsetAsync(P.total, 0, 2 * sizeof(unsigned long long), stream);
-  if (e != cudaSuccess) return e;
   if (P.n_runs == 0) {
     if (P.host_tail) memset(P.host_tail, 0, 7 * sizeof(unsigned long long));   // pinned host memory: plain store (caller synchronised)
     return cudaSuccess;

@@ -174,7 +174,10 @@ DI void walk_items_any(uint32_t lane, uint32_t CAND, uint32_t lg, const WalkCtx&
 
 // CD: cond and/or decision codes present   XO: any of fail/needs_cond/skip_dep/phase_out requested
 template <bool CD, bool XO>
-__global__ void __launch_bounds__(32 * PACK_MAX_WARPS, 1) frontier_pack_kernel(const KParams P) {
+#ifndef PACK_MIN_BLOCKS
+#define PACK_MIN_BLOCKS 1   // resident CTAs per SM the build is compiled for (BF_PACK_CTAS experiments)
+#endif
+__global__ void __launch_bounds__(32 * PACK_MAX_WARPS, PACK_MIN_BLOCKS) frontier_pack_kernel(const KParams P) {
   // BF_EVAL_PIPELINED: let the next kernel of the stream (launched as a programmatic dependent) take the SMs this grid leaves
   // as its CTAs run out of groups; a no-op otherwise
   if (P.flags & BF_EVAL_PIPELINED) asm volatile("griddepcontrol.launch_dependents;");

@@ -195,7 +195,7 @@ DI uint32_t row_status(uint32_t p, uint32_t n, const uint32_t (&x)[4], uint32_t 
 template <int K, int FMT, bool NEED_FD>
 DI void walk_group(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t rp_addr, uint32_t col_addr, uint32_t st_addr,
                    uint32_t& met_w, uint32_t& fd_w) {
-  uint32_t j[K], p[K], n[K], w[K], x[K][4];
+  uint32_t j[K], p[K], n[K], w[K], cw[K], x[K][4];
   bool c[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -204,8 +204,8 @@ DI void walk_group(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t rp_add
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const uint32_t cw = __shfl_sync(FULL, CAND, j[k]);
-    c[k] = (cw >> lane) & 1u;
+    cw[k] = __shfl_sync(FULL, CAND, j[k]);
+    c[k] = (cw[k] >> lane) & 1u;
     row_locate<FMT>(c[k], j[k] * 32u + lane, rp_addr, col_addr, p[k], n[k]);
   }
 #pragma unroll
@@ -214,11 +214,20 @@ DI void walk_group(uint32_t lane, uint32_t CAND, uint32_t& todo, uint32_t rp_add
   for (int k = 0; k < K; ++k) w[k] = row_status<FMT>(p[k], n[k], x[k], st_addr);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const uint32_t m = __ballot_sync(FULL, c[k] && (w[k] & 0x01010101u) == 0);
-    if (lane == j[k]) met_w = m;
-    if (NEED_FD) {
-      const uint32_t f = __ballot_sync(FULL, c[k] && (w[k] & 0x02020202u) != 0);
-      if (lane == j[k]) fd_w = f;
+    if (fmt_traits<FMT>::fixed) {   // every lane holds a real row: the (lane-uniform) candidate word masks the ballot
+      const uint32_t m = __ballot_sync(FULL, (w[k] & 0x01010101u) == 0) & cw[k];
+      if (lane == j[k]) met_w = m;
+      if (NEED_FD) {
+        const uint32_t f = __ballot_sync(FULL, (w[k] & 0x02020202u) != 0) & cw[k];
+        if (lane == j[k]) fd_w = f;
+      }
+    } else {
+      const uint32_t m = __ballot_sync(FULL, c[k] && (w[k] & 0x01010101u) == 0);
+      if (lane == j[k]) met_w = m;
+      if (NEED_FD) {
+        const uint32_t f = __ballot_sync(FULL, c[k] && (w[k] & 0x02020202u) != 0);
+        if (lane == j[k]) fd_w = f;
+      }
     }
   }
 }
