@@ -355,15 +355,16 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
     # of pass k (programmatic dependent launch).  BF_BENCH_PIPELINE=0 submits plain passes (fill + kernel, fully serialised).
     pipe_flags = (A.EVAL_COUNTS_SET | A.EVAL_PIPELINED) if (os.environ.get("BF_BENCH_PIPELINE", "1") != "0" and ROT >= 2) else 0
 
-    def one_pass(s, st_, with_gather=True):
+    def one_pass(s, st_, with_gather=True, pf=None):
+        pf = pipe_flags if pf is None else pf
         Lk, d_state, d_result, d_counts, _, d_exp, exp_cap = sets[s]
-        if not pipe_flags:
+        if not pf:
             d_counts.zero_()
         if exp_cap:
             fr.eval_device(Lk, n_runs, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), st_.cuda_stream,
-                           flags=A.EVAL_EXPANSION | pipe_flags, expansion_ptr=d_exp.data_ptr(), expansion_cap=exp_cap)
+                           flags=A.EVAL_EXPANSION | pf, expansion_ptr=d_exp.data_ptr(), expansion_cap=exp_cap)
         else:
-            fr.eval_device(Lk, n_runs, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), st_.cuda_stream, flags=pipe_flags)
+            fr.eval_device(Lk, n_runs, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), st_.cuda_stream, flags=pf)
         if world > 1 and with_gather:
             # the path's one collective: all-gather of the per-shard counts, overlapped with the next pass
             exch.gather(d_counts, gathered[s], st_)
@@ -380,11 +381,11 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
     U = graph_unroll(steps, args.unroll or 64) if use_graph else 1
     seq = set_sequence(U, ROT)
 
-    def capture(with_gather):
+    def capture(with_gather, pf=None):
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=work_stream, capture_error_mode="thread_local"):
             for i in range(U):
-                one_pass(seq[i], work_stream, with_gather)
+                one_pass(seq[i], work_stream, with_gather, pf)
             if with_gather:
                 exch.join(work_stream)
         with torch.cuda.stream(work_stream):
@@ -436,6 +437,15 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
     if graph_nc is not None:
         reg_nc = timed(graph_nc, False, max(3, reps // 2))
         exposed_us = 1e3 * (ms - float(np.median(reg_nc))) / steps
+    # the same region with PLAIN passes (counter fill + kernel, every pass waits for the one before): what pipelining buys
+    plain_ms = None
+    if pipe_flags and headline and graph is not None:
+        try:
+            graph_plain = capture(True, 0)
+            plain_ms = float(np.median(timed(graph_plain, True, max(3, reps // 2)))) / steps
+            del graph_plain
+        except Exception as e:
+            sys.stderr.write("bench: plain-pass graph failed (%s)\n" % e)
     counts_host = sets[seq[-1] if graph is not None else (steps - 1) % ROT][3].cpu().numpy().tolist()
     offsets = global_offsets(gathered[seq[-1] if graph is not None else (steps - 1) % ROT], rank) if world > 1 else None
 
@@ -484,6 +494,8 @@ def run_config(g, cfg, n_runs, ROT, steps, warmup, reps, headline):
                              "really draws. kernel_ms_isolated (event-bracketed single cold launches, max over ranks) is reported beside and not used"},
         "timing": {"region_ms": [float(x) for x in reg], "reps": int(len(reg)), "statistic": "median of the repetitions, each MAX over ranks",
                    "min_ms_per_step": float(np.min(reg)) / steps, "graph_unroll": U if graph is not None else 0,
+                   "plain_ms_per_step": plain_ms, "plain_value": (evals_per_pass / (plain_ms * 1e-3)) if plain_ms else None,
+                   "plain_note": "the same graph with plain passes (a counter fill + the kernel, fully serialised) instead of pipelined ones",
                    "launches_per_pass": launches_per_pass},
         "collective": None if world == 1 else {"what": "all_gather of 4 x int64 counts per pass, side stream, inside the graph",
                                                "exposed_us": exposed_us, "kernel_ms_max_rank": k_ms},

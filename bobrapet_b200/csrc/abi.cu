@@ -95,7 +95,11 @@ struct bf_ctx {
   uint8_t* d_state = nullptr; size_t d_state_cap = 0;
   uint8_t* d_result = nullptr; size_t d_result_cap = 0;
   unsigned long long* d_counts = nullptr;
-  unsigned long long* d_acc = nullptr;   // BF_EVAL_COUNTS_SET scratch of the packed-lanes kernel (device_record.h), zero between launches
+  // BF_EVAL_COUNTS_SET scratch of the packed-lanes kernel (device_record.h): a ring of kAccSlots blocks of 8 u64, one per launch
+  // in turn (launches of different streams may overlap; a block is left zeroed by the launch that used it)
+  static constexpr uint32_t kAccSlots = 256;
+  unsigned long long* d_acc = nullptr;
+  uint32_t acc_seq = 0;
   bf_counts* h_counts = nullptr;  // pinned landing zone for the counts block (a pageable target would make the copy synchronous)
   bf_expansion* d_exp = nullptr; size_t d_exp_cap = 0;
   // compact results (bf_eval_compact / bf_resident_tick_compact)
@@ -585,7 +589,7 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   const bool counts_set = (b.flags & BF_EVAL_COUNTS_SET) && P.counts != nullptr;
   const bool counts_in_kernel = counts_set && pack && !two_tier && !want_exp && b.n_runs != 0;
   if (counts_set && !counts_in_kernel) BF_CUDA(c, cudaMemsetAsync(P.counts, 0, sizeof(bf_counts), stream));
-  P.acc = counts_in_kernel ? c->d_acc : nullptr;
+  P.acc = counts_in_kernel ? c->d_acc + 8 * (size_t)(c->acc_seq++ % bf_ctx::kAccSlots) : nullptr;
   // BF_EVAL_PIPELINED applies to a pass that is the packed-lanes kernel alone and touches the counts only behind its wait
   if (!(pack && !two_tier && !want_exp && b.n_runs != 0 && (counts_in_kernel || P.counts == nullptr))) P.flags &= ~BF_EVAL_PIPELINED;
 
@@ -846,7 +850,7 @@ int bf_create(bf_ctx** out, const bf_config* cfg) {
   c->stats.sm_count = (uint32_t)prop.multiProcessorCount;
   if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&c->d_counts, sizeof(bf_counts)) != cudaSuccess ||
-      cudaMalloc(&c->d_acc, 64) != cudaSuccess || cudaMemset(c->d_acc, 0, 64) != cudaSuccess ||
+      cudaMalloc(&c->d_acc, bf_ctx::kAccSlots * 64) != cudaSuccess || cudaMemset(c->d_acc, 0, bf_ctx::kAccSlots * 64) != cudaSuccess ||
       cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 4 * sizeof(bf_counts), cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
     bf_destroy(c);  // releases whatever was created

@@ -603,8 +603,8 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, PACK_MIN_BLOCKS) frontier
     if (P.acc == nullptr) {
       if (threadIdx.x < 4 && blk_counts[threadIdx.x] != 0ull) atomicAdd(&P.counts[threadIdx.x], blk_counts[threadIdx.x]);
     } else {
-      // BF_EVAL_COUNTS_SET: totals gathered in the ctx scratch; the last CTA out writes them to `counts` and clears the scratch
-      // for the next launch (launches that touch the scratch are ordered: stream order, or the wait above)
+      // BF_EVAL_COUNTS_SET: totals gathered in this launch's block of the ctx scratch ring; the last CTA out writes them to
+      // `counts` and clears the block for the launch that gets it next
       if (threadIdx.x < 4 && blk_counts[threadIdx.x] != 0ull) atomicAdd(&P.acc[threadIdx.x], blk_counts[threadIdx.x]);
       __threadfence();
       __syncthreads();

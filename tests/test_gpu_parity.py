@@ -386,3 +386,46 @@ def test_row_formats(case):
                 assert np.array_equal(got[k, :(S + 31) // 32], closure_packed(ps, int(st))), (case, t, st)
     finally:
         f.close()
+
+
+def test_counts_set_on_every_dispatch_shape(fr):
+    """BF_EVAL_COUNTS_SET overwrites a counts block full of garbage whatever kernels the pass takes: packed lanes alone (the last
+    CTA out publishes), packed lanes + deferred runs, the one-run-per-warp kernel, expansion lists, and an empty batch."""
+    import torch
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(99)
+    cases = []
+    f2 = Frontier(0)
+    try:
+        ts = synth.topologies(3, 0, 3000, 256)                                  # a ctx without parallel steps: packed lanes alone
+        cases.append((f2, ts, f2.put_topologies(ts), False))
+        tsp = randgen.random_topologies(rng, 40, 20, 250, max_deg=4, fill=0.8)  # fr holds parallel steps: two tiers at S <= 512
+        cases.append((fr, tsp, fr.put_topologies(tsp), True))
+        tsw = randgen.random_topologies(rng, 12, 600, 1000, max_deg=4, fill=0.8)  # S > 512: the one-run-per-warp kernel
+        cases.append((fr, tsw, fr.put_topologies(tsw), True))
+        for f, t, slots, exp in cases:
+            L, state, _ = randgen.random_state(rng, t, slots, 2500, ALL, phase_mix="progress")
+            pt = PK.PackedTopologies(t, slots)
+            want, wc = PK.evaluate(pt, L, state, threads=8)
+            d_state = torch.from_numpy(state).to(dev)
+            d_result = torch.zeros((state.shape[0], L.result_stride), dtype=torch.uint8, device=dev)
+            d_counts = torch.full((4,), 0x5A5A5A5A5A, dtype=torch.int64, device=dev)
+            cur = torch.cuda.current_stream().cuda_stream
+            for _ in range(2):
+                f.eval_device(L, state.shape[0], d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), cur, flags=A.EVAL_COUNTS_SET)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_result.cpu().numpy(), want)
+            assert d_counts.cpu().numpy().tolist() == [wc["ready"], wc["skip"], wc["expansion"], wc["evals"]], f.stats()
+            if exp and wc["expansion"]:
+                d_exp = torch.zeros((int(wc["expansion"]), 8), dtype=torch.uint8, device=dev)
+                d_counts.fill_(77)
+                f.eval_device(L, state.shape[0], d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), cur,
+                              flags=A.EVAL_COUNTS_SET | A.EVAL_EXPANSION, expansion_ptr=d_exp.data_ptr(), expansion_cap=int(wc["expansion"]))
+                torch.cuda.synchronize()
+                assert d_counts.cpu().numpy().tolist() == [wc["ready"], wc["skip"], wc["expansion"], wc["evals"]]
+            d_counts.fill_(123)
+            f.eval_device(L, 0, d_state.data_ptr(), d_result.data_ptr(), d_counts.data_ptr(), cur, flags=A.EVAL_COUNTS_SET)
+            torch.cuda.synchronize()
+            assert d_counts.cpu().numpy().tolist() == [0, 0, 0, 0]
+    finally:
+        f2.close()
