@@ -162,6 +162,9 @@ const (
 	HeadListed      = 0x8000
 	HeadCountShift  = 16
 	EvalChangedOnly = 0x10 // BF_EVAL_CHANGED_ONLY: list only the runs whose result differs from the previous tick's
+	// bf_eval_device only (a co-located GPU pipeline submitting passes over device buffers; the host-buffer calls ignore them):
+	EvalCountsSet = 0x20 // BF_EVAL_COUNTS_SET: the pass overwrites the counts block, nobody zeroes it
+	EvalPipelined = 0x40 // BF_EVAL_PIPELINED: the pass is independent of the preceding kernel of its stream and may start in its tail
 )
 
 // EvalCompact is Eval with the results as lists.
