@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, PACK_MIN_BLOCKS) frontier
   uint32_t lane_ready = 0, lane_skip = 0, lane_evals = 0;  // per-lane running totals, reduced once at the end
 
   // the next group to consume: a CTA-wide ticket counter behind the four block counters (smem_p + 32)
-  const uint32_t ng_magic = (uint32_t)(0x100000000ull / NG) + 1u;   // t / NG = umulhi(t, ng_magic), exact for t < 2^32 / NG
+  const uint32_t ng_magic = NG > 1u ? (uint32_t)(0x100000000ull / NG) + 1u : 0u;   // t / NG = umulhi(t, ng_magic), exact for t < 2^32 / NG (NG = 1: T <= 1, t = 0)
   for (;;) {
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(reinterpret_cast<uint32_t*>(smem_p + 32), 1u);
