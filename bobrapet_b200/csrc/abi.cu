@@ -719,15 +719,35 @@ int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, cons
   // itself: no latency-bound small D2H copies
   unsigned long long* tail = reinterpret_cast<unsigned long long*>(c->h_counts + 2);   // 7 x u64 in the pinned block
   P.host_tail = tail; P.counts = c->d_counts; P.rejected = with_rejected ? c->d_rejected : nullptr;
+  // a head buffer in pinned host memory (bf_alloc_pinned, cudaHostAlloc / cudaHostRegister) gets the head words posted by the
+  // kernel itself; any other buffer gets them by a download
+  P.host_head = nullptr;
+  if (out->head && n_runs && !getenv("BF_NO_ZC_HEADS")) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, out->head) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      P.host_head = static_cast<uint32_t*>(at.devicePointer);
+    else
+      cudaGetLastError();   // an unregistered host pointer is not an error here
+  }
+  bool events_posted = false;
+  if (out->events && cap && !getenv("BF_NO_ZC_EVENTS")) {   // the event list likewise: posted by the emit kernel, no download (-5 us per tick)
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, out->events) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      P.events = static_cast<uint16_t*>(at.devicePointer);
+      events_posted = true;
+    } else
+      cudaGetLastError();
+  }
   if (n_runs == 0) BF_CUDA(c, cudaStreamSynchronize(s));   // the empty case stores to the pinned block from the host
   c->cblock_clean = false;   // until the call has gone through (resident_tick_locked / eval_host set it again after the sync)
   BF_CUDA(c, bf::launch_compact(P, s));
   c->stats.kernel_launches += n_runs ? 2 : 0;
   uint64_t guess = c->last_events + c->last_events / 32 + 4096;   // the previous tick's list + 3 %: one copy in the steady state
   if (guess > cap) guess = cap;
+  if (events_posted) guess = 0;
   if (guess) BF_CUDA(c, cudaMemcpyAsync(out->events, c->d_events, (size_t)guess * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
-  if (out->head && n_runs) BF_CUDA(c, cudaMemcpyAsync(out->head, c->d_head, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
-  *first_slice = guess;
+  if (out->head && n_runs && !P.host_head) BF_CUDA(c, cudaMemcpyAsync(out->head, c->d_head, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
+  *first_slice = events_posted ? cap : guess;   // posted: the whole list is in the caller's buffer after the synchronise
   return BF_OK;
 }
 // after the stream has been synchronised: fetch what the first slice missed

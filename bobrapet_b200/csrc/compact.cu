@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(CB) compact_heads(const CompactParams P) {
         const RunWords x = load_words(P, rr, w);
         c += __popc(x.rd | x.sk | x.fl | x.nc | x.sd);
       }
-    P.head[r] = (dead ? BF_HEAD_DEAD : (summary & BF_HEAD_SUMMARY_MASK)) | (listed ? BF_HEAD_LISTED : 0u) | (c << BF_HEAD_COUNT_SHIFT);
+    const uint32_t hw = (dead ? BF_HEAD_DEAD : (summary & BF_HEAD_SUMMARY_MASK)) | (listed ? BF_HEAD_LISTED : 0u) | (c << BF_HEAD_COUNT_SHIFT);
+    P.head[r] = hw;
+    if (P.host_head) P.host_head[r] = hw;   // posted, coalesced 128-byte writes over PCIe; visible after the stream's synchronise
   }
   const uint32_t wc = __reduce_add_sync(0xffffffffu, c), wl = __reduce_add_sync(0xffffffffu, listed);
   if (lane == 0) { sh[warp] = wc; shl[warp] = wl; }
@@ -143,8 +145,16 @@ __global__ void __launch_bounds__(CB) compact_emit(const CompactParams P) {
   }
   if (!staged) return;
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < btot; i += CB)
-    if (base + i < P.cap) P.events[base + i] = stage[i];
+  // the slice goes out as 32-bit words (two events each: a warp writes 128 contiguous bytes — whole PCIe packets when the
+  // list is posted straight to the caller's pinned buffer), with a single 16-bit store at an odd start and at an odd end
+  const unsigned long long room = P.cap > base ? P.cap - base : 0ull;
+  const uint32_t n = btot < room ? btot : (uint32_t)room;          // events of my slice that fit the caller's capacity
+  const uint32_t lead = (uint32_t)(base & 1ull) < n ? (uint32_t)(base & 1ull) : n;
+  if (threadIdx.x == 0 && lead) P.events[base] = stage[0];
+  const uint32_t pairs = (n - lead) >> 1;
+  uint32_t* out32 = reinterpret_cast<uint32_t*>(P.events + base + lead);
+  for (uint32_t i = threadIdx.x; i < pairs; i += CB) out32[i] = (uint32_t)stage[lead + 2 * i] | ((uint32_t)stage[lead + 2 * i + 1] << 16);
+  if (threadIdx.x == 0 && ((n - lead) & 1u)) P.events[base + n - 1] = stage[n - 1];
 }
 
 // scratch: block_sums needs ceil(n / 512) u64; total[2] is zero on entry (the caller zeroes it once, compact_emit leaves it zeroed)

@@ -138,6 +138,8 @@ struct CompactParams {
   const uint8_t* result;
   const uint8_t* prev_result;        // previous tick's records (changed-only mode) or nullptr: every run is listed
   uint32_t* head;                    // [n_runs]
+  uint32_t* host_head;               // the caller's pinned head buffer (device-visible address) or nullptr: heads are also posted
+                                     // straight to it, no separate download
   uint16_t* events;                  // [cap]
   unsigned long long cap;
   unsigned long long* block_sums;    // scratch: ceil(n_runs / 512)
