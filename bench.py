@@ -608,9 +608,10 @@ def e2e_legs(g, live, n_runs, S, steps):
         e2e = {"value": evals_per_pass * k_e2e / dtk, "unit": UNIT, "h2d_bytes_per_step": int(k_delta * 8),
                "d2h_bytes_per_step": int(n_runs * 4 + last[0] * 2 + 56), "steps": k_e2e, "change_rate": 0.01,
                "events_per_step": int(last[0]), "runs_listed_per_step": int(last[1]),
-               "api": "bf_resident_tick_compact (host buffers, synchronous): H2D of the tick's deltas (8 B per changed code) + scatter + "
-                      "frontier kernel + on-device compaction + D2H of one head word per run and one 16-bit event per ready / skipped step "
-                      "of EVERY run"}
+               "api": "bf_resident_tick_compact (pinned host buffers, synchronous): the tick's deltas (8 B per changed code) cross PCIe as "
+                      "the scatter kernel reads them from the caller's buffer, then the frontier kernel and the on-device compaction, whose "
+                      "kernels post one head word per run and one 16-bit event per ready / skipped step of EVERY run straight into the "
+                      "caller's buffers (h2d / d2h_bytes_per_step = those bytes; no staging copies on either side)"}
         dtc2 = timed_calls(tick(A.EVAL_CHANGED_ONLY))
         legs["incremental_changed_only"] = {
             "value": evals_per_pass * k_e2e / dtc2, "unit": UNIT, "change_rate": 0.01, "h2d_bytes_per_step": int(k_delta * 8),
