@@ -105,7 +105,13 @@ struct bf_ctx {
   // compact results (bf_eval_compact / bf_resident_tick_compact)
   uint32_t* d_head = nullptr; size_t d_head_cap = 0;
   uint16_t* d_events = nullptr; size_t d_events_cap = 0;
-  unsigned long long* d_cblock = nullptr; size_t d_cblock_cap = 0;   // [0] = events, [1] = listed runs, [2..] = per-block sums
+  // [0] = events, [1] = listed runs, then TWO buffers of per-512-run event totals used in turn: a tick's emit kernel leaves the
+  // other one zeroed, so a pass that adds its runs' counts itself (fused heads, device_record.h) finds a clean buffer
+  unsigned long long* d_cblock = nullptr; size_t d_cblock_cap = 0;
+  uint32_t cblock_flip = 0;
+  // set by a compact tick around its run_pass: where a packed-lanes pass may leave head words and block totals; run_pass reports
+  // through fused_done whether it did
+  uint32_t* fuse_head = nullptr; unsigned long long* fuse_sums = nullptr; bool fused_done = false;
   uint64_t last_events = 0;                                          // events of the previous compact pass (sizes the first D2H)
   // scratch shared by both entry points
   uint32_t* d_exp_counts = nullptr; size_t d_exp_counts_cap = 0;
@@ -590,6 +596,11 @@ int run_pass(bf_ctx* c, const bf_batch& b, const uint8_t* d_state, uint8_t* d_re
   const bool counts_in_kernel = counts_set && pack && !two_tier && !want_exp && b.n_runs != 0;
   if (counts_set && !counts_in_kernel) BF_CUDA(c, cudaMemsetAsync(P.counts, 0, sizeof(bf_counts), stream));
   P.acc = counts_in_kernel ? c->d_acc + 8 * (size_t)(c->acc_seq++ % bf_ctx::kAccSlots) : nullptr;
+  c->fused_done = false;
+  if (c->fuse_head && pack && !two_tier && b.n_runs != 0) {   // a compact tick: the packed-lanes pass leaves heads + block totals itself
+    P.head = c->fuse_head; P.head_sums = c->fuse_sums;
+    c->fused_done = true;
+  }
   // BF_EVAL_PIPELINED applies to a pass that is the packed-lanes kernel alone and touches the counts only behind its wait
   if (!(pack && !two_tier && !want_exp && b.n_runs != 0 && (counts_in_kernel || P.counts == nullptr))) P.flags &= ~BF_EVAL_PIPELINED;
 
@@ -698,20 +709,32 @@ uint32_t result_tail_of(const bf_layout& L) {
   return tail;
 }
 
-int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, const uint8_t* d_prev, uint32_t n_runs, bf_compact_out* out,
-                    cudaStream_t s, uint64_t* first_slice, bool with_rejected) {
-  const uint64_t cap = out->events ? out->events_cap : 0;
+// head words + the scratch block of a compaction (zeroed once; the kernels leave it clean): before the pass, so that a fused
+// pass can write into them
+int compact_prepare(bf_ctx* c, uint32_t n_runs, cudaStream_t s) {
   if (int rc = ensure_dev(c, c->d_head, c->d_head_cap, n_runs ? n_runs : 1)) return rc;
-  if (int rc = ensure_dev(c, c->d_events, c->d_events_cap, cap ? (size_t)cap : 1)) return rc;
-  {
-    const size_t cap_before = c->d_cblock_cap;
-    if (int rc = ensure_dev(c, c->d_cblock, c->d_cblock_cap, (size_t)(n_runs + 511) / 512 + 4)) return rc;
-    if (c->d_cblock_cap != cap_before) c->cblock_clean = false;
+  const size_t cap_before = c->d_cblock_cap;
+  if (int rc = ensure_dev(c, c->d_cblock, c->d_cblock_cap, 2 * ((size_t)(n_runs + 511) / 512 + 1) + 2)) return rc;
+  if (c->d_cblock_cap != cap_before) c->cblock_clean = false;
+  if (!c->cblock_clean) {
+    BF_CUDA(c, cudaMemsetAsync(c->d_cblock, 0, c->d_cblock_cap * sizeof(unsigned long long), s));
+    c->cblock_clean = true;
   }
-  if (!c->cblock_clean) { BF_CUDA(c, cudaMemsetAsync(c->d_cblock, 0, 2 * sizeof(unsigned long long), s)); c->cblock_clean = true; }
+  return BF_OK;
+}
+static unsigned long long* cblock_sums(bf_ctx* c, uint32_t which) { return c->d_cblock + 2 + (size_t)which * ((c->d_cblock_cap - 2) / 2); }
+
+int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, const uint8_t* d_prev, uint32_t n_runs, bf_compact_out* out,
+                    cudaStream_t s, uint64_t* first_slice, bool with_rejected, bool heads_done = false) {
+  const uint64_t cap = out->events ? out->events_cap : 0;
+  if (int rc = compact_prepare(c, n_runs, s)) return rc;
+  if (int rc = ensure_dev(c, c->d_events, c->d_events_cap, cap ? (size_t)cap : 1)) return rc;
   bf::CompactParams P{};
   P.result = d_result; P.prev_result = d_prev; P.head = c->d_head; P.events = c->d_events; P.cap = cap;
-  P.block_sums = c->d_cblock + 2; P.total = c->d_cblock;
+  P.block_sums = cblock_sums(c, c->cblock_flip); P.zero_sums = cblock_sums(c, c->cblock_flip ^ 1u); P.total = c->d_cblock;
+  P.zero_len = (uint32_t)((c->d_cblock_cap - 2) / 2);
+  P.heads_done = heads_done ? 1u : 0u;
+  c->cblock_flip ^= 1u;   // the next compaction (and a pass fused with it) uses the buffer this one leaves zeroed
   P.n_runs = n_runs; P.words = L.words; P.result_stride = L.result_stride; P.result_tail = result_tail_of(L);
   P.off_ready = L.off_ready; P.off_skip = L.off_skip;
   P.off_fail = L.off_fail; P.off_needs_cond = L.off_needs_cond; P.off_skip_dep = L.off_skip_dep;
@@ -741,7 +764,7 @@ int compact_enqueue(bf_ctx* c, const bf_layout& L, const uint8_t* d_result, cons
   if (n_runs == 0) BF_CUDA(c, cudaStreamSynchronize(s));   // the empty case stores to the pinned block from the host
   c->cblock_clean = false;   // until the call has gone through (resident_tick_locked / eval_host set it again after the sync)
   BF_CUDA(c, bf::launch_compact(P, s));
-  c->stats.kernel_launches += n_runs ? 2 : 0;
+  c->stats.kernel_launches += n_runs ? (heads_done ? 1 : 2) : 0;
   uint64_t guess = c->last_events + c->last_events / 32 + 4096;   // the previous tick's list + 3 %: one copy in the steady state
   if (guess > cap) guess = cap;
   if (events_posted) guess = 0;
@@ -1449,6 +1472,11 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
   uint32_t* h_rej = reinterpret_cast<uint32_t*>(c->h_counts + 1);  // second pinned slot: h_counts is 2 x bf_counts
   auto body = [&]() -> int {
     if (int rc = resident_apply_async(c, r, deltas, n_deltas)) return rc;
+    const bool may_fuse = co && chunks == 1 && !d_prev && !changed_only && !getenv("BF_NO_FUSED_HEADS");
+    if (may_fuse) {
+      if (int rc = compact_prepare(c, n_runs, s)) return rc;
+      c->fuse_head = c->d_head; c->fuse_sums = cblock_sums(c, c->cblock_flip);
+    }
     bf_batch db{};
     db.struct_size = sizeof(bf_batch);
     db.flags = flags & ~(uint32_t)(BF_EVAL_VALIDATE | BF_EVAL_COUNTS_SET | BF_EVAL_PIPELINED); db.max_iterations = max_iterations; db.layout = L;
@@ -1458,7 +1486,9 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
     for (uint32_t k = 0; k < chunks; ++k) {
       const size_t lo = (size_t)n_runs * k / chunks, hi = (size_t)n_runs * (k + 1) / chunks;
       db.n_runs = (uint32_t)(hi - lo);
-      if (int rc = run_pass(c, db, r->d_state + lo * L.state_stride, r->d_result + lo * L.result_stride, nullptr, c->d_counts, s)) return rc;
+      const int rc_pass = run_pass(c, db, r->d_state + lo * L.state_stride, r->d_result + lo * L.result_stride, nullptr, c->d_counts, s);
+      c->fuse_head = nullptr; c->fuse_sums = nullptr;
+      if (rc_pass) return rc_pass;
       const bool piped = chunks > 1;
       if (piped) {
         BF_CUDA(c, cudaEventRecord(c->ev_k[k], s));
@@ -1469,7 +1499,7 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
                                    (hi - lo) * L.result_stride, cudaMemcpyDeviceToHost, piped ? c->s_out : s));
     }
     if (co) {   // counts and the rejected-delta counter travel with the compaction's tail block
-      if (int rc2 = compact_enqueue(c, L, r->d_result, d_prev, n_runs, co, s, &first_slice, true)) return rc2;
+      if (int rc2 = compact_enqueue(c, L, r->d_result, d_prev, n_runs, co, s, &first_slice, true, may_fuse && c->fused_done)) return rc2;
     } else {
       BF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(bf_counts), cudaMemcpyDeviceToHost, s));
       BF_CUDA(c, cudaMemcpyAsync(h_rej, c->d_rejected, 4, cudaMemcpyDeviceToHost, s));

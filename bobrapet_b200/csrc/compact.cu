@@ -88,7 +88,12 @@ __global__ void __launch_bounds__(CB) compact_emit(const CompactParams P) {
   }
   __syncthreads();
   const uint32_t r = blockIdx.x * CB + threadIdx.x;
-  const uint32_t c = r < P.n_runs ? P.head[r] >> BF_HEAD_COUNT_SHIFT : 0u;
+  const uint32_t hw = r < P.n_runs ? P.head[r] : 0u;
+  const uint32_t c = hw >> BF_HEAD_COUNT_SHIFT;
+  if (P.heads_done && P.host_head && r < P.n_runs) P.host_head[r] = hw;   // the pass left the heads on the device: post them here
+  // the next tick's pass adds into the OTHER totals buffer: leave all of it zeroed (ticks may differ in size)
+  if (P.zero_sums)
+    for (uint32_t i = blockIdx.x * CB + threadIdx.x; i < P.zero_len; i += gridDim.x * CB) P.zero_sums[i] = 0ull;
   // exclusive scan of c over the block
   uint32_t inc = c;
 #pragma unroll
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(CB) compact_emit(const CompactParams P) {
       P.host_tail[0] = base + btot;
       for (int k = 0; k < 4; ++k) P.host_tail[1 + k] = P.counts ? P.counts[k] : 0ull;
       P.host_tail[5] = P.rejected ? (unsigned long long)*P.rejected : 0ull;
-      P.host_tail[6] = P.total[1];   // complete: every compact_heads block has finished before this kernel started
+      P.host_tail[6] = P.heads_done ? (unsigned long long)P.n_runs : P.total[1];   // (total[1]: every compact_heads block has finished)
     }
     // leave the scratch the way the next tick expects it (no memset launches in the steady state): the listed-runs total
     // and the rejected-delta counter have been delivered
@@ -164,7 +169,7 @@ cudaError_t launch_compact(const CompactParams& P, cudaStream_t stream) {
     return cudaSuccess;
   }
   const uint32_t nb = (P.n_runs + CB - 1) / CB;
-  compact_heads<<<nb, CB, 0, stream>>>(P);
+  if (!P.heads_done) compact_heads<<<nb, CB, 0, stream>>>(P);
   compact_emit<<<nb, CB, 0, stream>>>(P);
   return cudaGetLastError();
 }

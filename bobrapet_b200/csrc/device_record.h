@@ -101,6 +101,10 @@ struct KParams {
   uint8_t* result;
   const Slot* slots;
   unsigned long long* counts;   // bf_counts (4 x u64) or nullptr
+  // compact ticks whose pass is the packed-lanes kernel alone: the pass itself leaves every run's head word (summary | listed |
+  // event count) and adds the counts to the per-512-run totals the emit kernel scans — no separate heads kernel
+  uint32_t* head;               // [n_runs] or nullptr
+  unsigned long long* head_sums;   // [ceil(n_runs / 512)], zero on entry
   unsigned long long* acc;      // BF_EVAL_COUNTS_SET, packed-lanes kernel alone: ctx scratch {4 totals, CTA ticket}; the last CTA
                                 // out copies the totals to `counts` and clears the scratch (nullptr: add to `counts`)
   uint32_t* exp_counts;         // [n_runs] compact per-run expansion counts or nullptr
@@ -143,6 +147,9 @@ struct CompactParams {
   uint16_t* events;                  // [cap]
   unsigned long long cap;
   unsigned long long* block_sums;    // scratch: ceil(n_runs / 512)
+  unsigned long long* zero_sums;     // the OTHER totals buffer: the emit kernel leaves it zeroed for the next tick's pass to add into
+  uint32_t zero_len;                 // entries of zero_sums
+  uint32_t heads_done;               // the pass wrote head words and block totals itself (every run listed): no compact_heads
   unsigned long long* total;         // out: [0] events of the batch, [1] listed runs
   // the pass's small results, written straight to pinned host memory by the last block (no separate small D2H copies):
   // host_tail[0] = events, [1..4] = bf_counts, [5] = rejected deltas, [6] = listed runs

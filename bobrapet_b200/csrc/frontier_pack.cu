@@ -549,6 +549,17 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, PACK_MIN_BLOCKS) frontier
     const uint32_t cnt = __reduce_add_sync(gmask, (uint32_t)__popc(acc_ready) | ((uint32_t)__popc(acc_skip) << 16));
     bool changed = marked;
     if (CD) changed = (__ballot_sync(FULL, ((p0 ^ q0) | (p1 ^ q1) | (p2 ^ q2) | (p3 ^ q3)) != 0) & gmask) != 0;
+    // fused compaction head (compact.cu): events of the run = steps with a bit in any result mask the layout carries
+    uint32_t n_events = 0;
+    if (P.head) {
+      uint32_t u = acc_ready | acc_skip;
+      if (XO) {
+        if (P.off_fail != BF_OFF_NONE) u |= fail_w;
+        if (P.off_needs_cond != BF_OFF_NONE) u |= realtime ? 0u : (met_w & HASIF);
+        if (P.off_skip_dep != BF_OFF_NONE) u |= fd_w;
+      }
+      n_events = __reduce_add_sync(gmask, (uint32_t)__popc(u));
+    }
     if (deferred) {
       if (w == 0) P.defer_list[atomicAdd(P.defer_count, 1u)] = r;  // the general kernel writes this run's record
     } else if (in_batch) {
@@ -556,6 +567,10 @@ __global__ void __launch_bounds__(32 * PACK_MAX_WARPS, PACK_MIN_BLOCKS) frontier
         summary = live ? (summary | (changed ? BF_SUM_PHASE_CHANGED : 0u) | (1u << BF_SUM_ITER_SHIFT)) : 0xFFFFFFFFu;
         *reinterpret_cast<uint4*>(rr) = make_uint4(summary, cnt & 0xFFFFu, cnt >> 16, 0u);
         if (P.exp_counts) P.exp_counts[r] = 0;
+        if (P.head) {
+          P.head[r] = live ? ((summary & BF_HEAD_SUMMARY_MASK) | BF_HEAD_LISTED | (n_events << BF_HEAD_COUNT_SHIFT)) : (BF_HEAD_DEAD | BF_HEAD_LISTED);
+          if (live && n_events) atomicAdd(&P.head_sums[r >> 9], (unsigned long long)n_events);
+        }
       }
       if (w < Wmax) {
         reinterpret_cast<uint32_t*>(rr + P.off_ready)[w] = acc_ready;
