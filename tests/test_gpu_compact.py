@@ -139,3 +139,61 @@ def test_resident_tick_compact_and_changed_only(fr):
         assert n_listed == n
     finally:
         fr.resident_destroy(h)
+
+
+def test_fused_heads_ticks_of_different_sizes():
+    """On a ctx without parallel steps a compact tick's pass is the packed-lanes kernel alone and leaves the head words and the
+    per-512-run event totals itself (no heads kernel; two totals buffers used in turn, each left zeroed by the other tick's emit
+    kernel).  Ticks of very different sizes, changed-only ticks (which keep the heads kernel) and dead slots in between must not
+    leave anything behind in either buffer."""
+    f = Frontier(0)
+    try:
+        rng = np.random.default_rng(77)
+        batches = []
+        for n, S, fields in ((40000, 256, 0), (700, 256, ALL), (9000, 64, A.F_ALL_OUT)):
+            ts = synth.topologies(4 if fields == ALL else 3, n, n, S)
+            slots = f.put_topologies(ts)
+            L = make_layout(S, 0, fields)
+            state = synth.state(4 if fields == ALL else 3, n, n, L, slots, ts)
+            live5 = state[5, 0:4].copy()
+            if n == 700:
+                state[5, 0:4] = np.frombuffer(np.uint32(0x7FFFFFF0).tobytes(), np.uint8)   # a dead topology slot
+            h = f.resident_create(L, n)
+            f.resident_upload(h, 0, state)
+            batches.append((n, S, L, PK.PackedTopologies(ts, slots), h, None, live5))
+        order = [0, 1, 0, 2, 1, 1, 0, 2, 2, 0]
+        for step, b in enumerate(order):
+            n, S, L, pt, h, prev, live5 = batches[b]
+            k = int(rng.integers(0, 300))
+            flat = rng.choice(n * S, size=k, replace=False)
+            d = np.zeros(k, dtype=f.DELTA_DTYPE)
+            d["run"], d["index"], d["field"] = flat // S, flat % S, A.DELTA_PHASE
+            d["code"] = rng.choice([0, 2, 3, 3, 4, 13], size=k)
+            if b == 1:
+                d = d[d["run"] != 5]
+            changed_only = step % 3 == 2 and prev is not None
+            p_head = f.alloc_pinned(n * 4).view(np.uint32)
+            p_ev = f.alloc_pinned(400000 * 2).view(np.uint16)
+            try:
+                head, events, n_events, counts, n_listed = f.resident_tick_compact(
+                    h, n, d, 400000, flags=(A.EVAL_CHANGED_ONLY if changed_only else 0), head=p_head, events=p_ev)
+                cur = f.resident_download(h, 0, n, L.state_stride)
+                if b == 1:
+                    cur[5, 0:4] = live5      # the oracle takes live slots only; the dead run's record is patched below
+                want, wcounts = PK.evaluate(pt, L, cur, 0, 0, threads=8)
+                if b == 1:   # the dead run: marked, empty, not counted (as in test_compact_capacity_smaller_than_the_list_and_dead_slot)
+                    hdr = want[5, 0:16].view("<u4")
+                    wcounts = dict(wcounts, ready=wcounts["ready"] - int(hdr[1]), skip=wcounts["skip"] - int(hdr[2]), evals=wcounts["evals"] - S)
+                    want[5, :] = 0
+                    want[5, 0:4] = 0xFF
+                whead, wev, wlisted = PK.compact_events(L, want, prev if changed_only else None)
+                assert counts == wcounts and n_events == len(wev) and n_listed == wlisted, (step, b, n_events, len(wev), n_listed, wlisted)
+                assert np.array_equal(head, whead) and np.array_equal(events, wev), (step, b)
+                st = f.stats()
+                assert st["last_kernel"] == 1, st
+            finally:
+                f.free_pinned(p_head.view(np.uint8))
+                f.free_pinned(p_ev.view(np.uint8))
+            batches[b] = (n, S, L, pt, h, want, live5)
+    finally:
+        f.close()
