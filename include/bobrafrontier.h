@@ -490,8 +490,11 @@ typedef struct bf_compact_out {
 /* bf_eval with compact results: H2D(state) -> kernels -> D2H(heads + events).  batch->result is ignored
  * (may be NULL).  Host buffers, synchronous.                                                                     */
 int bf_eval_compact(bf_ctx* ctx, const bf_batch* batch, bf_compact_out* out);
-/* bf_resident_tick with compact results: H2D(deltas) -> scatter -> pass -> D2H(heads + events).  This is the
- * steady-state tick of the operator: both directions are proportional to what changed.                           */
+/* bf_resident_tick with compact results: deltas -> scatter -> pass -> heads + events.  This is the steady-state
+ * tick of the operator: both directions are proportional to what changed.  Buffers in PINNED host memory
+ * (bf_alloc_pinned, cudaHostAlloc, cudaHostRegister) are used in place: the scatter kernel reads the deltas from
+ * them and the compaction kernel posts head words and events into them, with no staging copy on either side;
+ * any other buffer goes through the upload / download copies.  Either way the call returns when they are filled. */
 int bf_resident_tick_compact(bf_ctx* ctx, uint32_t handle, const bf_delta* deltas, uint32_t n_deltas, uint32_t n_runs,
                              uint32_t flags, uint32_t max_iterations, bf_compact_out* out, bf_counts* counts);
 
