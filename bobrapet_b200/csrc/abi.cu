@@ -1183,6 +1183,7 @@ static int eval_host(bf_ctx* c, const bf_batch* b, bf_compact_out* co) {
     const cudaError_t e1 = cudaStreamSynchronize(c->s_in), e2 = cudaStreamSynchronize(c->s_out);
     if (e_sync == cudaSuccess) e_sync = e1 != cudaSuccess ? e1 : e2;
   }
+  if (body_rc != BF_OK || e_sync != cudaSuccess) c->cblock_clean = false;   // (the compaction scratch may hold a partial pass)
   if (body_rc != BF_OK) return body_rc;
   if (e_sync != cudaSuccess) return cuda_fail(c, e_sync, "cudaStreamSynchronize");
   hc = *c->h_counts;
@@ -1513,6 +1514,10 @@ static int resident_tick_locked(bf_ctx* c, Resident* r, const bf_delta* deltas, 
     if (es == cudaSuccess) es = e2;
   }
   r->prev_valid = false;
+  if (rc != BF_OK || es != cudaSuccess) {   // whatever the kernels left in the self-cleaning scratch is unknown: zero it before the next use
+    c->cblock_clean = false; c->rejected_clean = false;
+    c->fuse_head = nullptr; c->fuse_sums = nullptr;
+  }
   if (rc != BF_OK) return rc;
   if (es != cudaSuccess) return cuda_fail(c, es, "cudaStreamSynchronize");
   r->prev_valid = true; r->prev_runs = n_runs;
