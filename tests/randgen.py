@@ -10,7 +10,8 @@ from oracle.packed import child_first_of
 
 
 def random_topologies(rng: np.random.Generator, count: int, s_min: int, s_max: int, max_deg: int = 5,
-                      groups: bool = True, parallel: bool = True, forward_refs: bool = True, fill: float = 0.0) -> TopologySet:
+                      groups: bool = True, parallel: bool = True, forward_refs: bool = True, fill: float = 0.0,
+                      branch_choices=(0, 1, 2, 3, 7, 8, 9, 31, 32, 33, 40)) -> TopologySet:
     """fill: probability that a step takes the full max_deg needs (dense low-degree graphs qualify for the
     fixed-width row format of the device records; sparse ones stay CSR)"""
     S_l, E_l, P_l, rp_l, ci_l, fl_l, par_l, allow_bits = [], [], [], [], [], [], [], []
@@ -52,7 +53,7 @@ def random_topologies(rng: np.random.Generator, count: int, s_min: int, s_max: i
         fl[extra] &= ~np.uint8(A.SF_TYPE_MASK)
         pd = np.zeros(len(par_idx), PAR_DTYPE)
         for q, stp in enumerate(par_idx):
-            B = int(rng.choice([0, 1, 2, 3, 7, 8, 9, 31, 32, 33, 40]))
+            B = int(rng.choice(list(branch_choices)))
             pd[q] = (stp, B, len(allow_bits))
             allow_bits.extend((rng.random(B) < 0.3).tolist())
         S_l.append(S); E_l.append(int(rp[-1])); P_l.append(len(par_idx))

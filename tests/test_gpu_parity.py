@@ -429,3 +429,18 @@ def test_counts_set_on_every_dispatch_shape(fr):
             assert d_counts.cpu().numpy().tolist() == [0, 0, 0, 0]
     finally:
         f2.close()
+
+
+@pytest.mark.parametrize("mode", ["single", "fixpoint"])
+def test_parallel_steps_with_hundreds_of_branches(mode):
+    """stage H classifies eight child nibbles per lane, a sub-warp per descriptor; a step with more than 256 branches does not
+    fit a warp's 32 lanes x 8 children and takes the one-child-per-lane path.  Both, mixed in one batch, join + expansion."""
+    rng = np.random.default_rng(2024)
+    ts = randgen.random_topologies(rng, 30, 20, 60, max_deg=3, fill=0.5, branch_choices=(0, 5, 64, 128, 129, 255, 256, 257, 300, 600))
+    f = Frontier(0)
+    try:
+        slots = f.put_topologies(ts)
+        L, state, _ = randgen.random_state(rng, ts, slots, 1200, ALL, phase_mix="progress")
+        _compare(f, ts, slots, L, state, flags=(A.EVAL_FIXPOINT if mode == "fixpoint" else 0), expansion=True)
+    finally:
+        f.close()
