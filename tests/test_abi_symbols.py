@@ -51,3 +51,18 @@ def test_python_layout_rule_matches_bf_layout_init():
                                               (0, A.F_COND, A.F_DECISION | A.F_CHILD, A.F_COND | A.F_DECISION | A.F_CHILD | A.F_ALL_OUT,
                                                A.F_OUT_FAIL | A.F_OUT_PHASE, A.F_CHILD | A.F_OUT_SKIP_DEP | A.F_OUT_NEEDS_COND)):
         assert layout_py(S, child, fields).as_dict() == make_layout(S, child, fields).as_dict(), (S, child, fields)
+
+
+def test_eval_flag_constants_match_the_header_and_the_go_binding():
+    """the BF_EVAL_* bits of include/bobrafrontier.h == bobrapet_b200/_abi.py == go/frontier/frontier.go, and they are distinct"""
+    text = open(os.path.join(ROOT, "include", "bobrafrontier.h")).read()
+    hdr = {n: int(v, 16) for n, v in re.findall(r"#define (BF_EVAL_[A-Z_]+) (0x[0-9a-fA-F]+)u", text)}
+    want = {"BF_EVAL_VALIDATE": A.EVAL_VALIDATE, "BF_EVAL_FIXPOINT": A.EVAL_FIXPOINT, "BF_EVAL_EXPANSION": A.EVAL_EXPANSION,
+            "BF_EVAL_NO_COUNTS": A.EVAL_NO_COUNTS, "BF_EVAL_CHANGED_ONLY": A.EVAL_CHANGED_ONLY, "BF_EVAL_COUNTS_SET": A.EVAL_COUNTS_SET,
+            "BF_EVAL_PIPELINED": A.EVAL_PIPELINED}
+    assert hdr == want
+    assert len(set(hdr.values())) == len(hdr) and all(v < 0x10000 and v & (v - 1) == 0 for v in hdr.values())   # public bits, one each
+    go = open(os.path.join(ROOT, "go", "frontier", "frontier.go")).read()
+    for name, go_name in (("BF_EVAL_CHANGED_ONLY", "EvalChangedOnly"), ("BF_EVAL_COUNTS_SET", "EvalCountsSet"), ("BF_EVAL_PIPELINED", "EvalPipelined")):
+        m = re.search(r"\b%s\s*=\s*(0x[0-9a-fA-F]+)" % go_name, go)
+        assert m and int(m.group(1), 16) == hdr[name], go_name
