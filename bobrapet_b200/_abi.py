@@ -167,6 +167,7 @@ SYMBOLS = [
     ("bf_free_pinned", C.c_int, [C.c_void_p, C.c_void_p]),
     ("bf_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     ("bf_topology_record", C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    ("bf_topology_record_build", C.c_int, [C.POINTER(Topology), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
 ]
 
 _lib = None

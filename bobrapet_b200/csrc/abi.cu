@@ -1044,6 +1044,17 @@ int bf_topology_record(const bf_ctx* c, uint32_t slot, uint64_t* dev_addr, uint3
   return BF_OK;
 }
 
+int bf_topology_record_build(const bf_topology* topo, void* out, uint32_t cap, uint32_t* bytes_out) {
+  if (!topo) return BF_EINVAL;
+  RecPlan p;
+  std::string why;
+  if (int rc = plan_record(*topo, p, why, true, forced_format())) return rc;
+  if (bytes_out) *bytes_out = p.rec_bytes;
+  if (!out || cap < p.rec_bytes) return BF_ENOMEM;
+  build_record(*topo, p, static_cast<uint8_t*>(out));
+  return BF_OK;
+}
+
 int bf_layout_init(bf_layout* out, uint32_t steps_max, uint32_t child_nibbles, uint32_t fields) {
   if (!out || steps_max == 0 || steps_max > BF_MAX_STEPS) return BF_EINVAL;
   bf_layout L{};

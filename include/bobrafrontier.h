@@ -553,6 +553,10 @@ typedef struct bf_stats {
 int bf_get_stats(const bf_ctx* ctx, bf_stats* out);
 /* Device address + byte size of a topology record (for traffic accounting).   */
 int bf_topology_record(const bf_ctx* ctx, uint32_t slot, uint64_t* dev_addr, uint32_t* bytes);
+/* Host-only (no ctx, no GPU): validates `topo` exactly as bf_topology_put does and writes the device record it would upload
+ * (the row format chosen for it, device_record.h) into out[cap]; *bytes_out = the record's size, also when cap is too
+ * small (then nothing is written and BF_ENOMEM is returned).  For tests and for sizing an arena.                          */
+int bf_topology_record_build(const bf_topology* topo, void* out, uint32_t cap, uint32_t* bytes_out);
 
 #ifdef __cplusplus
 }
